@@ -1,0 +1,173 @@
+// api_core.cu -- error plumbing, device probing and the distance entry points of the C ABI.
+#include <string.h>
+
+#include <new>
+
+#include "api_common.h"
+#include "hamming.cuh"
+
+namespace gsb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no usable CUDA device (%s); libgsearch_b200 has no CPU path",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return GSB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device ordinal %d out of range (0..%d)", device, n - 1);
+        return GSB_ERR_INVALID_ARG;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+        return GSB_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                  prop.minor);
+        return GSB_ERR_NO_DEVICE;
+    }
+    return GSB_OK;
+}
+
+static uint32_t elem_of(uint32_t sig_type) {
+    switch (sig_type) {
+    case GSB_SIG_U64: return 8;
+    case GSB_SIG_U16: return 2;
+    case GSB_SIG_U32:
+    case GSB_SIG_F32: return 4;
+    default: return 0;
+    }
+}
+
+template <int ELEM, bool F32>
+static int launch_hamming(const uint8_t *q, uint32_t nq, const uint8_t *c, uint32_t n, uint32_t S, float *out,
+                          cudaStream_t st) {
+    const size_t row = (size_t)S * ELEM;
+    const size_t smem = (row + 127) & ~(size_t)127;
+    if (smem > 200 * 1024) {
+        set_error("signature row of %zu bytes does not fit the shared-memory staging buffer", row);
+        return GSB_ERR_UNSUPPORTED;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(k6_hamming_matrix<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+        attr_set = true;
+    }
+    // enough CTAs per query to fill the machine, but at least one candidate per warp
+    uint32_t per = 8;
+    while ((uint64_t)nq * ((n + per - 1) / per) > 148ull * 16 && per < 4096) per *= 2;
+    dim3 grid((n + per - 1) / per, nq);
+    k6_hamming_matrix<ELEM, F32><<<grid, kHamThreads, smem, st>>>(q, nq, c, n, S, per, out);
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB_OK;
+}
+
+int hamming_matrix_dev(const void *dq, uint32_t nq, const void *dc, uint32_t n, uint32_t S, uint32_t sig_type,
+                       float *dout, cudaStream_t st) {
+    if (nq == 0 || n == 0) return GSB_OK;
+    if (S == 0) {
+        set_error("S must be > 0");
+        return GSB_ERR_INVALID_ARG;
+    }
+    const uint8_t *q = (const uint8_t *)dq, *c = (const uint8_t *)dc;
+    switch (sig_type) {
+    case GSB_SIG_U64: return launch_hamming<8, false>(q, nq, c, n, S, dout, st);
+    case GSB_SIG_U32: return launch_hamming<4, false>(q, nq, c, n, S, dout, st);
+    case GSB_SIG_F32: return launch_hamming<4, true>(q, nq, c, n, S, dout, st);
+    case GSB_SIG_U16: return launch_hamming<2, false>(q, nq, c, n, S, dout, st);
+    default: set_error("unknown sig_type %u", sig_type); return GSB_ERR_INVALID_ARG;
+    }
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" const char *gsb_last_error(void) { return g_err; }
+extern "C" const char *gsb_version(void) { return "gsearch_b200 0.1.0 (sm_100a)"; }
+extern "C" int gsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int gsb_hamming_matrix_dev(const void *d_queries, uint32_t nq, const void *d_cands, uint32_t n,
+                                      uint32_t S, uint32_t sig_type, float *d_out, void *stream) {
+    if ((nq && !d_queries) || (n && !d_cands) || (nq && n && !d_out)) {
+        set_error("gsb_hamming_matrix_dev: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    return hamming_matrix_dev(d_queries, nq, d_cands, n, S, sig_type, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int gsb_hamming_matrix(const void *queries, uint32_t nq, const void *cands, uint32_t n, uint32_t S,
+                                  uint32_t sig_type, float *out, int device) {
+    if ((nq && !queries) || (n && !cands) || (nq && n && !out)) {
+        set_error("gsb_hamming_matrix: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    const uint32_t es = elem_of(sig_type);
+    if (!es) {
+        set_error("unknown sig_type %u", sig_type);
+        return GSB_ERR_INVALID_ARG;
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (nq == 0 || n == 0) return GSB_OK;
+    GSB_CUDA_TRY(cudaSetDevice(device));
+    const size_t row = (size_t)S * es;
+    void *dq = nullptr, *dc = nullptr;
+    float *dout = nullptr;
+    cudaStream_t st = nullptr;
+    GSB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaError_t e1 = cudaMalloc(&dq, row * nq), e2 = cudaMalloc(&dc, row * n),
+                e3 = cudaMalloc((void **)&dout, sizeof(float) * (size_t)nq * n);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaFree(dq);
+        cudaFree(dc);
+        cudaFree(dout);
+        cudaStreamDestroy(st);
+        set_error("cudaMalloc failed in gsb_hamming_matrix");
+        return GSB_ERR_OOM;
+    }
+    rc = GSB_OK;
+    cudaError_t e = cudaMemcpyAsync(dq, queries, row * nq, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dc, cands, row * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = hamming_matrix_dev(dq, nq, dc, n, S, sig_type, dout, st);
+    if (e == cudaSuccess && rc == GSB_OK)
+        e = cudaMemcpyAsync(out, dout, sizeof(float) * (size_t)nq * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dq);
+    cudaFree(dc);
+    cudaFree(dout);
+    cudaStreamDestroy(st);
+    if (e != cudaSuccess) {
+        set_error("CUDA failure in gsb_hamming_matrix: %s", cudaGetErrorString(e));
+        return GSB_ERR_CUDA;
+    }
+    return rc;
+}
+
+extern "C" int gsb_hamming_batch(const void *q, const void *cands, uint32_t n, uint32_t S, uint32_t sig_type,
+                                 float *out, int device) {
+    return gsb_hamming_matrix(q, 1, cands, n, S, sig_type, out, device);
+}

@@ -1,0 +1,537 @@
+// api_sketch.cu -- C-ABI of the sketcher (gsb_sketcher_*, gsb_sketch_fasta_batch*).
+//
+// Host-side orchestration only: sizes grids, owns device workspaces, launches the K1/K2/K3
+// kernels of fasta_pack.cuh / sketch_kernels.cuh on the caller's stream and handles the
+// (rare) early-stop-bound retries.  No arithmetic of the path runs on the CPU.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "api_common.h"
+#include "sketch_kernels.cuh"
+
+using namespace gsb;
+
+namespace {
+
+constexpr int kSlots = 4;  // genomes in flight on the prob path (hash sets sized for L2)
+
+struct ProbSlot {
+    DevBuf table, cnt, list, misc, hmin, sigw;
+    size_t cnt_dirty = 0;
+};
+
+__global__ void k_fill_u32(uint32_t *p, size_t n, uint32_t v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// per group: clear the hash sets, reset cursors and slot state, compute the bounds
+__global__ void __launch_bounds__(256)
+k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult *__restrict__ res,
+             SketchConsts sc, ProbBound *__restrict__ bound, uint32_t *__restrict__ overflow) {
+    const uint32_t j = blockIdx.y;
+    if (j >= njobs) return;
+    const ProbJob job = jobs[j];
+    uint4 *t4 = reinterpret_cast<uint4 *>(job.table);
+    const size_t n4 = ((size_t)job.cap + 3) / 4;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        t4[i] = z;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < sc.m; k += gridDim.x * blockDim.x) {
+        job.hmin[k] = 0x7FEFFFFFFFFFFFFFull;  // f64::MAX
+        job.sigw[k] = ~0ull;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *job.list_n = 0;
+        overflow[j] = 0;
+        const uint32_t N = res[job.file].nsym;
+        const uint32_t nk = N >= sc.k ? N - sc.k + 1 : 0;
+        ProbBound b;
+        if (nk == 0) {
+            b.T = 0.0;
+            b.uT = 0;
+        } else {
+            b.T = job.tmult * ((double)sc.m / (double)nk) * sc.lnm8;
+            b.uT = b.T >= 1.0 ? (1ull << 52) : (uint64_t)(b.T * 4503599627370496.0) + 2;
+        }
+        bound[j] = b;
+    }
+}
+
+__global__ void k_dens_reset(uint32_t *bins, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bins[i] = kDensLargeBits;
+}
+
+}  // namespace
+
+struct gsb_sketcher {
+    gsb_sketch_params p;
+    int device = 0;
+    int sig_type = 0;
+    uint32_t elem = 4;
+    bool kt32 = false;
+    SketchConsts sc;
+    cudaStream_t stream = nullptr;
+    DevBuf d_files, d_tile_prefix, d_tc4, d_ttrans, d_tnrec, d_tstate, d_tbase, d_trecbase, d_res,
+        d_packed, d_bounds, d_misc, d_retry, d_jobs, d_chunk_prefix, d_bound, d_overflow, d_bins;
+    PinBuf h_files, h_tile_prefix, h_jobs, h_chunk_prefix, h_retry, h_overflow;
+    ProbSlot slot[kSlots];
+    DevBuf d_bytes, d_sig, d_nb;
+    uint64_t launches = 0, retries = 0;
+};
+
+static int sig_type_of(const gsb_sketch_params &p) {
+    if (p.algo == GSB_ALGO_PROB3A) {
+        if (p.data_t == GSB_DATA_DNA) return (p.kmer_size <= 14 || p.kmer_size == 16) ? GSB_SIG_U32 : GSB_SIG_U64;
+        return p.kmer_size <= 6 ? GSB_SIG_U32 : GSB_SIG_U64;
+    }
+    return GSB_SIG_F32;
+}
+
+extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, gsb_sketcher **out) {
+    if (!params || !out) {
+        set_error("gsb_sketcher_create: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    const gsb_sketch_params &p = *params;
+    if (p.data_t != GSB_DATA_DNA && p.data_t != GSB_DATA_AA) {
+        set_error("data_t must be DNA(0) or AA(1)");
+        return GSB_ERR_INVALID_ARG;
+    }
+    const uint32_t kmax = p.data_t == GSB_DATA_DNA ? 31u : 12u;
+    if (p.kmer_size < 1 || p.kmer_size > kmax) {
+        set_error("kmer_size %u out of range 1..%u (k=32 overflows the reference's mask, "
+                  "src/dna/dnasketch.rs:166)", p.kmer_size, kmax);
+        return GSB_ERR_INVALID_ARG;
+    }
+    if (p.sketch_size < 2 || p.sketch_size > 65535) {
+        set_error("sketch_size %u out of range 2..65535", p.sketch_size);
+        return GSB_ERR_INVALID_ARG;
+    }
+    if (p.algo != GSB_ALGO_PROB3A && p.algo != GSB_ALGO_OPTDENS) {
+        set_error("algo %u is not built on the device path yet (prob, optdens are)", p.algo);
+        return p.algo <= GSB_ALGO_HLL ? GSB_ERR_UNSUPPORTED : GSB_ERR_INVALID_ARG;
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    gsb_sketcher *h = new (std::nothrow) gsb_sketcher();
+    if (!h) return GSB_ERR_OOM;
+    h->p = p;
+    h->device = device;
+    h->sig_type = sig_type_of(p);
+    h->elem = h->sig_type == GSB_SIG_U64 ? 8 : 4;
+    h->kt32 = p.data_t == GSB_DATA_DNA ? (p.kmer_size <= 14 || p.kmer_size == 16) : (p.kmer_size <= 6);
+    SketchConsts &sc = h->sc;
+    sc.k = p.kmer_size;
+    sc.m = p.sketch_size;
+    const uint64_t m = sc.m;
+    sc.zone = UINT64_MAX - ((UINT64_MAX - m + 1) % m);
+    sc.lnm8 = log((double)m) + 8.0;
+    const double lambda = log((double)m / (double)(m - 1));
+    sc.e01.lambda = lambda;
+    sc.e01.c1 = expm1(lambda) / lambda;
+    sc.e01.c2 = log(2.0 / (1.0 + exp(-lambda))) / lambda;
+    sc.e01.c3 = (1.0 - exp(-lambda)) / lambda;
+    // c1*u >= 1 needs u >= 1/c1; anything from a little below that goes to the exact path
+    sc.u_slow = (uint64_t)(4503599627370496.0 / sc.e01.c1) - 8;
+    sc.spec_flags = p.spec_flags;
+    cudaSetDevice(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        delete h;
+        return GSB_ERR_CUDA;
+    }
+    *out = h;
+    return GSB_OK;
+}
+
+extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    DevBuf *bufs[] = {&h->d_files, &h->d_tile_prefix, &h->d_tc4, &h->d_ttrans, &h->d_tnrec, &h->d_tstate,
+                      &h->d_tbase, &h->d_trecbase, &h->d_res, &h->d_packed, &h->d_bounds, &h->d_misc,
+                      &h->d_retry, &h->d_jobs, &h->d_chunk_prefix, &h->d_bound, &h->d_overflow, &h->d_bins,
+                      &h->d_bytes, &h->d_sig, &h->d_nb};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &s : h->slot) {
+        s.table.release();
+        s.cnt.release();
+        s.list.release();
+        s.misc.release();
+        s.hmin.release();
+        s.sigw.release();
+    }
+    PinBuf *pb[] = {&h->h_files, &h->h_tile_prefix, &h->h_jobs, &h->h_chunk_prefix, &h->h_retry, &h->h_overflow};
+    for (PinBuf *b : pb) b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int gsb_sketcher_sig_type(const gsb_sketcher *h) { return h ? h->sig_type : -1; }
+extern "C" uint32_t gsb_sketcher_elem_size(const gsb_sketcher *h) { return h ? h->elem : 0; }
+extern "C" uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h) { return h ? h->launches : 0; }
+extern "C" uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h) { return h ? h->retries : 0; }
+
+namespace {
+
+template <int DATA_T, bool SEQ_SEP>
+void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t n, uint32_t ntiles,
+               bool want_bounds, uint32_t bd_cap, cudaStream_t st) {
+    k1a_tile_summary<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
+        d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
+        h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>());
+    k1b_resolve<<<(n * 32 + 127) / 128, 128, 0, st>>>(
+        h->d_files.as<FileDesc>(), n, d_bytes, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(),
+        h->d_tnrec.as<uint16_t>(), h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(),
+        h->d_trecbase.as<uint32_t>(), h->d_res.as<FileResult>(), h->d_misc.as<uint32_t>(), bd_cap,
+        want_bounds ? 1 : 0, (DATA_T == 1 && SEQ_SEP) ? 1 : 0);
+    k1c_pack<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
+        d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
+        h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(), h->d_trecbase.as<uint32_t>(),
+        h->d_res.as<FileResult>(), DATA_T == 0 ? h->d_packed.as<uint32_t>() : nullptr,
+        DATA_T == 1 ? h->d_packed.as<uint8_t>() : nullptr,
+        want_bounds ? h->d_bounds.as<uint32_t>() : nullptr);
+    h->launches += 3;
+}
+
+template <class Src, typename KT>
+void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunks, uint32_t cpoff,
+                       bool dna, bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    const ProbJob *jobs = h->d_jobs.as<ProbJob>() + joff;
+    ProbBound *bound = h->d_bound.as<ProbBound>() + joff;
+    uint32_t *ovf = h->d_overflow.as<uint32_t>() + joff;
+    const FileResult *res = h->d_res.as<FileResult>();
+    k_prob_reset<<<dim3(296, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf);
+    if (nchunks)
+        k2_prob<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+            jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+            dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf);
+    k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
+    k3_prob_points<KT, 1><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
+    if (h->elem == 8)
+        k3_prob_finalize<uint64_t><<<njobs, 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint64_t *)d_sig,
+                                                          d_nb, h->d_retry.as<uint32_t>());
+    else
+        k3_prob_finalize<uint32_t><<<njobs, 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig,
+                                                          d_nb, h->d_retry.as<uint32_t>());
+    h->launches += nchunks ? 5 : 4;
+}
+
+template <class Src, typename KT>
+void launch_dens(gsb_sketcher *h, uint32_t njobs, uint32_t nchunks, bool dna, bool want_bounds, void *d_sig,
+                 uint64_t *d_nb, cudaStream_t st) {
+    const DensJob *jobs = h->d_jobs.as<DensJob>();
+    const FileResult *res = h->d_res.as<FileResult>();
+    if (nchunks)
+        k2_optdens<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+            jobs, h->d_chunk_prefix.as<uint32_t>(), njobs, h->d_files.as<FileDesc>(), res,
+            dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
+    k3_optdens_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (float *)d_sig, d_nb,
+                                               h->d_retry.as<uint32_t>());
+    h->launches += nchunks ? 2 : 1;
+}
+
+int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vector<double> &tmult,
+             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    const bool dna = h->p.data_t == GSB_DATA_DNA;
+    const bool want_bounds = dna && !h->p.block_flag;
+    const uint32_t n = (uint32_t)todo.size();
+    // slot capacities for this pass
+    size_t max_len = 0;
+    for (uint32_t f : todo) max_len = std::max<size_t>(max_len, h_offsets[f + 1] - h_offsets[f]);
+    if (max_len > kMaxProbSym) {
+        set_error("file of %zu bytes exceeds the %u-symbol limit of the prob path's 24-bit position "
+                  "field", max_len, kMaxProbSym);
+        return GSB_ERR_CAPACITY;
+    }
+    const size_t cap_max = std::max<size_t>(1024, (size_t)(1.6 * (double)max_len) + 64);
+    const size_t light_cap = (size_t)(3.0 * h->sc.m * h->sc.lnm8) + 65536;
+    const size_t list_cap_max = std::min<size_t>(max_len + 64, light_cap + max_len / 2) + 64;
+    for (int s = 0; s < kSlots && s < (int)n; s++) {
+        ProbSlot &sl = h->slot[s];
+        int rc;
+        if ((rc = sl.table.ensure(cap_max * 4 + 64))) return rc;
+        if ((rc = sl.cnt.ensure(cap_max * 4 + 64, true))) return rc;
+        if ((rc = sl.list.ensure(list_cap_max * sizeof(ListEntry)))) return rc;
+        if ((rc = sl.misc.ensure(256))) return rc;
+        if ((rc = sl.hmin.ensure((size_t)h->sc.m * 8))) return rc;
+        if ((rc = sl.sigw.ensure((size_t)h->sc.m * 8))) return rc;
+    }
+    const uint32_t ngroups = (n + kSlots - 1) / kSlots;
+    int rc;
+    if ((rc = h->h_jobs.ensure((size_t)n * sizeof(ProbJob)))) return rc;
+    if ((rc = h->d_jobs.ensure((size_t)n * sizeof(ProbJob)))) return rc;
+    if ((rc = h->h_chunk_prefix.ensure((size_t)ngroups * (kSlots + 1) * 4))) return rc;
+    if ((rc = h->d_chunk_prefix.ensure((size_t)ngroups * (kSlots + 1) * 4))) return rc;
+    if ((rc = h->d_bound.ensure((size_t)n * sizeof(ProbBound)))) return rc;
+    if ((rc = h->d_overflow.ensure((size_t)n * 4))) return rc;
+    if ((rc = h->h_overflow.ensure((size_t)n * 4))) return rc;
+    ProbJob *hj = h->h_jobs.as<ProbJob>();
+    uint32_t *hcp = h->h_chunk_prefix.as<uint32_t>();
+    std::vector<uint32_t> group_chunks(ngroups);
+    for (uint32_t g = 0; g < ngroups; g++) {
+        uint32_t acc = 0;
+        for (int s = 0; s <= kSlots; s++) {
+            hcp[g * (kSlots + 1) + s] = acc;
+            const uint32_t i = g * kSlots + s;
+            if (s < kSlots && i < n) {
+                const uint32_t f = todo[i];
+                const size_t len = h_offsets[f + 1] - h_offsets[f];
+                ProbSlot &sl = h->slot[s];
+                ProbJob &j = hj[i];
+                j.file = f;
+                j.cap = (uint32_t)std::max<size_t>(1024, (size_t)(1.6 * (double)len) + 64);
+                j.table = sl.table.as<uint32_t>();
+                j.cnt = sl.cnt.as<uint32_t>();
+                j.list = sl.list.as<ListEntry>();
+                j.list_cap = (uint32_t)(std::min<size_t>(len + 64, light_cap + len / 2) + 64);
+                j.list_n = sl.misc.as<uint32_t>();
+                j.hmin = sl.hmin.as<unsigned long long>();
+                j.sigw = sl.sigw.as<unsigned long long>();
+                j.tmult = tmult[i];
+                acc += (uint32_t)((len + kChunk - 1) / kChunk);
+            }
+        }
+        group_chunks[g] = acc;
+    }
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, hj, (size_t)n * sizeof(ProbJob), cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (kSlots + 1) * 4,
+                                 cudaMemcpyHostToDevice, st));
+    for (uint32_t g = 0; g < ngroups; g++) {
+        const uint32_t joff = g * kSlots, nj = std::min<uint32_t>(kSlots, n - joff);
+        const uint32_t cpoff = g * (kSlots + 1);
+        if (dna) {
+            if (h->kt32)
+                launch_prob_group<SrcDNA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, true,
+                                                              want_bounds, d_sig, d_nb, st);
+            else
+                launch_prob_group<SrcDNA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, true,
+                                                              want_bounds, d_sig, d_nb, st);
+        } else {
+            if (h->kt32)
+                launch_prob_group<SrcAA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, false, false,
+                                                             d_sig, d_nb, st);
+            else
+                launch_prob_group<SrcAA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, false, false,
+                                                             d_sig, d_nb, st);
+        }
+    }
+    GSB_CUDA_TRY(cudaGetLastError());
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->h_overflow.p, h->d_overflow.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    return GSB_OK;
+}
+
+int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vector<double> &tmult,
+             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    const bool dna = h->p.data_t == GSB_DATA_DNA;
+    const bool want_bounds = dna && !h->p.block_flag;
+    const uint32_t n = (uint32_t)todo.size();
+    int rc;
+    if ((rc = h->h_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
+    if ((rc = h->d_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
+    if ((rc = h->h_chunk_prefix.ensure((size_t)(n + 1) * 4))) return rc;
+    if ((rc = h->d_chunk_prefix.ensure((size_t)(n + 1) * 4))) return rc;
+    if ((rc = h->d_bins.ensure((size_t)n * h->sc.m * 4))) return rc;
+    DensJob *hj = h->h_jobs.as<DensJob>();
+    uint32_t *hcp = h->h_chunk_prefix.as<uint32_t>();
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t f = todo[i];
+        const size_t len = h_offsets[f + 1] - h_offsets[f];
+        hj[i].file = f;
+        hj[i].bins = h->d_bins.as<uint32_t>() + (size_t)i * h->sc.m;
+        hj[i].tmult = tmult[i];
+        hcp[i] = (uint32_t)acc;
+        acc += (len + kChunk - 1) / kChunk;
+    }
+    hcp[n] = (uint32_t)acc;
+    if (acc > 0x7FFFFFFFull) {
+        set_error("batch too large: %llu k-mer chunks", (unsigned long long)acc);
+        return GSB_ERR_CAPACITY;
+    }
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_chunk_prefix.p, hcp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
+    h->launches += 1;
+    const uint32_t nchunks = (uint32_t)acc;
+    if (dna) {
+        if (h->kt32) launch_dens<SrcDNA<uint32_t>, uint32_t>(h, n, nchunks, true, want_bounds, d_sig, d_nb, st);
+        else launch_dens<SrcDNA<uint64_t>, uint64_t>(h, n, nchunks, true, want_bounds, d_sig, d_nb, st);
+    } else {
+        if (h->kt32) launch_dens<SrcAA<uint32_t>, uint32_t>(h, n, nchunks, false, false, d_sig, d_nb, st);
+        else launch_dens<SrcAA<uint64_t>, uint64_t>(h, n, nchunks, false, false, d_sig, d_nb, st);
+    }
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace
+
+extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_bytes, const uint64_t *h_offsets,
+                                          uint32_t n, void *d_sig_out, uint64_t *d_nb_bases_out,
+                                          void *stream) {
+    if (!h || !h_offsets || (n && (!d_bytes && h_offsets[n] > 0)) || (n && !d_sig_out)) {
+        set_error("gsb_sketch_fasta_batch_dev: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    if (n == 0) return GSB_OK;
+    for (uint32_t i = 0; i < n; i++)
+        if (h_offsets[i + 1] < h_offsets[i]) {
+            set_error("offsets must be non-decreasing (file %u)", i);
+            return GSB_ERR_INVALID_ARG;
+        }
+    GSB_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dna = h->p.data_t == GSB_DATA_DNA;
+    const bool seq = !h->p.block_flag;
+    const bool want_bounds = dna && seq;
+    const uint64_t base0 = h_offsets[0];
+    const uint64_t total = h_offsets[n];
+
+    // ---- K1 descriptors
+    int rc;
+    if ((rc = h->h_files.ensure((size_t)n * sizeof(FileDesc)))) return rc;
+    if ((rc = h->h_tile_prefix.ensure((size_t)(n + 1) * 4))) return rc;
+    FileDesc *hf = h->h_files.as<FileDesc>();
+    uint32_t *htp = h->h_tile_prefix.as<uint32_t>();
+    uint64_t ntiles = 0, out_off = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t b = h_offsets[i], e = h_offsets[i + 1];
+        hf[i].beg = b;
+        hf[i].end = e;
+        hf[i].out_off = out_off;
+        hf[i].tile_first = (uint32_t)ntiles;
+        hf[i].ntiles = e > b ? (uint32_t)((e + kTile - 1) / kTile - b / kTile) : 0;
+        htp[i] = (uint32_t)ntiles;
+        ntiles += hf[i].ntiles;
+        const uint64_t len = e - b;
+        // DNA: words (16 bases each) rounded to an even count so 8-byte loads stay aligned;
+        // AA: bytes rounded to 16
+        out_off += dna ? ((len / 16 + 4) & ~1ull) : ((len + 31) & ~15ull);
+    }
+    htp[n] = (uint32_t)ntiles;
+    if (ntiles > 0x7FFFFFFFull) {
+        set_error("batch too large: %llu tiles", (unsigned long long)ntiles);
+        return GSB_ERR_CAPACITY;
+    }
+    (void)base0;
+    const size_t packed_bytes = (dna ? out_off * 4 : out_off) + (size_t)kChunk + 4096;
+    const uint32_t bd_cap = want_bounds ? (uint32_t)std::min<uint64_t>((total - base0) / 32 + n + 1024, 0x7FFFFFFFull) : 0;
+    if ((rc = h->d_files.ensure((size_t)n * sizeof(FileDesc)))) return rc;
+    if ((rc = h->d_tile_prefix.ensure((size_t)(n + 1) * 4))) return rc;
+    if ((rc = h->d_tc4.ensure((size_t)ntiles * 8 + 8))) return rc;
+    if ((rc = h->d_ttrans.ensure((size_t)ntiles + 8))) return rc;
+    if ((rc = h->d_tnrec.ensure((size_t)ntiles * 2 + 8))) return rc;
+    if ((rc = h->d_tstate.ensure((size_t)ntiles + 8))) return rc;
+    if ((rc = h->d_tbase.ensure((size_t)ntiles * 4 + 8))) return rc;
+    if ((rc = h->d_trecbase.ensure((size_t)ntiles * 4 + 8))) return rc;
+    if ((rc = h->d_res.ensure((size_t)n * sizeof(FileResult)))) return rc;
+    if ((rc = h->d_packed.ensure(packed_bytes))) return rc;
+    if ((rc = h->d_bounds.ensure((size_t)bd_cap * 4 + 8))) return rc;
+    if ((rc = h->d_misc.ensure(256))) return rc;
+    if ((rc = h->d_retry.ensure((size_t)n * 4))) return rc;
+    if ((rc = h->h_retry.ensure((size_t)n * 4))) return rc;
+
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_files.p, hf, (size_t)n * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_tile_prefix.p, htp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
+    GSB_CUDA_TRY(cudaMemsetAsync(h->d_retry.p, 0, (size_t)n * 4, st));
+    if (dna) GSB_CUDA_TRY(cudaMemsetAsync(h->d_packed.p, 0, packed_bytes, st));
+    if (ntiles) {
+        if (dna) launch_k1<0, false>(h, d_bytes, total, n, (uint32_t)ntiles, want_bounds, bd_cap, st);
+        else if (seq) launch_k1<1, true>(h, d_bytes, total, n, (uint32_t)ntiles, false, 0, st);
+        else launch_k1<1, false>(h, d_bytes, total, n, (uint32_t)ntiles, false, 0, st);
+        GSB_CUDA_TRY(cudaGetLastError());
+    } else {
+        GSB_CUDA_TRY(cudaMemsetAsync(h->d_res.p, 0, (size_t)n * sizeof(FileResult), st));
+    }
+
+    // ---- K2/K3 with bound retries
+    std::vector<uint32_t> todo(n);
+    std::vector<double> tmult(n, 1.0);
+    for (uint32_t i = 0; i < n; i++) todo[i] = i;
+    const bool prob = h->p.algo == GSB_ALGO_PROB3A;
+    for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++) {
+        rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st)
+                  : run_dens(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st);
+        if (rc) return rc;
+        GSB_CUDA_TRY(cudaMemcpyAsync(h->h_retry.p, h->d_retry.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GSB_CUDA_TRY(cudaStreamSynchronize(st));
+        const uint32_t *hr = h->h_retry.as<uint32_t>();
+        const uint32_t *ho = prob ? h->h_overflow.as<uint32_t>() : nullptr;
+        std::vector<uint32_t> next;
+        std::vector<double> next_t;
+        for (size_t i = 0; i < todo.size(); i++) {
+            const uint32_t f = todo[i];
+            const uint32_t status = hr[f] >> 8;
+            if (status == 5) {
+                set_error("file %u does not start with '>' (not FASTA)", f);
+                return GSB_ERR_BAD_INPUT;
+            }
+            if (status == 8) {
+                set_error("file %u: record-boundary pool exhausted", f);
+                return GSB_ERR_CAPACITY;
+            }
+            if (ho && ho[i]) {
+                // candidate list overflow: counters may be dirty; clear and fail loudly
+                for (auto &s : h->slot)
+                    if (s.cnt.p) cudaMemsetAsync(s.cnt.p, 0, s.cnt.cap, st);
+                set_error("file %u: candidate list overflow (pathological repeat structure)", f);
+                return GSB_ERR_CAPACITY;
+            }
+            if (hr[f] & 1u) {
+                next.push_back(f);
+                next_t.push_back(prob ? tmult[i] * 8.0 : 1e30);
+            }
+        }
+        h->retries += next.size();
+        todo.swap(next);
+        tmult.swap(next_t);
+    }
+    if (!todo.empty()) {
+        set_error("early-stop bound did not converge for %zu file(s)", todo.size());
+        return GSB_ERR_CUDA;
+    }
+    return GSB_OK;
+}
+
+extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets,
+                                      uint32_t n, void *sig_out, uint64_t *nb_bases_out) {
+    if (!h || !offsets || (n && !sig_out)) {
+        set_error("gsb_sketch_fasta_batch: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    if (n == 0) return GSB_OK;
+    GSB_CUDA_TRY(cudaSetDevice(h->device));
+    const uint64_t lo = offsets[0], hi = offsets[n];
+    if (hi < lo || (hi > lo && !bytes)) {
+        set_error("gsb_sketch_fasta_batch: bad offsets / NULL bytes");
+        return GSB_ERR_INVALID_ARG;
+    }
+    const size_t sig_bytes = (size_t)n * h->sc.m * h->elem;
+    int rc;
+    if ((rc = h->d_bytes.ensure(hi - lo + 64))) return rc;
+    if ((rc = h->d_sig.ensure(sig_bytes))) return rc;
+    if ((rc = h->d_nb.ensure((size_t)n * 8))) return rc;
+    cudaStream_t st = h->stream;
+    if (hi > lo) GSB_CUDA_TRY(cudaMemcpyAsync(h->d_bytes.p, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
+    std::vector<uint64_t> rel(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
+    rc = gsb_sketch_fasta_batch_dev(h, h->d_bytes.as<uint8_t>(), rel.data(), n, h->d_sig.p,
+                                    h->d_nb.as<uint64_t>(), (void *)st);
+    if (rc) return rc;
+    GSB_CUDA_TRY(cudaMemcpyAsync(sig_out, h->d_sig.p, sig_bytes, cudaMemcpyDeviceToHost, st));
+    if (nb_bases_out)
+        GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out, h->d_nb.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));
+    return GSB_OK;
+}

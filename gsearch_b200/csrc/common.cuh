@@ -1,0 +1,112 @@
+// common.cuh -- device-side primitives shared by the sm_100a kernels of libgsearch_b200.
+//
+// Arithmetic follows SURVEY.md Appendix A (the frozen SPEC of this repository):
+//   A.3  SplitMix64 / xoshiro256++ (rand_xoshiro::Xoshiro256PlusPlus::seed_from_u64)
+//   A.4  rand 0.8 Uniform<f64>, Uniform<f32>, Uniform<usize>
+//   A.6  probminhash::exp01::ExpRestricted01
+// All f64 steps use explicit round-to-nearest intrinsics so that no FMA contraction can
+// change a bit relative to the reference's (Rust, never contracted) arithmetic.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsb {
+
+constexpr uint64_t kGolden = 0x9e3779b97f4a7c15ULL;
+constexpr uint64_t kFxSeed64 = 0x517cc1b727220a95ULL;  // fxhash::FxHasher64, one word
+
+__device__ __forceinline__ uint64_t sm64_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+struct Xoshiro {
+    uint64_t s0, s1, s2, s3;
+    // seed_from_u64: four successive SplitMix64 outputs
+    __device__ __forceinline__ void seed(uint64_t seed) {
+        s0 = sm64_mix(seed + kGolden);
+        s1 = sm64_mix(seed + 2 * kGolden);
+        s2 = sm64_mix(seed + 3 * kGolden);
+        s3 = sm64_mix(seed + 4 * kGolden);
+    }
+    __device__ __forceinline__ uint64_t next() {
+        const uint64_t result = rotl64(s0 + s3, 23) + s0;
+        const uint64_t t = s1 << 17;
+        s2 ^= s0;
+        s3 ^= s1;
+        s1 ^= s2;
+        s0 ^= s3;
+        s2 ^= t;
+        s3 = rotl64(s3, 45);
+        return result;
+    }
+};
+
+// The first output of a freshly seeded generator only needs s0 and s3: two SplitMix64
+// mixes instead of four.  This is what the per-k-mer filter evaluates.
+__device__ __forceinline__ uint64_t first_output(uint64_t seed, uint64_t &s0_out) {
+    const uint64_t s0 = sm64_mix(seed + kGolden);
+    const uint64_t s3 = sm64_mix(seed + 4 * kGolden);
+    s0_out = s0;
+    return rotl64(s0 + s3, 23) + s0;
+}
+
+// Uniform::<f64>::new(0.,1.).sample : 52 random mantissa bits in [1,2) minus 1
+__device__ __forceinline__ double u01_f64_from_bits(uint64_t r) {
+    return __dadd_rn(__longlong_as_double((long long)((r >> 12) | 0x3FF0000000000000ULL)), -1.0);
+}
+// Uniform::<f32>::new(0.,1.).sample : next_u32 = high half of next_u64, 23 mantissa bits
+__device__ __forceinline__ float u01_f32_from_bits(uint64_t r) {
+    return __fadd_rn(__uint_as_float((((uint32_t)(r >> 32)) >> 9) | 0x3F800000u), -1.0f);
+}
+
+// Uniform::<usize>::new(0, m).sample : widening multiply + rejection zone
+__device__ __forceinline__ uint32_t uniform_usize(Xoshiro &rng, uint64_t m, uint64_t zone) {
+    for (;;) {
+        const uint64_t v = rng.next();
+        const uint64_t lo = v * m;
+        if (lo <= zone) return (uint32_t)__umul64hi(v, m);
+    }
+}
+
+struct Exp01 {
+    double lambda, c1, c2, c3;  // computed on the host with libm, exactly as the oracle does
+};
+
+// ExpRestricted01::sample, entered after the first uniform has been drawn (u0)
+__device__ __forceinline__ double exp01_sample_from(const Exp01 &e, double u0, Xoshiro &rng) {
+    double x = __dmul_rn(e.c1, u0);
+    if (x < 1.0) return x;
+    for (;;) {
+        x = u01_f64_from_bits(rng.next());
+        if (x < e.c2) return x;
+        double y = __dmul_rn(0.5, u01_f64_from_bits(rng.next()));
+        if (y > __dadd_rn(1.0, -x)) {
+            x = __dadd_rn(1.0, -x);
+            y = __dadd_rn(1.0, -y);
+        }
+        if (x <= __dmul_rn(e.c3, __dadd_rn(1.0, -y))) return x;
+        if (__dmul_rn(e.c1, y) <= __dadd_rn(1.0, -x)) return x;
+        if (__dmul_rn(__dmul_rn(y, e.c1), e.lambda) <= expm1(__dmul_rn(e.lambda, __dadd_rn(1.0, -x))))
+            return x;
+    }
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// warp-aggregated append: returns this lane's index in a global list, or ~0u if !pred
+__device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t *cursor) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return 0xffffffffu;
+    const uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane_id() == leader) base = atomicAdd(cursor, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + __popc(mask & ((1u << lane_id()) - 1)) : 0xffffffffu;
+}
+
+}  // namespace gsb

@@ -1,0 +1,425 @@
+// fasta_pack.cuh -- K1: raw FASTA bytes in HBM -> encoded sequence (sm_100a).
+//
+// Replaces, on device, the reference's file tasks
+//   src/dna/dnafiles.rs:43-107,115-195 (seq mode), :200-276,283-360 (block mode)
+//   src/aa/aafiles.rs:33-99,107-229
+// i.e. needletail record splitting [U], the "capsid" record filter (dnafiles.rs:67,145,248,329),
+// Sequence::encode_and_add (drop every byte outside ACGT/acgt, 2 bit/base) and
+// filter_out_non_aa (aafiles.rs:11-28).
+//
+// Layout produced (see DESIGN.md "data layout"):
+//   DNA : 2 bit/base, 16 bases per uint32 word, FIRST base in the MOST significant bits
+//         (so a k-mer value is a funnel-shift of two words), plus a sorted list of record
+//         start positions (seq mode only; k-mers must not span records, dnasketch.rs:347-365)
+//   AA  : 1 byte/residue, codes 1..20; in seq mode a 0 byte separates records.
+//
+// Three kernels, no spin-waits:
+//   k1a_tile_summary : per 4 KiB tile, the tile's effect on the parser state as a function
+//                      of the (unknown) incoming state, and its symbol count for each of the
+//                      four possible incoming states;
+//   k1b_resolve      : one warp per file walks its tiles, resolves states, prefix-sums counts;
+//   k1c_pack         : per tile again (bytes now come from L2), compacts and writes.
+// Parser state s = in_header | dropped<<1.  Every byte is a function {0..3}->{0..3}:
+//   '>' at a line start : s -> 1          (new record: in header, not dropped)
+//   '\n'                : s -> s & 2      (header ends)
+//   'c' of "capsid"     : s -> s|2 if s&1 (record id contains "capsid": dropped)
+// A byte is emitted iff it is in the alphabet and s == 0.
+#pragma once
+
+#include "common.cuh"
+
+namespace gsb {
+
+constexpr int kTile = 4096;       // bytes per tile
+constexpr int kK1Threads = 256;   // 16 bytes per thread
+
+struct FileDesc {
+    uint64_t beg, end;    // byte range of the file in the batch buffer
+    uint64_t out_off;     // DNA: uint32-word offset of its packed output; AA: byte offset
+    uint32_t tile_first;  // index of its first tile summary
+    uint32_t ntiles;      // tiles covering [beg, end) in absolute 4 KiB coordinates
+};
+
+struct FileResult {
+    uint32_t nsym;      // symbols written (DNA: bases; AA: residues + separators)
+    uint32_t nbases;    // encoded bases / residues (ItemDict.len of the reference)
+    uint32_t nrec;      // record starts seen
+    uint32_t bd_off;    // DNA seq mode: offset of its boundary list in the boundary pool
+    uint32_t status;    // 0 ok, 5 = does not start with '>' (needletail InvalidStart)
+    uint32_t pad_;
+};
+
+// ---- state-function algebra: 4 fields of 2 bits, field s = image of state s ----
+constexpr uint32_t kFnIdent = 0xE4;
+__device__ __forceinline__ uint32_t fn_apply(uint32_t f, uint32_t s) { return (f >> (2 * s)) & 3u; }
+// apply f first, then g
+__device__ __forceinline__ uint32_t fn_compose(uint32_t f, uint32_t g) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) out |= fn_apply(g, fn_apply(f, s)) << (2 * s);
+    return out;
+}
+// byte lane s of the result = 1 iff f(s) == 0
+__device__ __forceinline__ uint32_t fn_zero_lanes(uint32_t f) {
+    const uint32_t z = ~(f | (f >> 1)) & 0x55u;
+    return (z & 1u) | ((z >> 2) & 1u) << 8 | ((z >> 4) & 1u) << 16 | ((z >> 6) & 1u) << 24;
+}
+
+template <int DATA_T>
+__device__ __forceinline__ int sym_code(uint32_t c, const uint8_t *aa_lut) {
+    if (DATA_T == 0) {
+        const uint32_t d = (c | 0x20u) - 0x61u;  // 'a'..'z' -> 0..25
+        constexpr uint32_t ok = 1u | (1u << 2) | (1u << 6) | (1u << 19);  // a c g t
+        if (d > 25u || !((ok >> d) & 1u)) return -1;
+        const uint32_t x = (c >> 1) & 3u;  // A0 C1 T2 G3
+        return (int)(x ^ (x >> 1));        // A0 C1 G2 T3
+    } else {
+        const int v = aa_lut[c];
+        return v ? v : -1;
+    }
+}
+
+__device__ __forceinline__ bool is_capsid(const uint8_t *p) {
+    return p[0] == 'c' && p[1] == 'a' && p[2] == 'p' && p[3] == 's' && p[4] == 'i' && p[5] == 'd';
+}
+
+// stage one tile (+16 B halo on both sides) in shared memory, masking bytes outside the
+// file to '\n' (so that the file's first byte is a line start and nothing leaks across files)
+__device__ __forceinline__ void load_tile(const uint8_t *__restrict__ bytes, uint64_t total,
+                                          uint64_t tbase, uint64_t fbeg, uint64_t fend,
+                                          uint8_t *sm /* kTile + 32 */) {
+    const int t = threadIdx.x;
+    for (int blk = t; blk < kTile / 16 + 2; blk += kK1Threads) {
+        const int64_t off = (int64_t)tbase - 16 + (int64_t)blk * 16;
+        uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+        if (off >= 0 && (uint64_t)off + 16 <= total) {
+            v = __ldg(reinterpret_cast<const uint4 *>(bytes + off));
+        } else if (off + 16 > 0 && (uint64_t)(off < 0 ? 0 : off) < total) {
+            uint8_t tmp[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int64_t a = off + i;
+                tmp[i] = (a >= 0 && (uint64_t)a < total) ? bytes[a] : (uint8_t)'\n';
+            }
+            v = *reinterpret_cast<uint4 *>(tmp);
+        }
+        *reinterpret_cast<uint4 *>(sm + blk * 16) = v;
+    }
+    __syncthreads();
+    // mask bytes outside [fbeg, fend): only the first / last tile of a file needs it
+    const int64_t lo = (int64_t)tbase - 16, hi = (int64_t)tbase + kTile + 16;
+    if ((int64_t)fbeg > lo || (int64_t)fend < hi) {
+        for (int i = t; i < kTile + 32; i += kK1Threads) {
+            const int64_t a = lo + i;
+            if (a < (int64_t)fbeg || a >= (int64_t)fend) sm[i] = (uint8_t)'\n';
+        }
+        __syncthreads();
+    }
+}
+
+// per-thread fold of its 16 bytes: state function, per-incoming-state counts, record starts
+template <int DATA_T, bool SEQ_SEP>
+__device__ __forceinline__ void fold16(const uint8_t *p /* own 16 bytes; p[-1], p[16..21] valid */,
+                                       const uint8_t *aa_lut, uint32_t &f, uint32_t &cnt4,
+                                       uint32_t &nrec) {
+    f = kFnIdent;
+    cnt4 = 0;
+    nrec = 0;
+    uint32_t inc4 = fn_zero_lanes(f);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t c = p[i];
+        if (c == '>' && p[i - 1] == '\n') {
+            f = 0x55u;
+            inc4 = 0;
+            nrec++;
+            if (DATA_T == 1 && SEQ_SEP) cnt4 += 0x01010101u;  // separator symbol
+        } else if (c == '\n') {
+            f &= 0xAAu;
+            inc4 = fn_zero_lanes(f);
+        } else {
+            // a "capsid" match only changes states that are inside a header; in a sequence
+            // line the 'c' is an ordinary symbol, so fall through to the alphabet test
+            if (c == 'c' && is_capsid(p + i)) {
+                f |= (f & 0x55u) << 1;
+                inc4 = fn_zero_lanes(f);
+            }
+            if (sym_code<DATA_T>(c, aa_lut) >= 0) cnt4 += inc4;
+        }
+    }
+}
+
+// block-wide exclusive scan of state functions (composition) -> returns F_excl for this
+// thread and the block total in *total
+__device__ __forceinline__ uint32_t block_scan_fn(uint32_t f, uint32_t *warp_tot /* 8 */,
+                                                  uint32_t *total) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t incl = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl = fn_compose(up, incl);
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t pre = kFnIdent;
+    for (uint32_t w = 0; w < warp; w++) pre = fn_compose(pre, warp_tot[w]);
+    uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = kFnIdent;
+    excl = fn_compose(pre, excl);
+    if (total) {
+        uint32_t tot = kFnIdent;
+        for (int w = 0; w < kK1Threads / 32; w++) tot = fn_compose(tot, warp_tot[w]);
+        *total = tot;
+    }
+    __syncthreads();
+    return excl;
+}
+
+// block-wide exclusive sum of a uint32 (two packed 16-bit counters are fine)
+__device__ __forceinline__ uint32_t block_scan_add(uint32_t v, uint32_t *warp_tot /* 8 */,
+                                                   uint32_t *total) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+    for (int w = 0; w < kK1Threads / 32; w++) {
+        if ((uint32_t)w < warp) pre += warp_tot[w];
+        tot += warp_tot[w];
+    }
+    if (total) *total = tot;
+    __syncthreads();
+    return pre + incl - v;
+}
+
+// find the file a global tile index belongs to (tile_prefix has n+1 entries)
+__device__ __forceinline__ uint32_t find_file(const uint32_t *__restrict__ tile_prefix, uint32_t n,
+                                              uint32_t tile) {
+    uint32_t lo = 0, hi = n;  // invariant: tile_prefix[lo] <= tile < tile_prefix[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&tile_prefix[mid]) <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void init_aa_lut(uint8_t *lut) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = 0;
+    __syncthreads();
+    if (threadIdx.x < 20) lut[(uint8_t)"ACDEFGHIKLMNPQRSTVWY"[threadIdx.x]] = (uint8_t)(threadIdx.x + 1);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ K1a
+template <int DATA_T, bool SEQ_SEP>
+__global__ void __launch_bounds__(kK1Threads)
+k1a_tile_summary(const uint8_t *__restrict__ bytes, uint64_t total,
+                 const FileDesc *__restrict__ files, const uint32_t *__restrict__ tile_prefix,
+                 uint32_t nfiles, uint64_t *__restrict__ t_counts4, uint8_t *__restrict__ t_trans,
+                 uint16_t *__restrict__ t_nrec) {
+    __shared__ __align__(16) uint8_t sm[kTile + 32];
+    __shared__ uint8_t aa_lut[256];
+    __shared__ uint32_t wtot[kK1Threads / 32];
+    __shared__ unsigned long long wsum[kK1Threads / 32];
+    if (DATA_T == 1) init_aa_lut(aa_lut);
+    const uint32_t tile = blockIdx.x;
+    const uint32_t fi = find_file(tile_prefix, nfiles, tile);
+    const FileDesc fd = files[fi];
+    const uint32_t lt = tile - fd.tile_first;
+    const uint64_t tbase = (fd.beg / kTile + lt) * (uint64_t)kTile;
+    load_tile(bytes, total, tbase, fd.beg, fd.end, sm);
+
+    const uint8_t *p = sm + 16 + threadIdx.x * 16;
+    uint32_t f, cnt4, nrec;
+    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec);
+    uint32_t ftot;
+    const uint32_t fex = block_scan_fn(f, wtot, &ftot);
+    // this thread's symbol count for each possible tile-incoming state s0
+    unsigned long long c4 = 0;
+#pragma unroll
+    for (int s0 = 0; s0 < 4; s0++) {
+        const uint32_t s = fn_apply(fex, s0);
+        c4 |= (unsigned long long)((cnt4 >> (8 * s)) & 0xFFu) << (16 * s0);
+    }
+    // block reductions: 4x16-bit packed counts (<= 4096+256 each) and nrec
+    unsigned long long v = c4;
+    uint32_t r = nrec;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, d);
+        r += __shfl_xor_sync(0xffffffffu, r, d);
+    }
+    if (lane_id() == 0) {
+        wsum[threadIdx.x >> 5] = v;
+        wtot[threadIdx.x >> 5] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tv = 0;
+        uint32_t tr = 0;
+        for (int w = 0; w < kK1Threads / 32; w++) {
+            tv += wsum[w];
+            tr += wtot[w];
+        }
+        t_counts4[tile] = tv;
+        t_trans[tile] = (uint8_t)ftot;
+        t_nrec[tile] = (uint16_t)tr;
+    }
+}
+
+// ------------------------------------------------------------------ K1b
+// one warp per file: resolve incoming state and exclusive prefix of symbols / records per tile
+__global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
+                            const uint8_t *__restrict__ bytes,
+                            const uint64_t *__restrict__ t_counts4,
+                            const uint8_t *__restrict__ t_trans,
+                            const uint16_t *__restrict__ t_nrec, uint8_t *__restrict__ t_state,
+                            uint32_t *__restrict__ t_base, uint32_t *__restrict__ t_recbase,
+                            FileResult *__restrict__ res, uint32_t *__restrict__ bd_cursor,
+                            uint32_t bd_capacity, int want_boundaries, int sep_counts_as_symbol) {
+    const uint32_t fi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (fi >= nfiles) return;
+    const uint32_t lane = lane_id();
+    const FileDesc fd = files[fi];
+    uint32_t s_carry = 0, base = 0, recbase = 0;
+    for (uint32_t c0 = 0; c0 < fd.ntiles; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        const bool on = i < fd.ntiles;
+        const uint32_t T = fd.tile_first + i;
+        uint32_t f = on ? t_trans[T] : kFnIdent;
+        const unsigned long long c4 = on ? t_counts4[T] : 0ull;
+        const uint32_t nr = on ? t_nrec[T] : 0u;
+        uint32_t incl = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl = fn_compose(up, incl);
+        }
+        uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = kFnIdent;
+        const uint32_t s_in = fn_apply(excl, s_carry);
+        const uint32_t cnt = (uint32_t)((c4 >> (16 * s_in)) & 0xFFFFull);
+        uint32_t ci = cnt, ri = nr;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u1 = __shfl_up_sync(0xffffffffu, ci, d);
+            const uint32_t u2 = __shfl_up_sync(0xffffffffu, ri, d);
+            if (lane >= (uint32_t)d) {
+                ci += u1;
+                ri += u2;
+            }
+        }
+        if (on) {
+            t_state[T] = (uint8_t)s_in;
+            t_base[T] = base + ci - cnt;
+            t_recbase[T] = recbase + ri - nr;
+        }
+        s_carry = fn_apply(__shfl_sync(0xffffffffu, incl, 31), s_carry);
+        base += __shfl_sync(0xffffffffu, ci, 31);
+        recbase += __shfl_sync(0xffffffffu, ri, 31);
+    }
+    if (lane == 0) {
+        FileResult r;
+        r.nsym = base;
+        r.nrec = recbase;
+        r.nbases = sep_counts_as_symbol ? base - recbase : base;
+        r.status = (fd.end > fd.beg && bytes[fd.beg] != '>') ? 5u : 0u;
+        r.bd_off = 0;
+        r.pad_ = 0;
+        if (want_boundaries) {
+            r.bd_off = atomicAdd(bd_cursor, recbase);
+            if (r.bd_off + recbase > bd_capacity) r.status = 8u;
+        }
+        res[fi] = r;
+    }
+}
+
+// ------------------------------------------------------------------ K1c
+template <int DATA_T, bool SEQ_SEP>
+__global__ void __launch_bounds__(kK1Threads)
+k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__restrict__ files,
+         const uint32_t *__restrict__ tile_prefix, uint32_t nfiles,
+         const uint8_t *__restrict__ t_state, const uint32_t *__restrict__ t_base,
+         const uint32_t *__restrict__ t_recbase, const FileResult *__restrict__ res,
+         uint32_t *__restrict__ out_dna, uint8_t *__restrict__ out_aa,
+         uint32_t *__restrict__ boundaries /* DNA seq mode, else null */) {
+    __shared__ __align__(16) uint8_t sm[kTile + 32];
+    __shared__ __align__(16) uint8_t stage[kTile + 256 + 16];
+    __shared__ uint8_t aa_lut[256];
+    __shared__ uint32_t wtot[kK1Threads / 32];
+    if (DATA_T == 1) init_aa_lut(aa_lut);
+    const uint32_t tile = blockIdx.x;
+    const uint32_t fi = find_file(tile_prefix, nfiles, tile);
+    const FileDesc fd = files[fi];
+    const FileResult fr = res[fi];
+    if (fr.status != 0) return;
+    const uint32_t lt = tile - fd.tile_first;
+    const uint64_t tbase = (fd.beg / kTile + lt) * (uint64_t)kTile;
+    load_tile(bytes, total, tbase, fd.beg, fd.end, sm);
+
+    const uint8_t *p = sm + 16 + threadIdx.x * 16;
+    uint32_t f, cnt4, nrec;
+    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec);
+    const uint32_t fex = block_scan_fn(f, wtot, nullptr);
+    const uint32_t s0 = t_state[tile];
+    uint32_t s = fn_apply(fex, s0);
+    const uint32_t cnt = (cnt4 >> (8 * s)) & 0xFFu;
+    uint32_t tile_tot;
+    const uint32_t sc = block_scan_add(cnt | (nrec << 16), wtot, &tile_tot);
+    uint32_t o = sc & 0xFFFFu;          // symbols emitted by earlier threads of this tile
+    uint32_t ro = sc >> 16;             // record starts in earlier threads of this tile
+    const uint32_t ntile = tile_tot & 0xFFFFu;
+    const uint32_t pbase = t_base[tile];
+    // concrete pass: emit symbols into the staging buffer
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t c = p[i];
+        if (c == '>' && p[i - 1] == '\n') {
+            s = 1;
+            if (DATA_T == 1 && SEQ_SEP) stage[o++] = 0;
+            if (DATA_T == 0 && boundaries) {
+                boundaries[fr.bd_off + t_recbase[tile] + ro] = pbase + o;
+                ro++;
+            }
+        } else if (c == '\n') {
+            s &= 2u;
+        } else {
+            if (c == 'c' && (s & 1u) && is_capsid(p + i)) s |= 2u;
+            if (s == 0) {
+                const int code = sym_code<DATA_T>(c, aa_lut);
+                if (code >= 0) stage[o++] = (uint8_t)code;
+            }
+        }
+    }
+    __syncthreads();
+    if (DATA_T == 1) {
+        uint8_t *dst = out_aa + fd.out_off + pbase;
+        for (uint32_t i = threadIdx.x; i < ntile; i += kK1Threads) dst[i] = stage[i];
+    } else {
+        // pack 16 bases per word, first base in the top bits; edge words are shared with
+        // the neighbouring tiles and go through atomicOr (the output is pre-zeroed)
+        if (ntile == 0) return;
+        uint32_t *dst = out_dna + fd.out_off;
+        const uint32_t w_first = pbase >> 4, w_last = (pbase + ntile - 1) >> 4;
+        for (uint32_t w = w_first + threadIdx.x; w <= w_last; w += kK1Threads) {
+            uint32_t val = 0;
+            const int64_t rel = (int64_t)w * 16 - (int64_t)pbase;  // stage index of base 16w
+            bool full = rel >= 0 && rel + 16 <= (int64_t)ntile;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int64_t j = rel + i;
+                const uint32_t code = (j >= 0 && j < (int64_t)ntile) ? stage[j] : 0u;
+                val |= code << (30 - 2 * i);
+            }
+            if (full) dst[w] = val; else if (val) atomicOr(&dst[w], val);
+        }
+    }
+}
+
+}  // namespace gsb

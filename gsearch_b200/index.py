@@ -1,0 +1,84 @@
+"""Host mirror of hnsw_rs::Hnsw<Sig, DistHamming> [U] as the reference uses it:
+Hnsw::new (src/dna/dnasketch.rs:139), parallel_insert (:435), parallel_search
+(src/dna/dnarequest.rs:353), get_nb_point, file_dump / load (src/utils/dumpload.rs:31)."""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+from .distance import _TYPES
+from .params import HnswParams
+
+Neighbour = namedtuple("Neighbour", "d_id distance p_id")
+
+NEIGHBOUR_DTYPE = np.dtype([("d_id", np.uint64), ("distance", np.float32), ("layer", np.uint8),
+                            ("pad", np.uint8, 3), ("rank", np.int32)])
+
+
+class Hnsw:
+    def __init__(self, params: HnswParams, sketch_size: int, dtype, device: int = 0):
+        self.params = params
+        self.dtype = np.dtype(dtype)
+        self.sketch_size = sketch_size
+        cp = _lib.IndexParams(params.max_nb_conn, params.capacity, params.max_layer, params.ef,
+                              params.scale_modification, _TYPES[self.dtype], sketch_size,
+                              1 if params.extend_candidates else 0, 1 if params.keep_pruned else 0,
+                              params.level_seed)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().gsb_index_create(C.byref(cp), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().gsb_index_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def get_nb_point(self):
+        return _lib.lib().gsb_index_nb_point(self._h)
+
+    def parallel_insert(self, sigs, ids):
+        sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        _lib.check(_lib.lib().gsb_index_insert_batch(self._h, C.c_void_p(sigs.ctypes.data),
+                                                     C.c_void_p(ids.ctypes.data), len(ids)))
+
+    def load_graph(self, sigs, ids, levels, ranks, nbr_offsets, nbr_index, entry_point):
+        sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        levels = np.ascontiguousarray(levels, dtype=np.uint8)
+        ranks = np.ascontiguousarray(ranks, dtype=np.uint32)
+        nbr_offsets = np.ascontiguousarray(nbr_offsets, dtype=np.uint64)
+        nbr_index = np.ascontiguousarray(nbr_index, dtype=np.uint32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(_lib.lib().gsb_index_load_graph(self._h, p(sigs), p(ids), len(ids), p(levels), p(ranks),
+                                                   p(nbr_offsets), p(nbr_index), int(entry_point)))
+
+    def search_raw(self, queries, knbn, ef):
+        """-> (structured neighbour array nq x knbn, counts, nb_eval)"""
+        queries = np.ascontiguousarray(queries, dtype=self.dtype)
+        nq = queries.shape[0]
+        out = np.zeros((nq, knbn), dtype=NEIGHBOUR_DTYPE)
+        counts = np.zeros(nq, dtype=np.uint32)
+        neval = np.zeros(nq, dtype=np.uint64)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(_lib.lib().gsb_index_search_batch(self._h, p(queries), nq, knbn, ef, p(out), p(counts),
+                                                     p(neval)))
+        return out, counts, neval
+
+    def parallel_search(self, queries, knbn, ef):
+        """parallel_search(&[Vec<Sig>], knbn, ef) -> Vec<Vec<Neighbour>>"""
+        out, counts, _ = self.search_raw(queries, knbn, ef)
+        res = []
+        for i in range(out.shape[0]):
+            res.append([Neighbour(int(r["d_id"]), float(r["distance"]), (int(r["layer"]), int(r["rank"])))
+                        for r in out[i, :counts[i]]])
+        return res
+
+    def file_dump(self, directory, basename="hnswdump"):
+        _lib.check(_lib.lib().gsb_index_dump(self._h, str(directory).encode(), basename.encode()))
+
+    def load(self, directory, basename="hnswdump"):
+        _lib.check(_lib.lib().gsb_index_load(self._h, str(directory).encode(), basename.encode()))

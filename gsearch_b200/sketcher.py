@@ -1,0 +1,81 @@
+"""Host mirror of kmerutils::SeqSketcherT / SeqSketcherAAT as the reference drives them
+(src/dna/dnasketch.rs:336,357; src/aa/aasketch.rs:313,329): FASTA files in, one signature per
+file out.  All arithmetic runs in libgsearch_b200.so on the GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .params import SeqSketcherParams, sig_dtype
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class Sketcher:
+    def __init__(self, params: SeqSketcherParams, device: int = 0):
+        self.params = params
+        cp = _lib.SketchParams(params.kmer_size, params.sketch_size, params.algo, params.data_t,
+                               1 if params.block_flag else 0, params.spec_flags)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().gsb_sketcher_create(C.byref(cp), device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.sig_type = _lib.lib().gsb_sketcher_sig_type(h)
+        self.dtype = sig_dtype(self.sig_type)
+        self.elem_size = _lib.lib().gsb_sketcher_elem_size(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().gsb_sketcher_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def concat(files):
+        """list of bytes-like -> (uint8 array, uint64 offsets)"""
+        offs = np.zeros(len(files) + 1, dtype=np.uint64)
+        for i, f in enumerate(files):
+            offs[i + 1] = offs[i] + len(f)
+        buf = np.empty(int(offs[-1]), dtype=np.uint8)
+        for i, f in enumerate(files):
+            buf[int(offs[i]):int(offs[i + 1])] = np.frombuffer(bytes(f), dtype=np.uint8)
+        return buf, offs
+
+    def sketch_files(self, files):
+        """sketch_compressedkmer[_seqs] over a batch of FASTA files (bytes) -> (sigs, nb_bases)."""
+        buf, offs = self.concat(files)
+        return self.sketch_buffer(buf, offs)
+
+    def sketch_buffer(self, buf, offsets):
+        """Host buffers (numpy uint8 / uint64 offsets) -> (n x S signatures, n encoded lengths)."""
+        n = len(offsets) - 1
+        S = self.params.sketch_size
+        sig = np.zeros((n, S), dtype=self.dtype)
+        nb = np.zeros(n, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _lib.check(_lib.lib().gsb_sketch_fasta_batch(self._h, _ptr(buf), _ptr(offsets), n, _ptr(sig), _ptr(nb)))
+        return sig, nb
+
+    def sketch_pointers(self, bytes_ptr, offsets, n, sig_ptr, nb_ptr=0):
+        """Raw HOST pointers (e.g. torch pinned tensors): the e2e path of bench.py."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _lib.check(_lib.lib().gsb_sketch_fasta_batch(self._h, C.c_void_p(bytes_ptr), _ptr(offsets), n,
+                                                     C.c_void_p(sig_ptr), C.c_void_p(nb_ptr)))
+
+    def sketch_device(self, d_bytes_ptr, offsets, n, d_sig_ptr, d_nb_ptr=0, stream=0):
+        """Raw DEVICE pointers; offsets is a host array of n+1 values."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _lib.check(_lib.lib().gsb_sketch_fasta_batch_dev(self._h, C.c_void_p(d_bytes_ptr), _ptr(offsets), n,
+                                                         C.c_void_p(d_sig_ptr), C.c_void_p(d_nb_ptr),
+                                                         C.c_void_p(stream)))
+
+    @property
+    def launch_count(self):
+        return _lib.lib().gsb_sketcher_launch_count(self._h)
+
+    @property
+    def retry_count(self):
+        return _lib.lib().gsb_sketcher_retry_count(self._h)

@@ -1,0 +1,235 @@
+/*
+ * gsearch_b200.h -- C ABI of libgsearch_b200.so
+ *
+ * The drop-in boundary for the GSearch sketch-and-search hot path on NVIDIA B200
+ * (sm_100a).  Every entry point below is what a Rust `-sys` crate (cc + bindgen)
+ * for this path would bind; each one names the reference interface it replaces
+ * (paths relative to the reference checkout, `[U]` = upstream crate that carries
+ * the arithmetic and is not vendored in the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross the ABI;
+ *   - every function returns a gsb_status (0 = ok) unless stated otherwise;
+ *     the failing call's message is available from gsb_last_error() (thread local);
+ *     nothing ever unwinds or aborts across the ABI (reference: panic!/exit(1),
+ *     src/dna/dnasketch.rs:228,285,380,463);
+ *   - the caller owns all in/out buffers; the library owns opaque handles;
+ *   - `*_dev` variants take DEVICE pointers and a CUDA stream (passed as void*,
+ *     0 = default stream) and do not synchronise; the plain variants take HOST
+ *     pointers, stage through pinned memory, and return when results are in host
+ *     memory;
+ *   - there is NO CPU fallback: if no CUDA device is usable every compute call
+ *     returns GSB_ERR_NO_DEVICE.
+ */
+#ifndef GSEARCH_B200_H
+#define GSEARCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSB_API __attribute__((visibility("default")))
+#else
+#define GSB_API
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* status codes                                                               */
+/* ------------------------------------------------------------------------- */
+typedef enum {
+    GSB_OK = 0,
+    GSB_ERR_INVALID_ARG = 1,   /* bad parameter (k, S, algo, NULL pointer ...)       */
+    GSB_ERR_NO_DEVICE = 2,     /* no usable CUDA device: the library has no CPU path */
+    GSB_ERR_CUDA = 3,          /* a CUDA runtime call failed                         */
+    GSB_ERR_OOM = 4,           /* host or device allocation failed                   */
+    GSB_ERR_BAD_INPUT = 5,     /* malformed FASTA (reference: exit(1), dnafiles.rs:54)*/
+    GSB_ERR_UNSUPPORTED = 6,   /* valid in the reference, not (yet) built here       */
+    GSB_ERR_IO = 7,            /* file dump / reload failed                          */
+    GSB_ERR_CAPACITY = 8       /* index capacity or genome-length limit exceeded     */
+} gsb_status;
+
+/* thread-local message of the last failing call on this thread ("" if none) */
+GSB_API const char *gsb_last_error(void);
+/* library version string, e.g. "gsearch_b200 0.1.0 (sm_100a)" */
+GSB_API const char *gsb_version(void);
+/* number of visible CUDA devices (0 on a CPU box; never fails) */
+GSB_API int gsb_device_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* sketch parameters                                                          */
+/*   mirrors kmerutils::sketcharg::{SeqSketcherParams, SketchAlgo, DataType}  */
+/*   [U], re-exported at src/utils/parameters.rs:11 and built at              */
+/*   src/bin/gsearch.rs:181-196,258-263                                       */
+/* ------------------------------------------------------------------------- */
+typedef enum {
+    GSB_ALGO_PROB3A = 0,     /* --algo prob     ProbMinHash3a, Sig = k-mer value   */
+    GSB_ALGO_SUPER = 1,      /* --algo super    SuperMinHash,  Sig = f32            */
+    GSB_ALGO_OPTDENS = 2,    /* --algo optdens  OptDensMinHash, Sig = f32           */
+    GSB_ALGO_REVOPTDENS = 3, /* --algo revoptdens                                   */
+    GSB_ALGO_SUPER2 = 4,     /* --algo super2                                       */
+    GSB_ALGO_HLL = 5         /* --algo hll                                          */
+} gsb_algo;
+
+typedef enum { GSB_DATA_DNA = 0, GSB_DATA_AA = 1 } gsb_data_t;
+
+/* element type of a signature (reference: the `Sig` associated type chosen by the
+ * algo x k dispatch tables src/dna/dnasketch.rs:493-644, src/aa/aasketch.rs:449-552;
+ * same strings as hnswio `t_name`, src/utils/reloadhnsw.rs:13-37)                 */
+typedef enum { GSB_SIG_U32 = 0, GSB_SIG_U64 = 1, GSB_SIG_F32 = 2, GSB_SIG_U16 = 3 } gsb_sig_type;
+
+/* Switches for arithmetic that lives in un-pinned upstream crates (SURVEY 8c:
+ * "parity unpinned").  Default (0) is this repository's frozen SPEC; each bit
+ * flips one recalled-but-unverifiable upstream choice.                           */
+enum {
+    GSB_SPEC_NOHASH_IDENTITY = 1u << 0, /* ProbMinHash3a seed = k-mer value (default:
+                                           byte-swapped value, NoHashHasher::write) */
+    GSB_SPEC_OPTDENS_F64_DRAW = 1u << 1 /* OptDens r = (f32)Uniform<f64> (default:
+                                           Uniform<f32> from next_u32)              */
+};
+
+typedef struct {
+    uint32_t kmer_size;   /* -k ; DNA 1..31 (32 rejected: mask overflow, dnasketch.rs:166), AA 1..12 */
+    uint32_t sketch_size; /* -s ; 2..65535 (README.md:676)                                   */
+    uint32_t algo;        /* gsb_algo                                                        */
+    uint32_t data_t;      /* gsb_data_t (--aa)                                               */
+    uint32_t block_flag;  /* --block : concatenate records, k-mers span record boundaries    */
+    uint32_t spec_flags;  /* GSB_SPEC_* ; 0 = frozen default                                 */
+} gsb_sketch_params;
+
+/* ------------------------------------------------------------------------- */
+/* sketcher                                                                   */
+/*   replaces X::new(&SeqSketcherParams) (src/dna/dnasketch.rs:502,523,603)   */
+/*   and SeqSketcherT::sketch_compressedkmer[_seqs] / SeqSketcherAAT::        */
+/*   sketch_compressedkmeraa[_seqs] called at src/dna/dnasketch.rs:336,357,   */
+/*   src/dna/dnarequest.rs:272,287, src/aa/aasketch.rs:313,329,               */
+/*   src/aa/aarequest.rs:268,283.  The k-mer hash closures                    */
+/*   (src/dna/dnasketch.rs:164-169, src/aa/aasketch.rs:156-160) are fixed     */
+/*   functions of (data_t, k) and are built in, not callbacks.                */
+/* ------------------------------------------------------------------------- */
+typedef struct gsb_sketcher gsb_sketcher;
+
+/* device = CUDA ordinal to run on */
+GSB_API int gsb_sketcher_create(const gsb_sketch_params *params, int device, gsb_sketcher **out);
+GSB_API void gsb_sketcher_destroy(gsb_sketcher *h);
+/* gsb_sig_type of this sketcher's signatures, or -1 */
+GSB_API int gsb_sketcher_sig_type(const gsb_sketcher *h);
+/* bytes per signature element (2, 4 or 8), or 0 */
+GSB_API uint32_t gsb_sketcher_elem_size(const gsb_sketcher *h);
+
+/*
+ * Sketch n FASTA "files" (already decompressed bytes) -> n signatures.
+ *   bytes      concatenation of the n files
+ *   offsets    n+1 byte offsets into `bytes` (file i = [offsets[i], offsets[i+1]))
+ *   sig_out    n * sketch_size * elem_size bytes, row i = signature of file i
+ *   nb_bases_out (optional) n values: encoded bases/residues per file
+ *              (reference: ItemDict.len, src/dna/dnasketch.rs:341,361)
+ * Reproduces src/dna/dnafiles.rs:43-107 (seq mode) / :200-276 (block mode) or
+ * src/aa/aafiles.rs, then the sketcher, per file: one signature per file in both
+ * modes (seq mode = sketch_compressedkmer_seqs, k-mers never span records).
+ */
+GSB_API int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets,
+                                   uint32_t n, void *sig_out, uint64_t *nb_bases_out);
+
+/* Same, all pointers are device pointers; work is enqueued on `stream` and not
+ * synchronised.  d_offsets may be NULL if h_offsets (host copy, n+1 values) is
+ * supplied; h_offsets is required (grid sizing is done on the host).            */
+GSB_API int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_bytes,
+                                       const uint64_t *h_offsets, uint32_t n, void *d_sig_out,
+                                       uint64_t *d_nb_bases_out, void *stream);
+
+/* number of kernel launches issued by this handle so far (bench bookkeeping) */
+GSB_API uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h);
+/* number of genomes whose early-stop bound had to be widened and re-run so far */
+GSB_API uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h);
+
+/* ------------------------------------------------------------------------- */
+/* distance                                                                   */
+/*   replaces anndists::dist::DistHamming::eval [U] used through              */
+/*   Hnsw::<Sig,DistHamming>::new (src/dna/dnasketch.rs:139) and directly at  */
+/*   src/bin/bindash.rs:94-95:  count(a[i] != b[i]) as f32 / len as f32.      */
+/* ------------------------------------------------------------------------- */
+
+/* Batched: one query signature against n candidate signatures (row-major n x S).
+ * elem = gsb_sig_type.  out[i] = hamming(q, cands[i]).  Host pointers.           */
+GSB_API int gsb_hamming_batch(const void *q, const void *cands, uint32_t n, uint32_t S,
+                              uint32_t sig_type, float *out, int device);
+/* nq queries x n candidates -> out[nq*n] (row-major); the all-pairs shape used by
+ * src/bin/bindash.rs:93-164.  Host pointers.                                     */
+GSB_API int gsb_hamming_matrix(const void *queries, uint32_t nq, const void *cands, uint32_t n,
+                               uint32_t S, uint32_t sig_type, float *out, int device);
+/* device-pointer variants, enqueued on `stream` */
+GSB_API int gsb_hamming_matrix_dev(const void *d_queries, uint32_t nq, const void *d_cands,
+                                   uint32_t n, uint32_t S, uint32_t sig_type, float *d_out,
+                                   void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* index                                                                      */
+/*   replaces hnsw_rs::Hnsw<Sig,DistHamming> [U] as used at                   */
+/*   src/dna/dnasketch.rs:139-160,435 ; src/dna/dnarequest.rs:353 ;           */
+/*   src/utils/dumpload.rs:31 ; src/utils/reloadhnsw.rs:41-51                 */
+/* ------------------------------------------------------------------------- */
+typedef struct gsb_index gsb_index;
+
+typedef struct {
+    uint32_t max_nb_connection; /* M: Hnsw::new arg 1; layer 0 keeps 2M       */
+    uint64_t capacity;          /* Hnsw::new arg 2 (1_500_000 at src/bin/gsearch.rs:269)    */
+    uint32_t max_layer;         /* Hnsw::new arg 3 (16 at src/dna/dnasketch.rs:139)         */
+    uint32_t ef_construction;   /* Hnsw::new arg 4 (--ef)                                   */
+    double scale_modification;  /* modify_level_scale (src/dna/dnasketch.rs:141)            */
+    uint32_t sig_type;          /* gsb_sig_type                                             */
+    uint32_t sketch_size;       /* S                                                        */
+    uint32_t extend_candidates; /* set_extend_candidates(true)  src/dna/dnasketch.rs:159    */
+    uint32_t keep_pruned;       /* set_keeping_pruned(false)    src/dna/dnasketch.rs:160    */
+    uint64_t level_seed;        /* the reference seeds its level RNG from entropy; here it
+                                   is explicit so a build is reproducible                   */
+} gsb_index_params;
+
+typedef struct {
+    uint64_t d_id;    /* Neighbour.d_id   : caller's id of the data point            */
+    float distance;   /* Neighbour.distance                                          */
+    uint8_t layer;    /* Neighbour.p_id.0 : layer of the point                       */
+    uint8_t pad_[3];
+    int32_t rank;     /* Neighbour.p_id.1 : rank of the point in its layer           */
+} gsb_neighbour;
+
+GSB_API int gsb_index_create(const gsb_index_params *params, int device, gsb_index **out);
+GSB_API void gsb_index_destroy(gsb_index *idx);
+/* parallel_insert(&[(&Vec<Sig>, usize)]) : n signatures (row-major n x S) with ids */
+GSB_API int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids,
+                                   uint64_t n);
+/* parallel_search(&[Vec<Sig>], knbn, ef) -> Vec<Vec<Neighbour>> :
+ *   out        nq * knbn entries, row i sorted by ascending distance
+ *   counts_out nq values (<= knbn) : valid entries in each row
+ *   nb_eval_out (optional) nq values : number of distance evaluations performed   */
+GSB_API int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t nq,
+                                   uint32_t knbn, uint32_t ef, gsb_neighbour *out,
+                                   uint32_t *counts_out, uint64_t *nb_eval_out);
+/* get_nb_point() */
+GSB_API uint64_t gsb_index_nb_point(const gsb_index *idx);
+/* Load an externally built graph (CSR-like, see DESIGN.md "graph image") so a graph
+ * built elsewhere (the oracle, or a converted hnswdump) can be searched on device. */
+GSB_API int gsb_index_load_graph(gsb_index *idx, const void *sigs, const uint64_t *ids,
+                                 uint64_t n, const uint8_t *levels, const uint32_t *ranks,
+                                 const uint64_t *nbr_offsets /* n*(level+1)+1 prefix */,
+                                 const uint32_t *nbr_index, uint64_t entry_point);
+/* file_dump(dir, basename) / HnswIo::load_hnsw */
+GSB_API int gsb_index_dump(const gsb_index *idx, const char *dir, const char *basename);
+GSB_API int gsb_index_load(gsb_index *idx, const char *dir, const char *basename);
+
+/* ------------------------------------------------------------------------- */
+/* synthetic workloads (bench / tests; host code, seeded)       */
+/* ------------------------------------------------------------------------- */
+GSB_API uint64_t gsb_synth_max_bytes(uint64_t length, uint32_t nrecords);
+GSB_API uint64_t gsb_synth_dna_genome(uint64_t index, uint64_t length, uint32_t ncontigs,
+                                      uint8_t *out, uint64_t cap);
+GSB_API uint64_t gsb_synth_aa_proteome(uint64_t index, uint32_t nprot, uint32_t mean_len,
+                                       uint8_t *out, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSEARCH_B200_H */

@@ -1,0 +1,233 @@
+"""CPU tests: the oracle against published primitive vectors and against the independent
+pure-Python restatement of the definitions (tests/_pyref.py)."""
+import math
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _pyref as R
+import ctypes as C
+
+
+def test_splitmix64_published_vectors():
+    # SplitMix64 (Vigna), seed 1234567: the vectors quoted in SURVEY.md 4 / A.3
+    st = C.c_uint64(1234567)
+    got = [O.L().gso_splitmix64_next(C.byref(st)) for _ in range(3)]
+    assert got == [6457827717110365317, 3203168211198807973, 9817491932198370423]
+
+
+def test_xoshiro256pp_published_vectors():
+    # xoshiro256++ reference implementation, state {1,2,3,4}
+    x = O.Xoshiro()
+    x.s[:] = [1, 2, 3, 4]
+    got = [O.L().gso_xoshiro_next_u64(C.byref(x)) for _ in range(5)]
+    assert got == [41943041, 58720359, 3588806011781223, 3591011842654386, 9228616714210784205]
+
+
+def test_seed_from_u64_and_draws_match_python():
+    for seed in [0, 1, 42, 2**63 + 12345, 2**64 - 1]:
+        x = O.Xoshiro()
+        O.L().gso_xoshiro_seed_from_u64(C.byref(x), C.c_uint64(seed))
+        r = R.Xoshiro(seed)
+        assert list(x.s) == r.s
+        for _ in range(4):
+            assert O.L().gso_uniform_f64(C.byref(x)) == r.f64()
+            assert O.L().gso_uniform_f32(C.byref(x)) == r.f32()
+            assert O.L().gso_uniform_usize(C.byref(x), 18000) == r.usize(18000)
+            assert O.L().gso_xoshiro_next_u32(C.byref(x)) == r.next() >> 32
+
+
+@pytest.mark.parametrize("lam", [1.0, 3.0, math.log(18000 / 17999), math.log(2048 / 2047)])
+def test_exp_restricted01_matches_python_and_theory(lam):
+    e = O.Exp01()
+    O.L().gso_exp01_init(C.byref(e), lam)
+    pe = R.Exp01(lam)
+    assert (e.c1, e.c2, e.c3) == (pe.c1, pe.c2, pe.c3)
+    x = O.Xoshiro()
+    O.L().gso_xoshiro_seed_from_u64(C.byref(x), C.c_uint64(7))
+    r = R.Xoshiro(7)
+    xs = []
+    for _ in range(20000):
+        a = O.L().gso_exp01_sample(C.byref(e), C.byref(x))
+        assert a == pe.sample(r)
+        assert 0.0 <= a < 1.0
+        xs.append(a)
+    # truncated exponential on [0,1): mean = 1/lam - 1/(e^lam - 1)
+    mean = 1.0 / lam - 1.0 / math.expm1(lam)
+    assert abs(np.mean(xs) - mean) < 4 * np.std(xs) / math.sqrt(len(xs))
+
+
+FASTA_CASES = [
+    b"",
+    b">a\nACGT\n",
+    b">a\nACGTNNNNacgtRYKM\nGGCC\n>b desc\nTTTT\n",
+    b">a\r\nACGT\r\nAC\r\n>b\r\nGG\r\n",                     # CRLF
+    b">a\nACGT",                                             # no trailing newline
+    b">a\n\n\nAC\n\nGT\n",                                   # blank lines
+    b">virus capsid protein\nACGTACGT\n>ok\nGGGG\n",         # capsid record dropped
+    b">x\nAC>GT\n>y\n>z\nAAAA\n",                            # '>' inside a line; empty record
+    b">only header",
+    b">a\nNNNN\n>b\nACG\n",                                  # record that encodes to nothing
+    b">capsid\n>capsid2\nACGT\n>c\ncapsidACGT\n",            # "capsid" inside a sequence line is data
+]
+
+
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("data", FASTA_CASES)
+def test_fasta_parse_dna_matches_python(data, block):
+    got = [list(map(int, s)) for s in O.parse_fasta(data, 0, block)]
+    assert got == R.parse_fasta(data, 0, block)
+
+
+AA_CASES = [
+    b">p1\nMKVLAA*\n>p2 capsid\nMMMM\n>p3\nACDXBZUacd*EFG\n",
+    b">p\nMK\nVL\n",
+    b"",
+]
+
+
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("data", AA_CASES)
+def test_fasta_parse_aa_matches_python(data, block):
+    got = [list(map(int, s)) for s in O.parse_fasta(data, 1, block)]
+    assert got == R.parse_fasta(data, 1, block)
+
+
+def test_not_fasta_is_an_error():
+    with pytest.raises(RuntimeError):
+        O.parse_fasta(b"ACGT\n", 0, False)
+
+
+def _rand_fasta(rng, nrec, L, alphabet="ACGT", noise="N"):
+    out = []
+    for r in range(nrec):
+        seq = "".join(rng.choice(list(alphabet), L))
+        if noise and L > 20:
+            i = int(rng.integers(0, L - 5))
+            seq = seq[:i] + noise * 3 + seq[i + 3:]
+        out.append(f">rec{r}\n" + "\n".join(seq[i:i + 60] for i in range(0, L, 60)) + "\n")
+    return "".join(out).encode()
+
+
+@pytest.mark.parametrize("k", [1, 3, 11, 14, 15, 16, 21, 31])
+def test_kmer_values_dna_match_python(k):
+    rng = np.random.default_rng(k)
+    data = _rand_fasta(rng, 3, 200)
+    for block in (False, True):
+        got = [int(v) for v in O.kmer_values(data, 0, k, block)]
+        assert got == R.kmers(R.parse_fasta(data, 0, block), 0, k)
+
+
+def test_canonical_kmer_is_strand_symmetric():
+    comp = str.maketrans("ACGT", "TGCA")
+    rng = np.random.default_rng(3)
+    seq = "".join(rng.choice(list("ACGT"), 300))
+    rc = seq.translate(comp)[::-1]
+    a = O.kmer_values(f">a\n{seq}\n".encode(), 0, 21)
+    b = O.kmer_values(f">a\n{rc}\n".encode(), 0, 21)
+    assert sorted(a.tolist()) == sorted(b.tolist())
+
+
+@pytest.mark.parametrize("k", [1, 6, 7, 12])
+def test_kmer_values_aa_match_python(k):
+    rng = np.random.default_rng(100 + k)
+    data = _rand_fasta(rng, 4, 90, R.AA, "*")
+    got = [int(v) for v in O.kmer_values(data, 1, k)]
+    assert got == R.kmers(R.parse_fasta(data, 1), 1, k)
+
+
+@pytest.mark.parametrize("k,m,val_bytes", [(16, 64, 4), (21, 64, 8), (11, 256, 4), (31, 32, 8)])
+@pytest.mark.parametrize("identity", [False, True])
+def test_probminhash3a_two_pass_equals_definition(k, m, val_bytes, identity):
+    rng = np.random.default_rng(k * 1000 + m)
+    # repeats on purpose: half of the genome is a copy of the other half, plus a tandem repeat
+    half = "".join(rng.choice(list("ACGT"), 700))
+    data = (">g\n" + half + half[:500] + "ACGTTGCA" * 40 + "\n").encode()
+    vals = [int(v) for v in O.kmer_values(data, 0, k)]
+    want, _ = R.probminhash3a_definition(vals, m, val_bytes, identity)
+    sig, _ = O.sketch_files([data], k, m, spec_flags=1 if identity else 0)
+    assert [int(v) for v in sig[0]] == want
+
+
+def test_probminhash3a_tiny_input_fills_every_slot():
+    # fewer k-mers than slots: the reference keeps generating points until all slots are filled
+    data = b">g\nACGTACGGTCA\n"
+    vals = [int(v) for v in O.kmer_values(data, 0, 5)]
+    want, best = R.probminhash3a_definition(vals, 32, 4, hcut=80.0)
+    sig, _ = O.sketch_files([data], 5, 32)
+    assert [int(v) for v in sig[0]] == want
+    assert all(b[0] < float("inf") for b in best)
+
+
+def test_probminhash3a_empty_input_is_all_zero():
+    sig, nb = O.sketch_files([b">g\nACG\n", b""], 16, 64)
+    assert not sig.any() and nb.tolist() == [3, 0]
+
+
+def test_probminhash_estimates_weighted_jaccard():
+    # statistical KAT: E[1 - d_hamming] = Jp; here equal multiplicities so Jp = J
+    rng = np.random.default_rng(11)
+    a = "".join(rng.choice(list("ACGT"), 6000))
+    b = a[:3000] + "".join(rng.choice(list("ACGT"), 3000))
+    k, m = 16, 2048
+    sig, _ = O.sketch_files([f">a\n{a}\n".encode(), f">b\n{b}\n".encode()], k, m)
+    ka = set(O.kmer_values(f">a\n{a}\n".encode(), 0, k).tolist())
+    kb = set(O.kmer_values(f">b\n{b}\n".encode(), 0, k).tolist())
+    J = len(ka & kb) / len(ka | kb)
+    est = 1.0 - O.hamming(sig[0], sig[1])
+    assert abs(est - J) < 4 * math.sqrt(J * (1 - J) / m)
+    assert O.hamming(sig[0], sig[0]) == 0.0
+
+
+@pytest.mark.parametrize("f64_draw", [False, True])
+@pytest.mark.parametrize("n,m", [(3000, 64), (40, 64), (1, 16)])
+def test_optdens_equals_definition_including_densification(n, m, f64_draw):
+    rng = np.random.default_rng(n + m)
+    vals = [int(v) for v in rng.integers(0, 2**35, n)]
+    got = O.optdens(vals, m, 2 if f64_draw else 0)
+    want = R.optdens_definition(vals, m, f64_draw)
+    assert got.tobytes() == want.tobytes()
+    assert (got <= 1.0).all()
+
+
+def test_optdens_estimates_jaccard_aa():
+    rng = np.random.default_rng(5)
+    a = "".join(rng.choice(list(R.AA), 8000))
+    b = a[:4000] + "".join(rng.choice(list(R.AA), 4000))
+    k, m = 7, 1024
+    fa, fb = f">a\n{a}\n".encode(), f">b\n{b}\n".encode()
+    sig, _ = O.sketch_files([fa, fb], k, m, algo=2, data_t=1)
+    ka, kb = set(O.kmer_values(fa, 1, k).tolist()), set(O.kmer_values(fb, 1, k).tolist())
+    J = len(ka & kb) / len(ka | kb)
+    est = 1.0 - O.hamming(sig[0], sig[1])
+    assert abs(est - J) < 4 * math.sqrt(J * (1 - J) / m)
+
+
+def test_superminhash_is_order_free_and_estimates_jaccard():
+    rng = np.random.default_rng(9)
+    vals = [int(v) for v in rng.integers(0, 2**40, 5000)]
+    m = 512
+    a = O.superminhash(vals, m)
+    b = O.superminhash(vals[::-1], m)
+    assert a.tobytes() == b.tobytes()
+    other = vals[:2500] + [int(v) for v in rng.integers(0, 2**40, 2500)]
+    c = O.superminhash(other, m)
+    J = len(set(vals) & set(other)) / len(set(vals) | set(other))
+    assert abs((1.0 - O.hamming(a, c)) - J) < 4 * math.sqrt(J * (1 - J) / m)
+
+
+@pytest.mark.parametrize("dt", [np.uint16, np.uint32, np.uint64, np.float32])
+def test_hamming_matches_definition(dt):
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 5, 1001).astype(dt)
+    b = rng.integers(0, 5, 1001).astype(dt)
+    assert np.float32(O.hamming(a, b)) == R.hamming(a, b)
+    assert O.hamming(a, a) == 0.0
+
+
+def test_sig_type_table():
+    # src/dna/dnasketch.rs:500-515, src/aa/aasketch.rs:457-466
+    assert [O.sig_type(k, 64, 0, 0) for k in (8, 14, 15, 16, 17, 21, 31)] == [0, 0, 1, 0, 1, 1, 1]
+    assert [O.sig_type(k, 64, 0, 1) for k in (3, 6, 7, 12)] == [0, 0, 1, 1]
+    assert O.sig_type(21, 64, 2, 0) == 2 and O.sig_type(7, 64, 2, 1) == 2
