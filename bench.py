@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- genomes/sec sketched (the `tohnsw` sketch phase) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): ProbMinHash3a signatures of synthetic 5 Mbp genomes,
+k=21, s=18000 (Sig = u64).  A step = one pass of the hot path (FASTA bytes -> signatures) over
+one batch of `--batch` distinct genomes per GPU; the batch (~0.5 GB of FASTA) is larger than
+L2, so nothing is served from cache between steps.  `value` is measured with the batch
+resident in HBM (CUDA events, max over ranks); `e2e` goes through the public host-pointer C-ABI
+call with the FASTA in pinned host memory (H2D + kernels + D2H of the signatures inside the
+timed region).  With N > 1 every rank sketches its own genomes (weak scaling) and the finished
+signatures are all-gathered over NCCL inside the timed region, as `tohnsw` needs them on every
+GPU before HNSW insertion.
+
+`--impl reference` times the reference's CPU implementation of the same path: the C
+restatement under oracle/ (the Rust reference cannot be built in this image -- no cargo, crates
+not vendored), one genome per host thread as the reference does
+(src/dna/dnasketch.rs:325), on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genomes/sec sketched (tohnsw sketch phase)"
+UNIT = "genomes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batch", type=int, default=96, help="genomes per step per GPU")
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--kmer", type=int, default=21)
+    ap.add_argument("--sketch", type=int, default=18000)
+    ap.add_argument("--algo", default="prob", choices=["prob", "optdens"])
+    ap.add_argument("--cpu-sample", type=int, default=32, help="genomes in the CPU baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"configs[1]: ProbMinHash3a sketch of synthetic {a.genome_len / 1e6:g} Mbp genomes, k={a.kmer} "
+            f"s={a.sketch} --algo {a.algo}; step = batch of {a.batch} distinct genomes per GPU "
+            f"(slice of the 10k-genome set)")
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def gen_batch_numpy(first_index, n, length):
+    """n synthetic genomes -> (uint8 array, uint64 offsets); CPU arm only"""
+    import gsearch_b200 as g
+    files = [g.synth.dna_genome(first_index + i, length) for i in range(n)]
+    return g.Sketcher.concat(files)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    algo = 0 if a.algo == "prob" else 2
+    cores = host_threads()
+    sample = max(1, min(a.batch, a.cpu_sample))
+    buf, offs = gen_batch_numpy(0, sample, a.genome_len)
+    for _ in range(max(1, min(a.warmup, 1))):
+        O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 0, False, 0, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 0, False, 0, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * a.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "step_sample": f"{sample} genomes per step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} x {a.genome_len} bp genomes x {a.steps} steps, one genome per "
+                                   f"thread, C restatement of the reference CPU path (oracle/)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "power_w_max": float(max(power)), "samples": len(sm)}
+        return out
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- own arm
+def run_own(a):
+    import torch
+    import torch.distributed as dist
+    import gsearch_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the library has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    algo = g.ALGO_PROB3A if a.algo == "prob" else g.ALGO_OPTDENS
+    params = g.SeqSketcherParams(a.kmer, a.sketch, algo)
+    sk = g.Sketcher(params, device=local)
+    elem = sk.elem_size
+    B, S = a.batch, a.sketch
+
+    # ---- synthetic batch of this rank, generated straight into pinned host memory
+    cap1 = g.synth.max_bytes(a.genome_len, 1)
+    h_bytes = torch.empty(cap1 * B, dtype=torch.uint8, pin_memory=True)
+    offs = np.zeros(B + 1, dtype=np.uint64)
+    pos = 0
+    for i in range(B):
+        n = g.synth.dna_genome_into(rank * B + i, a.genome_len, 1, h_bytes.data_ptr() + pos, cap1)
+        assert n > 0
+        pos += n
+        offs[i + 1] = pos
+    total = pos
+    h_sig = torch.empty(B * S * elem, dtype=torch.uint8, pin_memory=True)
+    h_nb = torch.empty(B, dtype=torch.int64, pin_memory=True)
+    d_bytes = torch.empty(total + 64, dtype=torch.uint8, device=dev)
+    d_bytes[:total].copy_(h_bytes[:total], non_blocking=True)
+    d_sig = torch.empty(B * S * elem, dtype=torch.uint8, device=dev)
+    d_nb = torch.empty(B, dtype=torch.int64, device=dev)
+    d_all = torch.empty(world * B * S * elem, dtype=torch.uint8, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+
+    def step():
+        sk.sketch_device(d_bytes.data_ptr(), offs, B, d_sig.data_ptr(), d_nb.data_ptr(), stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_sig)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    barrier()
+
+    # ---- timed region: HBM-resident inputs
+    sk.enable_timing(True)
+    launches0 = sk.launch_count
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sk.launch_count - launches0
+    ktimes = sk.kernel_times()
+    sk.enable_timing(False)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * a.steps / (ms / 1e3)
+
+    # sanity, outside the timed region: every signature is filled and encoded lengths are right
+    nb = d_nb.cpu().numpy()
+    assert (nb > 0.99 * a.genome_len - 100).all() and (nb <= a.genome_len).all(), nb[:4]
+    sig0 = d_sig.cpu().numpy().view(sk.dtype).reshape(B, S)
+    assert (sig0 != 0).mean() > 0.999
+
+    # ---- e2e: host pointers through the public C-ABI call (H2D + kernels + D2H every step)
+    e2e_steps = max(2, min(a.steps, 4))
+    sk.sketch_pointers(h_bytes.data_ptr(), offs, B, h_sig.data_ptr(), h_nb.data_ptr())  # warm staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sk.sketch_pointers(h_bytes.data_ptr(), offs, B, h_sig.data_ptr(), h_nb.data_ptr())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+    assert np.array_equal(h_sig.numpy().view(sk.dtype).reshape(B, S), sig0), "e2e and resident paths differ"
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        fasta_per_genome = total / B
+        alg_bytes_per_genome = fasta_per_genome + S * elem  # L_fasta + S*sizeof(Sig)
+        k2_ms, k2_n = ktimes["k2_scan"]
+        genomes_timed = B * a.steps
+        achieved = (alg_bytes_per_genome * genomes_timed / 1e9) / (k2_ms / 1e3) if k2_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64" if elem == 8 else ("f32" if algo else "u32"),
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "batch_per_gpu": B, "fasta_bytes_per_step_per_gpu": int(total),
+                       "l2": "inputs larger than L2 (no flush needed)",
+                       "collective": "NCCL all_gather_into_tensor of signatures" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(total),
+                    "d2h_bytes_per_step": int(B * S * elem + B * 8), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {
+                "kernel": "k2_prob (k-mer scan + exact multiplicity set)" if algo == 0 else "k2_optdens",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_genome": alg_bytes_per_genome,
+                "avg_launch_ms": (k2_ms / k2_n) if k2_n else None, "launches_timed": k2_n,
+                "note": "integer-issue / L2-atomic bound, not HBM bound (DESIGN.md); fraction reported as required",
+            },
+            "kernel_ms": {k: v[0] for k, v in ktimes.items()},
+            "retries": int(sk.retry_count),
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(a)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a):
+    """the oracle (C port of the reference CPU path) on this box's host cores, bounded sample"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    cores = host_threads()
+    sample = max(1, min(a.batch, a.cpu_sample))
+    buf, offs = gen_batch_numpy(0, sample, a.genome_len)
+    algo = 0 if a.algo == "prob" else 2
+    t0 = time.perf_counter()
+    O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 0, False, 0, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} x {a.genome_len} bp genomes, one genome per thread (oracle/, C restatement)"}
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)

@@ -43,6 +43,8 @@ SYMBOLS = {
     "gsb_sketch_fasta_batch_dev": (_int, [_vp, _vp, _vp, _u32, _vp, _vp, _vp]),
     "gsb_sketcher_launch_count": (_u64, [_vp]),
     "gsb_sketcher_retry_count": (_u64, [_vp]),
+    "gsb_sketcher_enable_timing": (None, [_vp, _int]),
+    "gsb_sketcher_kernel_times": (None, [_vp, _vp, _vp]),
     "gsb_hamming_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _int]),
     "gsb_hamming_matrix": (_int, [_vp, _u32, _vp, _u32, _u32, _u32, _vp, _int]),
     "gsb_hamming_matrix_dev": (_int, [_vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp]),

@@ -224,6 +224,7 @@ extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint3
     if ((rc = idx->d_counts.ensure((size_t)nq * 4))) return rc;
     if ((rc = idx->d_neval.ensure((size_t)nq * 8))) return rc;
     cudaStream_t st = idx->stream;
+    GSB_CUDA_TRY(cudaMemsetAsync(idx->d_out.p, 0, (size_t)nq * knbn * sizeof(gsb_neighbour), st));
     GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_queries.p, queries, (size_t)nq * row, cudaMemcpyHostToDevice, st));
     switch (idx->p.sig_type) {
     case GSB_SIG_U64: rc = launch_search<8, false>(idx, nq, knbn, efs, st); break;

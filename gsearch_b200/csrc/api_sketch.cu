@@ -83,7 +83,57 @@ struct gsb_sketcher {
     ProbSlot slot[kSlots];
     DevBuf d_bytes, d_sig, d_nb;
     uint64_t launches = 0, retries = 0;
+    // optional per-kernel-family timing (bench.py's roofline): CUDA events around launches
+    bool timing = false;
+    struct Span {
+        int cat;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double cat_ms[4] = {0, 0, 0, 0};
+    uint64_t cat_n[4] = {0, 0, 0, 0};
 };
+
+namespace {
+enum { CAT_K1 = 0, CAT_K2 = 1, CAT_K3 = 2, CAT_RESET = 3 };
+struct Timed {
+    gsb_sketcher *h;
+    cudaStream_t st;
+    bool on;
+    gsb_sketcher::Span sp;
+    Timed(gsb_sketcher *h_, int cat, cudaStream_t st_) : h(h_), st(st_), on(h_->timing) {
+        if (!on) return;
+        sp.cat = cat;
+        for (cudaEvent_t *e : {&sp.a, &sp.b}) {
+            if (h->ev_pool.empty()) {
+                cudaEventCreate(e);
+            } else {
+                *e = h->ev_pool.back();
+                h->ev_pool.pop_back();
+            }
+        }
+        cudaEventRecord(sp.a, st);
+    }
+    ~Timed() {
+        if (!on) return;
+        cudaEventRecord(sp.b, st);
+        h->spans.push_back(sp);
+    }
+};
+void collect_spans(gsb_sketcher *h) {  // call after the stream has been synchronised
+    for (auto &sp : h->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            h->cat_ms[sp.cat] += ms;
+            h->cat_n[sp.cat] += 1;
+        }
+        h->ev_pool.push_back(sp.a);
+        h->ev_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+}
+}  // namespace
 
 static int sig_type_of(const gsb_sketch_params &p) {
     if (p.algo == GSB_ALGO_PROB3A) {
@@ -170,6 +220,11 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
     }
     PinBuf *pb[] = {&h->h_files, &h->h_tile_prefix, &h->h_jobs, &h->h_chunk_prefix, &h->h_retry, &h->h_overflow};
     for (PinBuf *b : pb) b->release();
+    for (auto &sp : h->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -178,12 +233,27 @@ extern "C" int gsb_sketcher_sig_type(const gsb_sketcher *h) { return h ? h->sig_
 extern "C" uint32_t gsb_sketcher_elem_size(const gsb_sketcher *h) { return h ? h->elem : 0; }
 extern "C" uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h) { return h ? h->launches : 0; }
 extern "C" uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h) { return h ? h->retries : 0; }
+extern "C" void gsb_sketcher_enable_timing(gsb_sketcher *h, int on) {
+    if (!h) return;
+    h->timing = on != 0;
+    for (int i = 0; i < 4; i++) {
+        h->cat_ms[i] = 0;
+        h->cat_n[i] = 0;
+    }
+}
+extern "C" void gsb_sketcher_kernel_times(const gsb_sketcher *h, double *ms_out, uint64_t *n_out) {
+    for (int i = 0; i < 4; i++) {
+        if (ms_out) ms_out[i] = h ? h->cat_ms[i] : 0.0;
+        if (n_out) n_out[i] = h ? h->cat_n[i] : 0;
+    }
+}
 
 namespace {
 
 template <int DATA_T, bool SEQ_SEP>
 void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t n, uint32_t ntiles,
                bool want_bounds, uint32_t bd_cap, cudaStream_t st) {
+    Timed t_(h, CAT_K1, st);
     k1a_tile_summary<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
         d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
         h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>());
@@ -208,12 +278,18 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     ProbBound *bound = h->d_bound.as<ProbBound>() + joff;
     uint32_t *ovf = h->d_overflow.as<uint32_t>() + joff;
     const FileResult *res = h->d_res.as<FileResult>();
-    k_prob_reset<<<dim3(296, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf);
-    if (nchunks)
+    {
+        Timed t_(h, CAT_RESET, st);
+        k_prob_reset<<<dim3(296, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf);
+    }
+    if (nchunks) {
+        Timed t_(h, CAT_K2, st);
         k2_prob<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
             jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
             dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
             want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf);
+    }
+    Timed t3_(h, CAT_K3, st);
     k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
     k3_prob_points<KT, 1><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
     if (h->elem == 8)
@@ -230,11 +306,14 @@ void launch_dens(gsb_sketcher *h, uint32_t njobs, uint32_t nchunks, bool dna, bo
                  uint64_t *d_nb, cudaStream_t st) {
     const DensJob *jobs = h->d_jobs.as<DensJob>();
     const FileResult *res = h->d_res.as<FileResult>();
-    if (nchunks)
+    if (nchunks) {
+        Timed t_(h, CAT_K2, st);
         k2_optdens<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
             jobs, h->d_chunk_prefix.as<uint32_t>(), njobs, h->d_files.as<FileDesc>(), res,
             dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
             want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
+    }
+    Timed t3_(h, CAT_K3, st);
     k3_optdens_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (float *)d_sig, d_nb,
                                                h->d_retry.as<uint32_t>());
     h->launches += nchunks ? 2 : 1;
@@ -466,6 +545,7 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
         if (rc) return rc;
         GSB_CUDA_TRY(cudaMemcpyAsync(h->h_retry.p, h->d_retry.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         GSB_CUDA_TRY(cudaStreamSynchronize(st));
+        collect_spans(h);
         const uint32_t *hr = h->h_retry.as<uint32_t>();
         const uint32_t *ho = prob ? h->h_overflow.as<uint32_t>() : nullptr;
         std::vector<uint32_t> next;

@@ -79,3 +79,13 @@ class Sketcher:
     @property
     def retry_count(self):
         return _lib.lib().gsb_sketcher_retry_count(self._h)
+
+    def enable_timing(self, on=True):
+        _lib.lib().gsb_sketcher_enable_timing(self._h, 1 if on else 0)
+
+    def kernel_times(self):
+        """-> {family: (total ms, timed spans)} measured with CUDA events on the launch stream"""
+        ms = np.zeros(4, dtype=np.float64)
+        n = np.zeros(4, dtype=np.uint64)
+        _lib.lib().gsb_sketcher_kernel_times(self._h, _ptr(ms), _ptr(n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("k1_pack", "k2_scan", "k3_slots", "reset"))}

@@ -25,7 +25,8 @@ static int8_t dna_code[256];
 static int8_t aa_code[256];
 static int tables_ready = 0;
 
-static void init_tables(void) {
+/* built once at load time: the per-file driver parses from several threads */
+__attribute__((constructor)) static void init_tables(void) {
     if (tables_ready) return;
     memset(dna_code, -1, sizeof dna_code);
     memset(aa_code, -1, sizeof aa_code);

@@ -36,8 +36,9 @@ class Seqs(C.Structure):
                 ("nb_raw", C.c_uint64)]
 
 
-NEIGHBOUR_DTYPE = np.dtype([("d_id", np.uint64), ("distance", np.float32), ("layer", np.uint8),
-                            ("pad", np.uint8, 3), ("rank", np.int32)])
+NEIGHBOUR_DTYPE = np.dtype({"names": ["d_id", "distance", "layer", "rank"],
+                            "formats": [np.uint64, np.float32, np.uint8, np.int32],
+                            "offsets": [0, 8, 12, 16], "itemsize": 24})  # = sizeof(gsb_neighbour)
 
 _L = None
 

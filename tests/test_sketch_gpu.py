@@ -1,0 +1,114 @@
+"""GPU parity: the CUDA sketch path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Integer signatures and f32 bit patterns must be identical."""
+import numpy as np
+import pytest
+
+import gsearch_b200 as g
+from _cases import adversarial_aa_files, adversarial_dna_files, fasta, rand_seq
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(oracle, files, k, S, algo=g.ALGO_PROB3A, data_t=g.DATA_DNA, block=False, spec=0):
+    sk = g.Sketcher(g.SeqSketcherParams(k, S, algo, data_t, block, spec))
+    got, nb = sk.sketch_files(files)
+    want, wnb = oracle.sketch_files(files, k, S, algo, data_t, block, spec, nthreads=8)
+    sk.close()
+    return got, nb, want, wnb
+
+
+def assert_same(got, nb, want, wnb):
+    assert got.dtype == want.dtype
+    assert nb.tolist() == wnb.tolist()
+    bad = [i for i in range(len(got)) if got[i].tobytes() != want[i].tobytes()]
+    assert not bad, f"signature mismatch for files {bad[:10]}"
+
+
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("k,S", [(16, 2048), (21, 1800), (14, 512), (15, 300), (31, 1000), (5, 64)])
+def test_prob_dna_adversarial_inputs(oracle, k, S, block):
+    assert_same(*run_both(oracle, adversarial_dna_files(k), k, S, block=block))
+
+
+@pytest.mark.parametrize("spec", [g.SPEC_NOHASH_IDENTITY])
+def test_prob_dna_spec_switch(oracle, spec):
+    files = adversarial_dna_files(3)[-4:]
+    assert_same(*run_both(oracle, files, 21, 2000, spec=spec))
+
+
+def test_prob_dna_baseline_config0_shape(oracle):
+    # BASELINE configs[0]: 1 Mbp genomes, k=16, s=2048, --algo prob (8 of the 32 files here)
+    files = [g.synth.dna_genome(i, 1_000_000) for i in range(8)]
+    assert_same(*run_both(oracle, files, 16, 2048))
+
+
+def test_prob_dna_baseline_config1_shape(oracle):
+    # BASELINE configs[1] per-genome shape: 5 Mbp, k=21, s=18000 (2 genomes)
+    files = [g.synth.dna_genome(i, 5_000_000) for i in (0, 1)]
+    assert_same(*run_both(oracle, files, 21, 18000))
+
+
+def test_prob_heavy_repeats(oracle):
+    rng = np.random.default_rng(1)
+    unit = rand_seq(rng, 300)
+    files = [fasta([("tandem", unit * 200)]), fasta([("poly", "A" * 50000)]),
+             fasta([("mix", rand_seq(rng, 30000) + unit * 100)])]
+    assert_same(*run_both(oracle, files, 21, 4096))
+    assert_same(*run_both(oracle, files, 16, 1024))
+
+
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("k,S", [(7, 1200), (6, 256), (12, 500)])
+def test_optdens_aa(oracle, k, S, block):
+    assert_same(*run_both(oracle, adversarial_aa_files(k), k, S, g.ALGO_OPTDENS, g.DATA_AA, block))
+
+
+def test_optdens_aa_f64_draw_switch(oracle):
+    files = adversarial_aa_files(1)[-3:]
+    assert_same(*run_both(oracle, files, 7, 1000, g.ALGO_OPTDENS, g.DATA_AA, spec=g.SPEC_OPTDENS_F64_DRAW))
+
+
+@pytest.mark.parametrize("k,S", [(21, 1800), (16, 512)])
+def test_optdens_dna(oracle, k, S):
+    assert_same(*run_both(oracle, adversarial_dna_files(k), k, S, g.ALGO_OPTDENS))
+
+
+@pytest.mark.parametrize("k,S", [(7, 300), (5, 128)])
+def test_prob_aa(oracle, k, S):
+    assert_same(*run_both(oracle, adversarial_aa_files(k), k, S, g.ALGO_PROB3A, g.DATA_AA))
+
+
+def test_optdens_baseline_config3_shape(oracle):
+    # BASELINE configs[3] per-proteome shape: ~1.5 M residues, k=7, s=12000
+    files = [g.synth.aa_proteome(i, 4500, 333) for i in (0, 1)]
+    assert_same(*run_both(oracle, files, 7, 12000, g.ALGO_OPTDENS, g.DATA_AA))
+
+
+def test_not_fasta_is_reported(oracle):
+    sk = g.Sketcher(g.SeqSketcherParams(16, 64))
+    with pytest.raises(g.GsbError) as e:
+        sk.sketch_files([b">ok\nACGT\n", b"ACGT\n"])
+    assert e.value.status == 5
+    # the handle stays usable
+    got, _ = sk.sketch_files([b">ok\nACGTACGTACGTACGTACGTACGT\n"])
+    want, _ = oracle.sketch_files([b">ok\nACGTACGTACGTACGTACGTACGT\n"], 16, 64)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_sketch_is_batch_invariant_and_idempotent():
+    files = [g.synth.dna_genome(i, 100_000) for i in range(9)]
+    sk = g.Sketcher(g.SeqSketcherParams(21, 2000))
+    a, _ = sk.sketch_files(files)
+    b, _ = sk.sketch_files(files[::-1])
+    c = np.stack([sk.sketch_files([f])[0][0] for f in files])
+    assert a.tobytes() == b[::-1].tobytes() == c.tobytes()
+
+
+def test_estimates_jaccard_between_family_members(oracle):
+    # size-independent property at a larger size: 1 - d_hamming tracks the exact Jp
+    files = [g.synth.dna_genome(i, 400_000) for i in (32, 33, 34, 48)]
+    sk = g.Sketcher(g.SeqSketcherParams(21, 8192))
+    sig, _ = sk.sketch_files(files)
+    d = g.DistHamming().matrix(sig, sig)
+    assert (np.diag(d) == 0).all()
+    assert d[0, 1] < d[0, 2] < 0.9 < d[0, 3]     # substitution rates 0.5 % < 1 % ; stranger ~ 1
