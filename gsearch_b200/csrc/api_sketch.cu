@@ -4,6 +4,7 @@
 // kernels of fasta_pack.cuh / sketch_kernels.cuh on the caller's stream and handles the
 // (rare) early-stop-bound retries.  No arithmetic of the path runs on the CPU.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -17,7 +18,18 @@ using namespace gsb;
 
 namespace {
 
-constexpr int kSlots = 4;  // genomes in flight on the prob path (hash sets sized for L2)
+constexpr int kMaxSlots = 8;
+// genomes in flight on the prob path (hash sets sized for L2); GSB_PROB_SLOTS overrides (1..8)
+static int prob_slots() {
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("GSB_PROB_SLOTS");
+        v = e ? atoi(e) : 4;
+        if (v < 1) v = 1;
+        if (v > kMaxSlots) v = kMaxSlots;
+    }
+    return v;
+}
 
 struct ProbSlot {
     DevBuf table, cnt, list, misc, hmin, sigw;
@@ -36,6 +48,14 @@ k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult 
     const uint32_t j = blockIdx.y;
     if (j >= njobs) return;
     const ProbJob job = jobs[j];
+    // clear the counters left by the previous genome of this slot (entries of kind "repeated")
+    {
+        const uint32_t np = *job.prev_n;
+        for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < np; e += gridDim.x * blockDim.x) {
+            const ListEntry le = job.list[e];
+            if (le.kind == 1) job.cnt[le.slot] = 0;
+        }
+    }
     uint4 *t4 = reinterpret_cast<uint4 *>(job.table);
     const size_t n4 = ((size_t)job.cap + 3) / 4;
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -80,7 +100,7 @@ struct gsb_sketcher {
     DevBuf d_files, d_tile_prefix, d_tc4, d_ttrans, d_tnrec, d_tstate, d_tbase, d_trecbase, d_res,
         d_packed, d_bounds, d_misc, d_retry, d_jobs, d_chunk_prefix, d_bound, d_overflow, d_bins;
     PinBuf h_files, h_tile_prefix, h_jobs, h_chunk_prefix, h_retry, h_overflow;
-    ProbSlot slot[kSlots];
+    ProbSlot slot[kMaxSlots];
     DevBuf d_bytes, d_sig, d_nb;
     uint64_t launches = 0, retries = 0;
     // optional per-kernel-family timing (bench.py's roofline): CUDA events around launches
@@ -324,6 +344,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     const bool dna = h->p.data_t == GSB_DATA_DNA;
     const bool want_bounds = dna && !h->p.block_flag;
     const uint32_t n = (uint32_t)todo.size();
+    const int kSlots = prob_slots();
     // slot capacities for this pass
     size_t max_len = 0;
     for (uint32_t f : todo) max_len = std::max<size_t>(max_len, h_offsets[f + 1] - h_offsets[f]);
@@ -338,10 +359,16 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     for (int s = 0; s < kSlots && s < (int)n; s++) {
         ProbSlot &sl = h->slot[s];
         int rc;
+        const void *old_cnt = sl.cnt.p, *old_list = sl.list.p, *old_misc = sl.misc.p;
         if ((rc = sl.table.ensure(cap_max * 4 + 64))) return rc;
-        if ((rc = sl.cnt.ensure(cap_max * 4 + 64, true))) return rc;
+        if ((rc = sl.cnt.ensure(cap_max * 4 + 64))) return rc;
         if ((rc = sl.list.ensure(list_cap_max * sizeof(ListEntry)))) return rc;
         if ((rc = sl.misc.ensure(256))) return rc;
+        if (sl.cnt.p != old_cnt || sl.list.p != old_list || sl.misc.p != old_misc) {
+            // a (re)allocated slot starts clean: all counters zero, no pending list
+            GSB_CUDA_TRY(cudaMemsetAsync(sl.cnt.p, 0, sl.cnt.cap, st));
+            GSB_CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 256, st));
+        }
         if ((rc = sl.hmin.ensure((size_t)h->sc.m * 8))) return rc;
         if ((rc = sl.sigw.ensure((size_t)h->sc.m * 8))) return rc;
     }
@@ -374,6 +401,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 j.list = sl.list.as<ListEntry>();
                 j.list_cap = (uint32_t)(std::min<size_t>(len + 64, light_cap + len / 2) + 64);
                 j.list_n = sl.misc.as<uint32_t>();
+                j.prev_n = sl.misc.as<uint32_t>() + 1;
                 j.hmin = sl.hmin.as<unsigned long long>();
                 j.sigw = sl.sigw.as<unsigned long long>();
                 j.tmult = tmult[i];
@@ -564,7 +592,10 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
             if (ho && ho[i]) {
                 // candidate list overflow: counters may be dirty; clear and fail loudly
                 for (auto &s : h->slot)
-                    if (s.cnt.p) cudaMemsetAsync(s.cnt.p, 0, s.cnt.cap, st);
+                    if (s.cnt.p) {
+                        cudaMemsetAsync(s.cnt.p, 0, s.cnt.cap, st);
+                        cudaMemsetAsync(s.misc.p, 0, 256, st);
+                    }
                 set_error("file %u: candidate list overflow (pathological repeat structure)", f);
                 return GSB_ERR_CAPACITY;
             }

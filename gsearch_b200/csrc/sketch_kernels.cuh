@@ -48,6 +48,7 @@ struct ProbJob {
     ListEntry *list;     // candidates
     uint32_t list_cap;
     uint32_t *list_n;    // cursor (device)
+    uint32_t *prev_n;    // entries of the slot's previous genome whose counters are still set
     unsigned long long *hmin;  // [m] ordered bits of min h per slot
     unsigned long long *sigw;  // [m] winning k-mer per slot
     double tmult;        // early-stop bound multiplier (1 = default, grown on retry)
@@ -370,12 +371,11 @@ k3_prob_finalize(const ProbJob *__restrict__ jobs, uint32_t njobs,
         retry[job.file] = r | (res[job.file].status << 8);
         if (nb_bases_out) nb_bases_out[job.file] = res[job.file].nbases;
     }
-    // reset the extra-occurrence counters touched by this genome
-    uint32_t n = *job.list_n;
-    if (n > job.list_cap) n = job.list_cap;
-    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-        const ListEntry le = job.list[e];
-        if (le.kind == 1) job.cnt[le.slot] = 0;
+    // the extra-occurrence counters touched by this genome are cleared by the slot's next
+    // k_prob_reset (full grid) from the list left here
+    if (threadIdx.x == 0) {
+        const uint32_t n = *job.list_n;
+        *job.prev_n = n > job.list_cap ? job.list_cap : n;
     }
 }
 

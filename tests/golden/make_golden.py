@@ -1,0 +1,66 @@
+"""Regenerates tests/golden/*.npz from the CPU oracle (oracle/) and the seeded generator.
+
+The reference ships no golden vectors and cannot be built here, so these fixtures
+pin the oracle itself against regressions and give the GPU tests a second, committed target.
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import _oracle as O  # noqa: E402
+import gsearch_b200 as g  # noqa: E402
+
+CASES = {
+    # name: (files builder, k, S, algo, data_t, block)
+    "prob_dna_k16_s256": (lambda: [g.synth.dna_genome(i, 30000, 1 + i) for i in range(3)], 16, 256, 0, 0, False),
+    "prob_dna_k21_s512_block": (lambda: [g.synth.dna_genome(i, 30000, 2) for i in range(16, 19)], 21, 512, 0, 0, True),
+    "optdens_aa_k7_s512": (lambda: [g.synth.aa_proteome(i, 40, 150) for i in range(3)], 7, 512, 2, 1, False),
+    "optdens_dna_k21_s256": (lambda: [g.synth.dna_genome(i, 20000) for i in range(2)], 21, 256, 2, 0, False),
+    "prob_aa_k6_s128": (lambda: [g.synth.aa_proteome(i, 30, 120) for i in range(2)], 6, 128, 0, 1, False),
+}
+
+
+def main():
+    for name, (mk, k, S, algo, data_t, block) in CASES.items():
+        files = mk()
+        sig, nb = O.sketch_files(files, k, S, algo, data_t, block)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), sig=sig, nb=nb,
+                            meta=np.array([k, S, algo, data_t, int(block), len(files)]),
+                            sha=np.array([hash_bytes(f) for f in files], dtype=np.uint64))
+        print(name, sig.shape, sig.dtype, nb.tolist())
+    # hamming + hnsw search fixture
+    rng = np.random.default_rng(123)
+    base = rng.integers(1, 2**40, (300, 256)).astype(np.uint64)
+    for i in range(1, 300):
+        redraw = rng.random(256) >= 0.85
+        base[i] = np.where(redraw, base[i], base[(i - 1) // 2])
+    h = O.Hnsw(16, 64, 256, np.uint64)
+    h.insert(base, np.arange(300, dtype=np.uint64) + 7)
+    q = base[::29]
+    out, counts, neval = h.search(q, 6, 80)
+    gr = h.export()
+    np.savez_compressed(os.path.join(HERE, "hnsw_u64_s256.npz"), base=base, q=q, d_id=out["d_id"],
+                        distance=out["distance"], layer=out["layer"], rank=out["rank"], counts=counts,
+                        neval=neval, levels=gr["levels"], ranks=gr["ranks"], ids=gr["ids"],
+                        nbr_offsets=gr["nbr_offsets"], nbr_index=gr["nbr_index"],
+                        entry=np.array([gr["entry_point"]], dtype=np.uint64),
+                        dist_q_base=O.hamming_matrix(q, base))
+    print("hnsw fixture", counts.tolist(), neval.tolist())
+
+
+def hash_bytes(b):
+    """FNV-1a 64 of the generated input, so a generator change is detected"""
+    h = 0xcbf29ce484222325
+    for c in np.frombuffer(b, dtype=np.uint8)[::97]:
+        h = ((h ^ int(c)) * 0x100000001b3) & ((1 << 64) - 1)
+    return h
+
+
+if __name__ == "__main__":
+    main()
