@@ -20,11 +20,22 @@ namespace {
 
 constexpr int kMaxSlots = 8;
 // genomes in flight on the prob path (hash sets sized for L2); GSB_PROB_SLOTS overrides (1..8)
+// filter slots per input byte; GSB_PROB_LOAD overrides (2 .. 32)
+static double prob_load() {
+    static double v = 0;
+    if (v == 0) {
+        const char *e = getenv("GSB_PROB_LOAD");
+        v = e ? atof(e) : 8.0;
+        if (v < 2.0) v = 2.0;
+        if (v > 32.0) v = 32.0;
+    }
+    return v;
+}
 static int prob_slots() {
     static int v = 0;
     if (!v) {
         const char *e = getenv("GSB_PROB_SLOTS");
-        v = e ? atoi(e) : 4;
+        v = e ? atoi(e) : 8;
         if (v < 1) v = 1;
         if (v > kMaxSlots) v = kMaxSlots;
     }
@@ -32,7 +43,7 @@ static int prob_slots() {
 }
 
 struct ProbSlot {
-    DevBuf table, cnt, list, misc, hmin, sigw;
+    DevBuf bitmap, table, cnt, list, ovf, misc, hmin, sigw;
     size_t cnt_dirty = 0;
 };
 
@@ -56,8 +67,8 @@ k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult 
             if (le.kind == 1) job.cnt[le.slot] = 0;
         }
     }
-    uint4 *t4 = reinterpret_cast<uint4 *>(job.table);
-    const size_t n4 = ((size_t)job.cap + 3) / 4;
+    uint4 *t4 = reinterpret_cast<uint4 *>(job.bitmap);
+    const size_t n4 = ((size_t)job.nslot1 / 16 + 3) / 4 + 1;
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
         t4[i] = z;
@@ -67,6 +78,8 @@ k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult 
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *job.list_n = 0;
+        *job.ovf_n = 0;
+        *job.n_coll = 0;
         overflow[j] = 0;
         const uint32_t N = res[job.file].nsym;
         const uint32_t nk = N >= sc.k ? N - sc.k + 1 : 0;
@@ -233,7 +246,9 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
     for (auto &s : h->slot) {
         s.table.release();
         s.cnt.release();
+        s.bitmap.release();
         s.list.release();
+        s.ovf.release();
         s.misc.release();
         s.hmin.release();
         s.sigw.release();
@@ -304,10 +319,24 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     }
     if (nchunks) {
         Timed t_(h, CAT_K2, st);
-        k2_prob<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+        k2_prob_mark<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+            jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+            dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
+        k2_prob_mid<<<dim3(74, njobs), 256, 0, st>>>(jobs, njobs);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k2_prob_classify<Src, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kStageCap * sizeof(ListEntry)));
+            attr_set = true;
+        }
+        k2_prob_classify<Src, KT><<<nchunks, kK2Threads, kStageCap * sizeof(ListEntry), st>>>(
             jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
             dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
             want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf);
+        k2_prob_overflow<Src, KT><<<dim3(148, njobs), 256, 0, st>>>(
+            jobs, njobs, h->d_files.as<FileDesc>(), res, dna ? h->d_packed.as<uint32_t>() : nullptr,
+            dna ? nullptr : h->d_packed.as<uint8_t>(), h->sc, ovf);
     }
     Timed t3_(h, CAT_K3, st);
     k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
@@ -318,7 +347,7 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     else
         k3_prob_finalize<uint32_t><<<njobs, 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig,
                                                           d_nb, h->d_retry.as<uint32_t>());
-    h->launches += nchunks ? 5 : 4;
+    h->launches += nchunks ? 8 : 4;
 }
 
 template <class Src, typename KT>
@@ -353,16 +382,19 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                   "field", max_len, kMaxProbSym);
         return GSB_ERR_CAPACITY;
     }
-    const size_t cap_max = std::max<size_t>(1024, (size_t)(1.6 * (double)max_len) + 64);
+    const size_t cap_max = std::max<size_t>(4096, (size_t)(2.0 * (double)max_len) + 64);
+    const size_t filter_bytes_max = (((size_t)(prob_load() * (double)max_len) + 64) / 16 + 8) * 4;
     const size_t light_cap = (size_t)(3.0 * h->sc.m * h->sc.lnm8) + 65536;
     const size_t list_cap_max = std::min<size_t>(max_len + 64, light_cap + max_len / 2) + 64;
     for (int s = 0; s < kSlots && s < (int)n; s++) {
         ProbSlot &sl = h->slot[s];
         int rc;
         const void *old_cnt = sl.cnt.p, *old_list = sl.list.p, *old_misc = sl.misc.p;
+        if ((rc = sl.bitmap.ensure(filter_bytes_max + 64))) return rc;
         if ((rc = sl.table.ensure(cap_max * 4 + 64))) return rc;
         if ((rc = sl.cnt.ensure(cap_max * 4 + 64))) return rc;
         if ((rc = sl.list.ensure(list_cap_max * sizeof(ListEntry)))) return rc;
+        if ((rc = sl.ovf.ensure((max_len + 64) * sizeof(OvfEntry)))) return rc;
         if ((rc = sl.misc.ensure(256))) return rc;
         if (sl.cnt.p != old_cnt || sl.list.p != old_list || sl.misc.p != old_misc) {
             // a (re)allocated slot starts clean: all counters zero, no pending list
@@ -395,13 +427,20 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 ProbSlot &sl = h->slot[s];
                 ProbJob &j = hj[i];
                 j.file = f;
-                j.cap = (uint32_t)std::max<size_t>(1024, (size_t)(1.6 * (double)len) + 64);
+                j.nslot1 = (uint32_t)(((size_t)(prob_load() * (double)len) + 64) & ~(size_t)15);
+                j.bitmap = sl.bitmap.as<uint32_t>();
+                j.n_coll = sl.misc.as<uint32_t>() + 3;
+                j.cap2_max = (uint32_t)std::max<size_t>(4096, (size_t)(2.0 * (double)len) + 64);
+                j.cap2 = sl.misc.as<uint32_t>() + 4;
                 j.table = sl.table.as<uint32_t>();
                 j.cnt = sl.cnt.as<uint32_t>();
                 j.list = sl.list.as<ListEntry>();
                 j.list_cap = (uint32_t)(std::min<size_t>(len + 64, light_cap + len / 2) + 64);
                 j.list_n = sl.misc.as<uint32_t>();
                 j.prev_n = sl.misc.as<uint32_t>() + 1;
+                j.ovf = sl.ovf.as<OvfEntry>();
+                j.ovf_cap = (uint32_t)(len + 64);
+                j.ovf_n = sl.misc.as<uint32_t>() + 2;
                 j.hmin = sl.hmin.as<unsigned long long>();
                 j.sigw = sl.sigw.as<unsigned long long>();
                 j.tmult = tmult[i];

@@ -32,6 +32,10 @@ constexpr int kK2Threads = 256;
 constexpr int kRun = 32;                        // consecutive k-mer positions per thread
 constexpr int kChunk = kK2Threads * kRun;       // positions per CTA
 constexpr uint32_t kMaxProbSym = (1u << 24) - 2;  // 24-bit position field of a set entry
+constexpr int kG = 8;                             // k-mers hashed and probed together per thread
+constexpr int kProbeRounds = 4;                   // probes before an insertion is deferred
+constexpr uint32_t kStageCap = 3072;              // per-CTA candidate stage (entries, 48 KiB)
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;         // list entry of a k-mer that never entered the exact set
 
 struct ListEntry {
     uint64_t kmer;
@@ -42,13 +46,20 @@ struct ListEntry {
 // per-genome device-side job state for the prob path
 struct ProbJob {
     uint32_t file;       // index into FileDesc / FileResult
-    uint32_t cap;        // hash-set capacity (entries)
-    uint32_t *table;     // hash set
+    uint32_t nslot1;     // filter slots (2 bits each, 16 per word)
+    uint32_t *bitmap;    // collision-bit filter
+    uint32_t *n_coll;    // occurrences that found their filter slot already seen
+    uint32_t cap2_max;   // allocated exact-set capacity
+    uint32_t *cap2;      // exact-set capacity in use (sized on device from n_coll)
+    uint32_t *table;     // exact set: fingerprint | position+1 of the first occurrence
     uint32_t *cnt;       // extra occurrences per slot
     ListEntry *list;     // candidates
     uint32_t list_cap;
     uint32_t *list_n;    // cursor (device)
     uint32_t *prev_n;    // entries of the slot's previous genome whose counters are still set
+    struct OvfEntry *ovf;  // deferred insertions (probe sequence longer than kProbeRounds)
+    uint32_t ovf_cap;
+    uint32_t *ovf_n;
     unsigned long long *hmin;  // [m] ordered bits of min h per slot
     unsigned long long *sigw;  // [m] winning k-mer per slot
     double tmult;        // early-stop bound multiplier (1 = default, grown on retry)
@@ -96,16 +107,12 @@ __device__ __forceinline__ uint64_t dna_extract(const uint32_t *__restrict__ w, 
 
 template <typename KT>
 struct SrcDNA {
-    uint64_t W0, W1;
+    uint64_t nw;  // the next bases to enter the window, first one in the top two bits
     KT fw, rc, mask;
     uint32_t k, p0, nb, bi;
     const uint32_t *bounds;
     uint32_t nbounds, N;
 
-    __device__ __forceinline__ uint32_t base(uint32_t j) const {
-        const uint64_t w = j < 32 ? W0 : W1;
-        return (uint32_t)(w >> (62 - 2 * (j & 31u))) & 3u;
-    }
     __device__ __forceinline__ void init(const SeqView &sv, uint32_t p0_, uint32_t k_) {
         k = k_;
         p0 = p0_;
@@ -115,12 +122,15 @@ struct SrcDNA {
         const uint32_t wi = p0 >> 4;  // p0 is a multiple of 32 -> wi even
         const uint2 a = __ldg(reinterpret_cast<const uint2 *>(sv.dna + wi));
         const uint2 b = __ldg(reinterpret_cast<const uint2 *>(sv.dna + wi + 2));
-        W0 = ((uint64_t)a.x << 32) | a.y;
-        W1 = ((uint64_t)b.x << 32) | b.y;
+        const uint64_t W0 = ((uint64_t)a.x << 32) | a.y;
+        const uint64_t W1 = ((uint64_t)b.x << 32) | b.y;
         mask = (KT)((k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1));
         const uint64_t f0 = k > 1 ? (W0 >> (64 - 2 * (k - 1))) : 0ull;  // first k-1 bases
         fw = (KT)f0;
         rc = (KT)(revcomp64(f0, k - 1) << 2);
+        // bases p0+k-1 .. p0+k+30 : the kRun = 32 bases that complete this thread's k-mers
+        const uint32_t sh = 2 * (k - 1);
+        nw = sh ? ((W0 << sh) | (W1 >> (64 - sh))) : W0;
         // first record boundary strictly after p0 (bounds is sorted ascending)
         uint32_t lo = 0, hi = nbounds;
         while (lo < hi) {
@@ -130,13 +140,21 @@ struct SrcDNA {
         bi = lo;
         nb = bi < nbounds ? __ldg(&bounds[bi]) : N;
     }
-    // advance to the k-mer starting at p0 + i; returns false if it crosses a record boundary
-    // or the end of the sequence
-    __device__ __forceinline__ bool step(uint32_t i, KT &canon) {
-        const uint32_t b = base(k - 1 + i);
+    __device__ __forceinline__ void roll(KT &canon) {
+        const uint32_t b = (uint32_t)(nw >> 62);
+        nw <<= 2;
         fw = (KT)(((fw << 2) | b) & mask);
         rc = (KT)((rc >> 2) | ((KT)(3u - b) << (2 * (k - 1))));
         canon = fw < rc ? fw : rc;
+    }
+    // true if the k-mers starting at p0+i0 .. p0+i0+n-1 are all inside one record
+    __device__ __forceinline__ bool all_valid(uint32_t i0, uint32_t n) const {
+        return p0 + i0 + n - 1 + k <= nb;  // nb <= N always
+    }
+    // advance to the k-mer starting at p0 + i (steps must be taken in order); returns false
+    // if it crosses a record boundary or the end of the sequence
+    __device__ __forceinline__ bool step(uint32_t i, KT &canon) {
+        roll(canon);
         const uint32_t pos = p0 + i;
         while (nb <= pos) {
             bi++;
@@ -144,6 +162,11 @@ struct SrcDNA {
             if (bi >= nbounds) break;
         }
         return pos + k <= nb && pos + k <= N;
+    }
+    // same, when all_valid() held for the block containing i
+    __device__ __forceinline__ bool step_fast(uint32_t, KT &canon) {
+        roll(canon);
+        return true;
     }
     static __device__ __forceinline__ KT kmer_at(const SeqView &sv, uint32_t pos, uint32_t k) {
         const uint64_t f = dna_extract(sv.dna, pos, k);
@@ -179,6 +202,8 @@ struct SrcAA {
         val = v;
         return run >= k;
     }
+    __device__ __forceinline__ bool all_valid(uint32_t, uint32_t) const { return false; }
+    __device__ __forceinline__ bool step_fast(uint32_t i, KT &val) { return step(i, val); }
     static __device__ __forceinline__ KT kmer_at(const SeqView &sv, uint32_t pos, uint32_t k) {
         uint64_t x = 0;
         for (uint32_t j = 0; j < k; j++) x = (x << 5) | __ldg(&sv.aa[pos + j]);
@@ -216,71 +241,339 @@ __global__ void k_prob_setup(const ProbJob *__restrict__ jobs, uint32_t njobs,
 }
 
 // ------------------------------------------------------------------ prob: K2
+// Deferred insertion: a k-mer whose first kProbeRounds slots are all taken by other k-mers
+// is finished by k2_prob_overflow.  Linear probing keeps this exact: every occurrence of that
+// k-mer sees the same occupied prefix, so all of them are deferred together and continue from
+// the same slot.
+struct OvfEntry {   // a k-mer occurrence that must go through the exact set
+    uint64_t kmer;
+    uint32_t pos1;  // fingerprint | position + 1 : the set entry to write
+    uint32_t cand;  // first draw below the bound?
+};
+
+template <class Src, typename KT>
+__device__ __forceinline__ void set_probe_result(const SeqView &sv, uint32_t k, const ProbJob &job,
+                                                 uint32_t cap, uint32_t old, KT kmer, uint32_t entry, bool cand,
+                                                 uint32_t &slot, bool &act, bool &put, uint32_t &kind) {
+    if (old == 0u) {  // first occurrence of this k-mer
+        put = cand;
+        kind = 0;
+        act = false;
+        return;
+    }
+    bool same = false;
+    if ((old >> 24) == (entry >> 24)) {
+        const uint32_t pos2 = (old & 0xFFFFFFu) - 1;
+        same = Src::kmer_at(sv, pos2, k) == kmer;  // verified against the sequence: exact
+    }
+    if (same) {
+        put = atomicAdd(&job.cnt[slot], 1u) == 0u;  // first repeat reports the k-mer once
+        kind = 1;
+        act = false;
+    } else {
+        slot = slot + 1 == cap ? 0 : slot + 1;
+    }
+}
+
+// warp-level append of up to NI items per lane into a global list
+template <int NI, class Item, class Make>
+__device__ __forceinline__ void warp_list_append(uint32_t mask_bits /* per-lane item mask */, Item *list,
+                                                 uint32_t *cursor, uint32_t cap, uint32_t *overflow_flag,
+                                                 Make &&make) {
+    const uint32_t lane = lane_id();
+    const uint32_t mine = __popc(mask_bits);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+    for (int g = 0; g < NI; g++) {
+        if (mask_bits & (1u << g)) {
+            if (base < cap) list[base] = make(g);
+            else atomicOr(overflow_flag, 1u);
+            base++;
+        }
+    }
+}
+
+// common prologue of the chunked scan kernels: which genome / which positions
+struct ChunkCtx {
+    uint32_t j, p0;
+    bool live;
+    SeqView sv;
+};
+__device__ __forceinline__ ChunkCtx chunk_ctx(const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
+                                              uint32_t file_of_job, const FileDesc *__restrict__ files,
+                                              const FileResult *__restrict__ res,
+                                              const uint32_t *__restrict__ packed_dna,
+                                              const uint8_t *__restrict__ packed_aa,
+                                              const uint32_t *__restrict__ boundaries, uint32_t j) {
+    ChunkCtx c;
+    c.j = j;
+    const FileResult fr = res[file_of_job];
+    const uint32_t cbase = (blockIdx.x - chunk_prefix[j]) * kChunk;
+    c.live = fr.status == 0 && cbase < fr.nsym;  // grid is sized from the byte-length upper bound
+    const FileDesc fd = files[file_of_job];
+    c.sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
+    c.sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
+    c.sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
+    c.sv.nbounds = boundaries ? fr.nrec : 0;
+    c.sv.N = fr.nsym;
+    c.p0 = cbase + threadIdx.x * kRun;
+    return c;
+}
+
+// ---- pass A: mark.  Two bits per filter slot: bit0 = "seen", bit1 = "seen more than once".
+// One returning atomicOr per k-mer on an L2-resident bitmap, all independent (no probing).
 template <class Src, typename KT>
 __global__ void __launch_bounds__(kK2Threads)
-k2_prob(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix,
-        uint32_t njobs, const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
-        const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
-        const uint32_t *__restrict__ boundaries, const ProbBound *__restrict__ bound,
-        SketchConsts sc, uint32_t *__restrict__ overflow) {
+k2_prob_mark(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
+             const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+             const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+             const uint32_t *__restrict__ boundaries, SketchConsts sc) {
     const uint32_t j = find_file(chunk_prefix, njobs, blockIdx.x);
+    const ProbJob job = jobs[j];
+    const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j);
+    if (!cx.live) return;
+    __shared__ uint32_t s_coll;
+    if (threadIdx.x == 0) s_coll = 0;
+    __syncthreads();
+    Src src;
+    src.init(cx.sv, cx.p0, sc.k);
+    uint32_t ncoll = 0;
+    for (uint32_t blk = 0; blk < kRun / kG; blk++) {
+        uint32_t slot[kG], act = 0;
+        if (__all_sync(0xffffffffu, src.all_valid(blk * kG, kG))) {
+            act = (1u << kG) - 1;
+#pragma unroll
+            for (int g = 0; g < kG; g++) {
+                KT kmer;
+                src.step_fast(blk * kG + g, kmer);
+                const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
+                slot[g] = __umulhi((uint32_t)s0, job.nslot1);
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < kG; g++) {
+                KT kmer;
+                const bool valid = src.step(blk * kG + g, kmer);
+                const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
+                slot[g] = __umulhi((uint32_t)s0, job.nslot1);
+                if (valid) act |= 1u << g;
+            }
+        }
+        uint32_t old[kG];
+#pragma unroll
+        for (int g = 0; g < kG; g++)
+            if (act & (1u << g)) old[g] = atomicOr(&job.bitmap[slot[g] >> 4], 1u << (2 * (slot[g] & 15u)));
+#pragma unroll
+        for (int g = 0; g < kG; g++) {
+            if (act & (1u << g)) {
+                const uint32_t sh = 2 * (slot[g] & 15u);
+                if ((old[g] >> sh) & 1u) {
+                    ncoll++;
+                    if (!((old[g] >> sh) & 2u)) atomicOr(&job.bitmap[slot[g] >> 4], 2u << sh);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ncoll += __shfl_xor_sync(0xffffffffu, ncoll, d);
+    if (lane_id() == 0 && ncoll) atomicAdd(&s_coll, ncoll);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_coll) atomicAdd(job.n_coll, s_coll);
+}
+
+// ---- between the passes: size and clear the exact set from the number of collisions
+__global__ void __launch_bounds__(256)
+k2_prob_mid(const ProbJob *__restrict__ jobs, uint32_t njobs) {
+    const uint32_t j = blockIdx.y;
+    if (j >= njobs) return;
+    const ProbJob job = jobs[j];
+    // every occurrence in a collided filter slot goes to the exact set: at most 2 * n_coll k-mers
+    const uint64_t want = 4ull * (uint64_t)(*job.n_coll) + 1024ull;
+    const uint32_t cap2 = (uint32_t)(want < job.cap2_max ? want : job.cap2_max);
+    uint4 *t4 = reinterpret_cast<uint4 *>(job.table);
+    const size_t n4 = ((size_t)cap2 + 3) / 4;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        t4[i] = z;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *job.cap2 = cap2;
+}
+
+// ---- pass B: classify.  A k-mer whose filter slot was seen exactly once is unique (weight 1,
+// exactly); every other occurrence goes through the exact set (fingerprint | position, verified
+// against the sequence), which therefore holds only the few k-mers that share a filter slot.
+template <class Src, typename KT>
+__global__ void __launch_bounds__(kK2Threads, 3)
+k2_prob_classify(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
+                 const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+                 const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+                 const uint32_t *__restrict__ boundaries, const ProbBound *__restrict__ bound,
+                 SketchConsts sc, uint32_t *__restrict__ overflow) {
+    const uint32_t j = find_file(chunk_prefix, njobs, blockIdx.x);
+    const ProbJob job = jobs[j];
+    const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j);
+    if (!cx.live) return;
+    const ProbBound pb = bound[j];
+    // CTA stage (shared memory): unique light k-mers grow from the bottom, occurrences that must
+    // go through the exact set grow from the top; each side is flushed with ONE global atomic.
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    ListEntry *s_lo = reinterpret_cast<ListEntry *>(s_raw);
+    OvfEntry *s_hi = reinterpret_cast<OvfEntry *>(s_raw);  // same 16-byte cells, indexed from the top
+    __shared__ uint32_t s_nlo, s_nhi, s_blo, s_bhi;
+    if (threadIdx.x == 0) {
+        s_nlo = 0;
+        s_nhi = 0;
+    }
+    __syncthreads();
+    Src src;
+    src.init(cx.sv, cx.p0, sc.k);
+    for (uint32_t blk = 0; blk < kRun / kG; blk++) {
+        KT kmer[kG];
+        uint32_t slot[kG], fp[kG];
+        uint32_t act = 0, cand = 0;
+        const bool fast = __all_sync(0xffffffffu, src.all_valid(blk * kG, kG));
+#pragma unroll
+        for (int g = 0; g < kG; g++) {
+            const uint32_t i = blk * kG + g;
+            const bool valid = fast ? src.step_fast(i, kmer[g]) : src.step(i, kmer[g]);
+            uint64_t s0;
+            const uint64_t out1 = first_output(nohash_seed<KT>(kmer[g], sc.spec_flags), s0);
+            const uint64_t U = out1 >> 12;
+            if ((U < pb.uT) | (U >= sc.u_slow)) cand |= 1u << g;
+            slot[g] = __umulhi((uint32_t)s0, job.nslot1);
+            fp[g] = (uint32_t)s0 << 24;
+            if (valid) act |= 1u << g;
+        }
+        // filter words: independent loads
+        uint32_t w[kG];
+#pragma unroll
+        for (int g = 0; g < kG; g++) w[g] = (act & (1u << g)) ? __ldcg(&job.bitmap[slot[g] >> 4]) : 0u;
+        uint32_t lo_m = 0, hi_m = 0;
+#pragma unroll
+        for (int g = 0; g < kG; g++) {
+            const uint32_t coll = (w[g] >> (2 * (slot[g] & 15u))) & 2u;
+            if (act & (1u << g)) {
+                if (coll) hi_m |= 1u << g;                     // shares its filter slot: exact set
+                else if ((cand >> g) & 1u) lo_m |= 1u << g;    // unique (weight 1) and light
+            }
+        }
+        // reserve cells in the stage: one shared-memory atomic per warp and side
+        {
+            const uint32_t lane = lane_id();
+            uint32_t v = __popc(lo_m) | (__popc(hi_m) << 16), incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += up;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t blo = 0, bhi = 0;
+            if (lane == 31) {
+                if (tot & 0xFFFFu) blo = atomicAdd(&s_nlo, tot & 0xFFFFu);
+                if (tot >> 16) bhi = atomicAdd(&s_nhi, tot >> 16);
+            }
+            blo = __shfl_sync(0xffffffffu, blo, 31) + ((incl - v) & 0xFFFFu);
+            bhi = __shfl_sync(0xffffffffu, bhi, 31) + ((incl - v) >> 16);
+#pragma unroll
+            for (int g = 0; g < kG; g++) {
+                if (lo_m & (1u << g)) {
+                    ListEntry e;
+                    e.kmer = (uint64_t)kmer[g];
+                    e.slot = kNoSlot;
+                    e.kind = 0;
+                    s_lo[blo++] = e;
+                } else if (hi_m & (1u << g)) {
+                    OvfEntry e;
+                    e.kmer = (uint64_t)kmer[g];
+                    e.pos1 = fp[g] | (cx.p0 + blk * kG + g + 1);
+                    e.cand = (cand >> g) & 1u;
+                    s_hi[kStageCap - 1 - bhi++] = e;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_nlo + s_nhi > kStageCap - kK2Threads * kG || blk + 1 == kRun / kG) {
+            const uint32_t nlo = s_nlo, nhi = s_nhi;
+            if (threadIdx.x == 0) s_blo = nlo ? atomicAdd(job.list_n, nlo) : 0u;
+            if (threadIdx.x == 32) s_bhi = nhi ? atomicAdd(job.ovf_n, nhi) : 0u;
+            __syncthreads();
+            const uint32_t glo = s_blo, ghi = s_bhi;
+            for (uint32_t t = threadIdx.x; t < nlo; t += kK2Threads) {
+                if (glo + t < job.list_cap) job.list[glo + t] = s_lo[t];
+                else atomicOr(&overflow[j], 1u);
+            }
+            for (uint32_t t = threadIdx.x; t < nhi; t += kK2Threads) {
+                if (ghi + t < job.ovf_cap) job.ovf[ghi + t] = s_hi[kStageCap - 1 - t];
+                else atomicOr(&overflow[j], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_nlo = 0;
+                s_nhi = 0;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// exact-set insertions for the occurrences that share a filter slot: one per thread,
+// linear probing, equality verified against the packed sequence
+template <class Src, typename KT>
+__global__ void __launch_bounds__(256)
+k2_prob_overflow(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileDesc *__restrict__ files,
+                 const FileResult *__restrict__ res, const uint32_t *__restrict__ packed_dna,
+                 const uint8_t *__restrict__ packed_aa, SketchConsts sc, uint32_t *__restrict__ overflow) {
+    const uint32_t j = blockIdx.y;
+    if (j >= njobs) return;
     const ProbJob job = jobs[j];
     const FileResult fr = res[job.file];
     if (fr.status != 0) return;
-    const uint32_t chunk = blockIdx.x - chunk_prefix[j];
-    const uint32_t cbase = chunk * kChunk;
-    if (cbase >= fr.nsym) return;  // grid is sized from the byte-length upper bound
     const FileDesc fd = files[job.file];
     SeqView sv;
     sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
     sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
-    sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
-    sv.nbounds = boundaries ? fr.nrec : 0;
+    sv.bounds = nullptr;
+    sv.nbounds = 0;
     sv.N = fr.nsym;
-    const ProbBound pb = bound[j];
-    const uint32_t p0 = cbase + threadIdx.x * kRun;
-    Src src;
-    src.init(sv, p0, sc.k);
-    for (uint32_t i = 0; i < kRun; i++) {
-        KT canon;
-        const bool valid = src.step(i, canon);
-        bool light = false, rep = false;
-        uint32_t slot = 0;
-        if (valid) {
-            uint64_t s0;
-            const uint64_t out1 = first_output(nohash_seed<KT>(canon, sc.spec_flags), s0);
-            const uint64_t U = out1 >> 12;
-            const bool cand = (U < pb.uT) | (U >= sc.u_slow);
-            const uint32_t entry = ((uint32_t)(s0 >> 56) << 24) | (p0 + i + 1);
-            slot = __umulhi((uint32_t)s0, job.cap);
-            for (;;) {
-                const uint32_t old = atomicCAS(&job.table[slot], 0u, entry);
-                if (old == 0u) {  // first occurrence of this k-mer
-                    light = cand;
-                    break;
-                }
-                if ((old >> 24) == (entry >> 24)) {
-                    const uint32_t pos2 = (old & 0xFFFFFFu) - 1;
-                    if (Src::kmer_at(sv, pos2, sc.k) == canon) {  // exact: a repeat
-                        rep = atomicAdd(&job.cnt[slot], 1u) == 0u;
-                        break;
-                    }
-                }
-                slot = slot + 1 == job.cap ? 0 : slot + 1;
-            }
+    uint32_t n = *job.ovf_n;
+    if (n > job.ovf_cap) n = job.ovf_cap;
+    const uint32_t cap2 = *job.cap2;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps iterate together so that the warp-level append below stays convergent
+    for (uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; e0 < n; e0 += stride) {
+        const uint32_t e = e0 + lane_id();
+        bool act = e < n, put = false;
+        uint32_t kind = 0, slot = 0, entry = 0;
+        KT kmer = 0;
+        bool cand = false;
+        if (act) {
+            const OvfEntry oe = job.ovf[e];
+            kmer = (KT)oe.kmer;
+            entry = oe.pos1;
+            cand = oe.cand != 0;
+            const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
+            slot = __umulhi((uint32_t)(s0 >> 32), cap2);
         }
-        const uint32_t idx = warp_append(light | rep, job.list_n);
-        if (light | rep) {
-            if (idx < job.list_cap) {
-                ListEntry e;
-                e.kmer = (uint64_t)canon;
-                e.slot = slot;
-                e.kind = rep ? 1u : 0u;
-                job.list[idx] = e;
-            } else {
-                atomicOr(&overflow[j], 1u);
-            }
+        while (act) {
+            const uint32_t old = atomicCAS(&job.table[slot], 0u, entry);
+            set_probe_result<Src, KT>(sv, sc.k, job, cap2, old, kmer, entry, cand, slot, act, put, kind);
         }
+        warp_list_append<1>(put ? 1u : 0u, job.list, job.list_n, job.list_cap, &overflow[j], [&](int) {
+            ListEntry le;
+            le.kmer = (uint64_t)kmer;
+            le.slot = slot;
+            le.kind = kind;
+            return le;
+        });
     }
 }
 
@@ -322,7 +615,7 @@ k3_prob_points(const ProbJob *__restrict__ jobs, uint32_t njobs,
     const double T = bound[j].T;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const ListEntry le = job.list[e];
-        const uint32_t extra = job.cnt[le.slot];
+        const uint32_t extra = le.slot == kNoSlot ? 0u : job.cnt[le.slot];
         if (le.kind == 0 && extra != 0) continue;  // handled through its "repeated" entry
         const KT d = (KT)le.kmer;
         pmh_points<KT>(d, 1u + extra, T, sc, [&](double h, uint32_t k) {
