@@ -124,12 +124,17 @@ struct gsb_sketcher {
     };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> ev_pool;
-    double cat_ms[4] = {0, 0, 0, 0};
-    uint64_t cat_n[4] = {0, 0, 0, 0};
+    double cat_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t cat_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // host-pointer entry point: H2D of the next sub-batch overlaps the kernels of the current one
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    uint32_t file_base = 0;  // index of the sub-batch's first file in the caller's batch (messages)
 };
 
 namespace {
-enum { CAT_K1 = 0, CAT_K2 = 1, CAT_K3 = 2, CAT_RESET = 3 };
+enum { CAT_K1 = 0, CAT_K2 = 1, CAT_K3 = 2, CAT_RESET = 3, CAT_K2_MARK = 4, CAT_K2_CLASSIFY = 5, CAT_K2_EXACT = 6,
+       CAT_K1_SUMMARY = 7, CAT_N = 8 };
 struct Timed {
     gsb_sketcher *h;
     cudaStream_t st;
@@ -261,6 +266,10 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
     }
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    for (cudaEvent_t e : h->ev_h2d)
+        if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -271,13 +280,13 @@ extern "C" uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h) { return h ?
 extern "C" void gsb_sketcher_enable_timing(gsb_sketcher *h, int on) {
     if (!h) return;
     h->timing = on != 0;
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < CAT_N; i++) {
         h->cat_ms[i] = 0;
         h->cat_n[i] = 0;
     }
 }
 extern "C" void gsb_sketcher_kernel_times(const gsb_sketcher *h, double *ms_out, uint64_t *n_out) {
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < CAT_N; i++) {
         if (ms_out) ms_out[i] = h ? h->cat_ms[i] : 0.0;
         if (n_out) n_out[i] = h ? h->cat_n[i] : 0;
     }
@@ -289,9 +298,12 @@ template <int DATA_T, bool SEQ_SEP>
 void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t n, uint32_t ntiles,
                bool want_bounds, uint32_t bd_cap, cudaStream_t st) {
     Timed t_(h, CAT_K1, st);
-    k1a_tile_summary<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
-        d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
-        h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>());
+    {
+        Timed ts_(h, CAT_K1_SUMMARY, st);
+        k1a_tile_summary<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
+            d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
+            h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>());
+    }
     k1b_resolve<<<(n * 32 + 127) / 128, 128, 0, st>>>(
         h->d_files.as<FileDesc>(), n, d_bytes, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(),
         h->d_tnrec.as<uint16_t>(), h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(),
@@ -319,24 +331,33 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     }
     if (nchunks) {
         Timed t_(h, CAT_K2, st);
-        k2_prob_mark<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
-            jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
-            dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
-        k2_prob_mid<<<dim3(74, njobs), 256, 0, st>>>(jobs, njobs);
+        {
+            Timed tm_(h, CAT_K2_MARK, st);
+            k2_prob_mark<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+                jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+                dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
+        }
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(k2_prob_classify<Src, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kStageCap * sizeof(ListEntry)));
             attr_set = true;
         }
-        k2_prob_classify<Src, KT><<<nchunks, kK2Threads, kStageCap * sizeof(ListEntry), st>>>(
-            jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
-            dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf);
-        k2_prob_overflow<Src, KT><<<dim3(148, njobs), 256, 0, st>>>(
-            jobs, njobs, h->d_files.as<FileDesc>(), res, dna ? h->d_packed.as<uint32_t>() : nullptr,
-            dna ? nullptr : h->d_packed.as<uint8_t>(), h->sc, ovf);
+        {
+            Timed tc_(h, CAT_K2_CLASSIFY, st);
+            k2_prob_classify<Src, KT><<<nchunks, kK2Threads, kStageCap * sizeof(ListEntry), st>>>(
+                jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+                dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf);
+        }
+        {
+            Timed te_(h, CAT_K2_EXACT, st);
+            k2_prob_mid<<<dim3(74, njobs), 256, 0, st>>>(jobs, njobs);
+            k2_prob_overflow<Src, KT><<<dim3(148, njobs), 256, 0, st>>>(
+                jobs, njobs, h->d_files.as<FileDesc>(), res, dna ? h->d_packed.as<uint32_t>() : nullptr,
+                dna ? nullptr : h->d_packed.as<uint8_t>(), h->sc, ovf);
+        }
     }
     Timed t3_(h, CAT_K3, st);
     k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
@@ -621,11 +642,11 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
             const uint32_t f = todo[i];
             const uint32_t status = hr[f] >> 8;
             if (status == 5) {
-                set_error("file %u does not start with '>' (not FASTA)", f);
+                set_error("file %u does not start with '>' (not FASTA)", h->file_base + f);
                 return GSB_ERR_BAD_INPUT;
             }
             if (status == 8) {
-                set_error("file %u: record-boundary pool exhausted", f);
+                set_error("file %u: record-boundary pool exhausted", h->file_base + f);
                 return GSB_ERR_CAPACITY;
             }
             if (ho && ho[i]) {
@@ -635,7 +656,7 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
                         cudaMemsetAsync(s.cnt.p, 0, s.cnt.cap, st);
                         cudaMemsetAsync(s.misc.p, 0, 256, st);
                     }
-                set_error("file %u: candidate list overflow (pathological repeat structure)", f);
+                set_error("file %u: candidate list overflow (pathological repeat structure)", h->file_base + f);
                 return GSB_ERR_CAPACITY;
             }
             if (hr[f] & 1u) {
@@ -667,21 +688,67 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
         set_error("gsb_sketch_fasta_batch: bad offsets / NULL bytes");
         return GSB_ERR_INVALID_ARG;
     }
-    const size_t sig_bytes = (size_t)n * h->sc.m * h->elem;
+    const size_t sig_row = (size_t)h->sc.m * h->elem;
     int rc;
     if ((rc = h->d_bytes.ensure(hi - lo + 64))) return rc;
-    if ((rc = h->d_sig.ensure(sig_bytes))) return rc;
+    if ((rc = h->d_sig.ensure((size_t)n * sig_row))) return rc;
     if ((rc = h->d_nb.ensure((size_t)n * 8))) return rc;
     cudaStream_t st = h->stream;
-    if (hi > lo) GSB_CUDA_TRY(cudaMemcpyAsync(h->d_bytes.p, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
-    std::vector<uint64_t> rel(n + 1);
-    for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
-    rc = gsb_sketch_fasta_batch_dev(h, h->d_bytes.as<uint8_t>(), rel.data(), n, h->d_sig.p,
-                                    h->d_nb.as<uint64_t>(), (void *)st);
-    if (rc) return rc;
-    GSB_CUDA_TRY(cudaMemcpyAsync(sig_out, h->d_sig.p, sig_bytes, cudaMemcpyDeviceToHost, st));
-    if (nb_bases_out)
-        GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out, h->d_nb.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    GSB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (!h->copy_stream) {
+        GSB_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        GSB_CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        for (auto &e : h->ev_h2d) GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // Sub-batches of whole files: the H2D copy of sub-batch i+1 (copy stream) overlaps the
+    // kernels of sub-batch i (compute stream); finished signatures leave on a third stream.
+    // With pageable host memory the copies block the host instead: same result, no overlap.
+    std::vector<uint32_t> cut{0};
+    {
+        const uint64_t kSubBytes = 96ull << 20;
+        const uint32_t kSubFiles = 16;
+        uint32_t b = 0;
+        for (uint32_t i = 1; i <= n; i++)
+            if (i == n || i - b >= kSubFiles || offsets[i + 1] - offsets[b] > kSubBytes) {
+                cut.push_back(i);
+                b = i;
+            }
+    }
+    const size_t nsub = cut.size() - 1;
+    auto h2d = [&](size_t s) -> cudaError_t {
+        const uint64_t b = offsets[cut[s]], e = offsets[cut[s + 1]];
+        cudaError_t ce = cudaSuccess;
+        if (e > b)
+            ce = cudaMemcpyAsync(h->d_bytes.as<uint8_t>() + (b - lo), bytes + b, e - b, cudaMemcpyHostToDevice,
+                                 h->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_h2d[s & 1], h->copy_stream);
+        return ce;
+    };
+    GSB_CUDA_TRY(h2d(0));
+    std::vector<uint64_t> rel;
+    for (size_t s = 0; s < nsub; s++) {
+        const uint32_t f0 = cut[s], nf = cut[s + 1] - f0;
+        GSB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[s & 1], 0));
+        // the event of sub-batch s+1 reuses the slot of s-1, which the compute stream has passed
+        if (s + 1 < nsub) GSB_CUDA_TRY(h2d(s + 1));
+        rel.resize(nf + 1);
+        for (uint32_t i = 0; i <= nf; i++) rel[i] = offsets[f0 + i] - lo;
+        uint8_t *d_sig = h->d_sig.as<uint8_t>() + (size_t)f0 * sig_row;
+        uint64_t *d_nb = h->d_nb.as<uint64_t>() + f0;
+        h->file_base = f0;
+        rc = gsb_sketch_fasta_batch_dev(h, h->d_bytes.as<uint8_t>(), rel.data(), nf, d_sig, d_nb, (void *)st);
+        h->file_base = 0;
+        if (rc) {
+            cudaStreamSynchronize(h->copy_stream);
+            cudaStreamSynchronize(h->d2h_stream);
+            return rc;
+        }
+        // batch_dev returned after synchronising `st`: the results are complete
+        GSB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)sig_out + (size_t)f0 * sig_row, d_sig, (size_t)nf * sig_row,
+                                     cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (nb_bases_out)
+            GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out + f0, d_nb, (size_t)nf * 8, cudaMemcpyDeviceToHost,
+                                         h->d2h_stream));
+    }
+    GSB_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     return GSB_OK;
 }

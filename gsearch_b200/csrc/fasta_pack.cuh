@@ -117,16 +117,85 @@ __device__ __forceinline__ void load_tile(const uint8_t *__restrict__ bytes, uin
     }
 }
 
+// ---- SIMD-in-register view of a thread's 16 bytes (the common case: no record start, no
+// "capsid" text).  Bit i of a 16-bit mask = byte i.
+__device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t pat4) {  // 0x80 per equal byte
+    const uint32_t t = w ^ pat4;
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t nib_of(uint32_t m80) {  // 0x80-per-byte mask -> 4 bits
+    return (((m80 >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
+struct Chunk16 {
+    uint32_t sym;    // bytes that are alphabet symbols
+    uint32_t nl;     // bytes that are '\n'
+    uint32_t codes[4];  // DNA: 2-bit code of every byte, one per byte lane
+};
+
+// returns false if the chunk needs the byte-serial state machine ('>' or a "capsid" match)
+template <int DATA_T>
+__device__ __forceinline__ bool chunk16_scan(const uint8_t *p, const uint8_t *aa_lut, Chunk16 &c) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t gt = 0, lc = 0;
+    c.sym = 0;
+    c.nl = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        gt |= bytes_eq(w[j], 0x3e3e3e3eu);
+        c.nl |= nib_of(bytes_eq(w[j], 0x0a0a0a0au)) << (4 * j);
+        const uint32_t cj = bytes_eq(w[j], 0x63636363u);  // lower-case 'c'
+        lc |= nib_of(cj) << (4 * j);
+        if (DATA_T == 0) {
+            const uint32_t y = w[j] | 0x20202020u;
+            const uint32_t m = bytes_eq(y, 0x61616161u) | bytes_eq(y, 0x63636363u) |
+                               bytes_eq(y, 0x67676767u) | bytes_eq(y, 0x74747474u);
+            c.sym |= nib_of(m) << (4 * j);
+            const uint32_t x = (w[j] >> 1) & 0x03030303u;  // A0 C1 T2 G3
+            c.codes[j] = x ^ (x >> 1);                     // A0 C1 G2 T3
+        }
+    }
+    if (gt) return false;
+    while (lc) {
+        const int i = __ffs(lc) - 1;
+        lc &= lc - 1;
+        if (is_capsid(p + i)) return false;
+    }
+    if (DATA_T == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c.sym |= (aa_lut[p[i]] ? 1u : 0u) << i;
+    }
+    return true;
+}
+
 // per-thread fold of its 16 bytes: state function, per-incoming-state counts, record starts
 template <int DATA_T, bool SEQ_SEP>
 __device__ __forceinline__ void fold16(const uint8_t *p /* own 16 bytes; p[-1], p[16..21] valid */,
                                        const uint8_t *aa_lut, uint32_t &f, uint32_t &cnt4,
-                                       uint32_t &nrec) {
+                                       uint32_t &nrec, Chunk16 &ck, bool &fast) {
+    fast = chunk16_scan<DATA_T>(p, aa_lut, ck);
+    if (fast) {
+        // no record start and no drop: before the first newline the incoming state decides,
+        // after it the header flag is cleared (s -> s & 2)
+        nrec = 0;
+        if (ck.nl == 0) {
+            f = kFnIdent;
+            cnt4 = __popc(ck.sym);
+        } else {
+            const uint32_t first = __ffs(ck.nl) - 1;
+            const uint32_t before = __popc(ck.sym & ((1u << first) - 1u));
+            const uint32_t after = __popc(ck.sym >> (first + 1));
+            f = kFnIdent & 0xAAu;
+            cnt4 = (before + after) | (after << 8);
+        }
+        return;
+    }
     f = kFnIdent;
     cnt4 = 0;
     nrec = 0;
     uint32_t inc4 = fn_zero_lanes(f);
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 16; i++) {
         const uint32_t c = p[i];
         if (c == '>' && p[i - 1] == '\n') {
@@ -237,7 +306,9 @@ k1a_tile_summary(const uint8_t *__restrict__ bytes, uint64_t total,
 
     const uint8_t *p = sm + 16 + threadIdx.x * 16;
     uint32_t f, cnt4, nrec;
-    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec);
+    Chunk16 ck;
+    bool fast;
+    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec, ck, fast);
     uint32_t ftot;
     const uint32_t fex = block_scan_fn(f, wtot, &ftot);
     // this thread's symbol count for each possible tile-incoming state s0
@@ -365,7 +436,9 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
 
     const uint8_t *p = sm + 16 + threadIdx.x * 16;
     uint32_t f, cnt4, nrec;
-    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec);
+    Chunk16 ck;
+    bool fast;
+    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec, ck, fast);
     const uint32_t fex = block_scan_fn(f, wtot, nullptr);
     const uint32_t s0 = t_state[tile];
     uint32_t s = fn_apply(fex, s0);
@@ -377,23 +450,49 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
     const uint32_t ntile = tile_tot & 0xFFFFu;
     const uint32_t pbase = t_base[tile];
     // concrete pass: emit symbols into the staging buffer
+    if (fast) {
+        // emitted = symbols before the first newline if s == 0, after it if (s & 2) == 0
+        uint32_t emit = ck.sym;
+        if (ck.nl) {
+            const uint32_t first = __ffs(ck.nl) - 1;
+            const uint32_t lo = (1u << first) - 1u;
+            emit = (s == 0 ? (ck.sym & lo) : 0u) | ((s & 2u) == 0 ? (ck.sym & ~lo) : 0u);
+        } else if (s != 0) {
+            emit = 0;
+        }
+        if (DATA_T == 0) {
+            if (emit == 0xFFFFu) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t c = p[i];
-        if (c == '>' && p[i - 1] == '\n') {
-            s = 1;
-            if (DATA_T == 1 && SEQ_SEP) stage[o++] = 0;
-            if (DATA_T == 0 && boundaries) {
-                boundaries[fr.bd_off + t_recbase[tile] + ro] = pbase + o;
-                ro++;
+                for (int i = 0; i < 16; i++) stage[o + i] = (uint8_t)((ck.codes[i >> 2] >> (8 * (i & 3))) & 3u);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if ((emit >> i) & 1u) stage[o++] = (uint8_t)((ck.codes[i >> 2] >> (8 * (i & 3))) & 3u);
             }
-        } else if (c == '\n') {
-            s &= 2u;
         } else {
-            if (c == 'c' && (s & 1u) && is_capsid(p + i)) s |= 2u;
-            if (s == 0) {
-                const int code = sym_code<DATA_T>(c, aa_lut);
-                if (code >= 0) stage[o++] = (uint8_t)code;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if ((emit >> i) & 1u) stage[o++] = aa_lut[p[i]];
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) {
+            const uint32_t c = p[i];
+            if (c == '>' && p[i - 1] == '\n') {
+                s = 1;
+                if (DATA_T == 1 && SEQ_SEP) stage[o++] = 0;
+                if (DATA_T == 0 && boundaries) {
+                    boundaries[fr.bd_off + t_recbase[tile] + ro] = pbase + o;
+                    ro++;
+                }
+            } else if (c == '\n') {
+                s &= 2u;
+            } else {
+                if (c == 'c' && (s & 1u) && is_capsid(p + i)) s |= 2u;
+                if (s == 0) {
+                    const int code = sym_code<DATA_T>(c, aa_lut);
+                    if (code >= 0) stage[o++] = (uint8_t)code;
+                }
             }
         }
     }

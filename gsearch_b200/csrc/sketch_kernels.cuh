@@ -46,9 +46,9 @@ struct ListEntry {
 // per-genome device-side job state for the prob path
 struct ProbJob {
     uint32_t file;       // index into FileDesc / FileResult
-    uint32_t nslot1;     // filter slots (2 bits each, 16 per word)
-    uint32_t *bitmap;    // collision-bit filter
-    uint32_t *n_coll;    // occurrences that found their filter slot already seen
+    uint32_t nslot1;     // filter size in 2-bit units (16 per 32-bit word)
+    uint32_t *bitmap;    // blocked filter: per word 24 "seen" bits + 8 "repeated" flags
+    uint32_t *n_coll;    // occurrences that found their seen bits already set (statistics)
     uint32_t cap2_max;   // allocated exact-set capacity
     uint32_t *cap2;      // exact-set capacity in use (sized on device from n_coll)
     uint32_t *table;     // exact set: fingerprint | position+1 of the first occurrence
@@ -247,7 +247,7 @@ __global__ void k_prob_setup(const ProbJob *__restrict__ jobs, uint32_t njobs,
 // the same slot.
 struct OvfEntry {   // a k-mer occurrence that must go through the exact set
     uint64_t kmer;
-    uint32_t pos1;  // fingerprint | position + 1 : the set entry to write
+    uint32_t pos1;  // position + 1 of this occurrence (the set entry is fingerprint | pos1)
     uint32_t cand;  // first draw below the bound?
 };
 
@@ -330,8 +330,34 @@ __device__ __forceinline__ ChunkCtx chunk_ctx(const uint32_t *__restrict__ chunk
     return c;
 }
 
-// ---- pass A: mark.  Two bits per filter slot: bit0 = "seen", bit1 = "seen more than once".
-// One returning atomicOr per k-mer on an L2-resident bitmap, all independent (no probing).
+// ---- the first-level filter.  One 32-bit word per k-mer (chosen by a cheap hash of the k-mer):
+// bits 0..23 are "seen" bits, of which a k-mer owns two; bits 24..31 are "repeated" flags, of
+// which it owns one.  mark: old = atomicOr(word, seen pair); if both were already set the
+// occurrence is not the first one mapping there and raises the k-mer's flag.  Atomics on one
+// word are totally ordered, so a k-mer that occurs twice ALWAYS ends with its flag raised;
+// a k-mer whose flag is down after the pass occurs exactly once (weight 1, exactly).  A false
+// flag only sends a unique k-mer through the exact set.
+struct FilterPos {
+    uint32_t word, seen, flag;
+};
+template <typename KT>
+__device__ __forceinline__ FilterPos filter_pos(KT kmer, uint32_t nwords) {
+    uint32_t h = (uint32_t)kmer * 0x9E3779B1u;
+    if (sizeof(KT) == 8) h += (uint32_t)((uint64_t)kmer >> 32) * 0x85EBCA77u;
+    h ^= h >> 16;
+    h *= 0xC2B2AE3Du;
+    h ^= h >> 13;
+    uint32_t g = h * 0x27D4EB2Fu;
+    g ^= g >> 15;
+    FilterPos f;
+    f.word = __umulhi(h, nwords);
+    f.seen = (1u << (((g & 0xFFu) * 24u) >> 8)) | (1u << ((((g >> 8) & 0xFFu) * 24u) >> 8));
+    f.flag = 1u << (24u + ((g >> 16) & 7u));
+    return f;
+}
+
+// ---- pass A: mark.  One returning atomicOr per k-mer on an L2-resident filter, all
+// independent (no probing); no SplitMix64 here, only the rolling k-mer and a cheap hash.
 template <class Src, typename KT>
 __global__ void __launch_bounds__(kK2Threads)
 k2_prob_mark(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
@@ -342,75 +368,46 @@ k2_prob_mark(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chun
     const ProbJob job = jobs[j];
     const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j);
     if (!cx.live) return;
-    __shared__ uint32_t s_coll;
-    if (threadIdx.x == 0) s_coll = 0;
-    __syncthreads();
+    const uint32_t nwords = job.nslot1 >> 4;
     Src src;
     src.init(cx.sv, cx.p0, sc.k);
     uint32_t ncoll = 0;
+#pragma unroll 1
     for (uint32_t blk = 0; blk < kRun / kG; blk++) {
-        uint32_t slot[kG], act = 0;
-        if (__all_sync(0xffffffffu, src.all_valid(blk * kG, kG))) {
-            act = (1u << kG) - 1;
+        FilterPos fp[kG];
+        uint32_t act = 0;
+        const bool fast = __all_sync(0xffffffffu, src.all_valid(blk * kG, kG));
 #pragma unroll
-            for (int g = 0; g < kG; g++) {
-                KT kmer;
-                src.step_fast(blk * kG + g, kmer);
-                const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
-                slot[g] = __umulhi((uint32_t)s0, job.nslot1);
-            }
-        } else {
-#pragma unroll
-            for (int g = 0; g < kG; g++) {
-                KT kmer;
-                const bool valid = src.step(blk * kG + g, kmer);
-                const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
-                slot[g] = __umulhi((uint32_t)s0, job.nslot1);
-                if (valid) act |= 1u << g;
-            }
+        for (int g = 0; g < kG; g++) {
+            KT kmer;
+            const bool valid = fast ? src.step_fast(blk * kG + g, kmer) : src.step(blk * kG + g, kmer);
+            fp[g] = filter_pos<KT>(kmer, nwords);
+            if (valid) act |= 1u << g;
         }
         uint32_t old[kG];
 #pragma unroll
         for (int g = 0; g < kG; g++)
-            if (act & (1u << g)) old[g] = atomicOr(&job.bitmap[slot[g] >> 4], 1u << (2 * (slot[g] & 15u)));
+            if (act & (1u << g)) old[g] = atomicOr(&job.bitmap[fp[g].word], fp[g].seen);
 #pragma unroll
         for (int g = 0; g < kG; g++) {
-            if (act & (1u << g)) {
-                const uint32_t sh = 2 * (slot[g] & 15u);
-                if ((old[g] >> sh) & 1u) {
-                    ncoll++;
-                    if (!((old[g] >> sh) & 2u)) atomicOr(&job.bitmap[slot[g] >> 4], 2u << sh);
-                }
+            if ((act & (1u << g)) && (old[g] & fp[g].seen) == fp[g].seen) {
+                ncoll++;
+                if (!(old[g] & fp[g].flag)) atomicOr(&job.bitmap[fp[g].word], fp[g].flag);
             }
         }
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) ncoll += __shfl_xor_sync(0xffffffffu, ncoll, d);
-    if (lane_id() == 0 && ncoll) atomicAdd(&s_coll, ncoll);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_coll) atomicAdd(job.n_coll, s_coll);
+    if (lane_id() == 0 && ncoll) atomicAdd(job.n_coll, ncoll);
 }
 
-// ---- between the passes: size and clear the exact set from the number of collisions
-__global__ void __launch_bounds__(256)
-k2_prob_mid(const ProbJob *__restrict__ jobs, uint32_t njobs) {
-    const uint32_t j = blockIdx.y;
-    if (j >= njobs) return;
-    const ProbJob job = jobs[j];
-    // every occurrence in a collided filter slot goes to the exact set: at most 2 * n_coll k-mers
-    const uint64_t want = 4ull * (uint64_t)(*job.n_coll) + 1024ull;
-    const uint32_t cap2 = (uint32_t)(want < job.cap2_max ? want : job.cap2_max);
-    uint4 *t4 = reinterpret_cast<uint4 *>(job.table);
-    const size_t n4 = ((size_t)cap2 + 3) / 4;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-        t4[i] = z;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *job.cap2 = cap2;
-}
+// ---- pass B: classify.  A k-mer whose flag is down is unique (weight 1, exactly) and is kept
+// only if its first draw can be below the bound ("light"); a k-mer whose flag is up goes
+// through the exact set.  The scan only builds two 32-bit masks per thread; the few flagged
+// positions are re-extracted from the packed sequence afterwards and leave through a CTA
+// stage in shared memory (one global atomic per list and CTA).
+constexpr uint32_t kStageHalf = kStageCap / 2;
 
-// ---- pass B: classify.  A k-mer whose filter slot was seen exactly once is unique (weight 1,
-// exactly); every other occurrence goes through the exact set (fingerprint | position, verified
-// against the sequence), which therefore holds only the few k-mers that share a filter slot.
 template <class Src, typename KT>
 __global__ void __launch_bounds__(kK2Threads, 3)
 k2_prob_classify(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
@@ -423,106 +420,132 @@ k2_prob_classify(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ 
     const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j);
     if (!cx.live) return;
     const ProbBound pb = bound[j];
-    // CTA stage (shared memory): unique light k-mers grow from the bottom, occurrences that must
-    // go through the exact set grow from the top; each side is flushed with ONE global atomic.
     extern __shared__ __align__(16) uint8_t s_raw[];
-    ListEntry *s_lo = reinterpret_cast<ListEntry *>(s_raw);
-    OvfEntry *s_hi = reinterpret_cast<OvfEntry *>(s_raw);  // same 16-byte cells, indexed from the top
+    ListEntry *s_lo = reinterpret_cast<ListEntry *>(s_raw);              // [kStageHalf] unique light k-mers
+    OvfEntry *s_hi = reinterpret_cast<OvfEntry *>(s_raw) + kStageHalf;   // [kStageHalf] flagged occurrences
     __shared__ uint32_t s_nlo, s_nhi, s_blo, s_bhi;
     if (threadIdx.x == 0) {
         s_nlo = 0;
         s_nhi = 0;
     }
     __syncthreads();
+    const uint32_t nwords = job.nslot1 >> 4;
     Src src;
     src.init(cx.sv, cx.p0, sc.k);
+    uint32_t m_light = 0, m_coll = 0, m_cand = 0;  // bit i = k-mer starting at p0 + i
+#pragma unroll 1
     for (uint32_t blk = 0; blk < kRun / kG; blk++) {
-        KT kmer[kG];
-        uint32_t slot[kG], fp[kG];
+        uint32_t word[kG], flag[kG];
         uint32_t act = 0, cand = 0;
         const bool fast = __all_sync(0xffffffffu, src.all_valid(blk * kG, kG));
 #pragma unroll
         for (int g = 0; g < kG; g++) {
-            const uint32_t i = blk * kG + g;
-            const bool valid = fast ? src.step_fast(i, kmer[g]) : src.step(i, kmer[g]);
+            KT kmer;
+            const bool valid = fast ? src.step_fast(blk * kG + g, kmer) : src.step(blk * kG + g, kmer);
+            const FilterPos fp = filter_pos<KT>(kmer, nwords);
+            word[g] = fp.word;
+            flag[g] = fp.flag;
             uint64_t s0;
-            const uint64_t out1 = first_output(nohash_seed<KT>(kmer[g], sc.spec_flags), s0);
-            const uint64_t U = out1 >> 12;
+            const uint64_t U = first_output(nohash_seed<KT>(kmer, sc.spec_flags), s0) >> 12;
             if ((U < pb.uT) | (U >= sc.u_slow)) cand |= 1u << g;
-            slot[g] = __umulhi((uint32_t)s0, job.nslot1);
-            fp[g] = (uint32_t)s0 << 24;
             if (valid) act |= 1u << g;
         }
-        // filter words: independent loads
         uint32_t w[kG];
 #pragma unroll
-        for (int g = 0; g < kG; g++) w[g] = (act & (1u << g)) ? __ldcg(&job.bitmap[slot[g] >> 4]) : 0u;
-        uint32_t lo_m = 0, hi_m = 0;
+        for (int g = 0; g < kG; g++) w[g] = (act & (1u << g)) ? __ldcg(&job.bitmap[word[g]]) : 0u;
+        uint32_t coll = 0;
 #pragma unroll
-        for (int g = 0; g < kG; g++) {
-            const uint32_t coll = (w[g] >> (2 * (slot[g] & 15u))) & 2u;
-            if (act & (1u << g)) {
-                if (coll) hi_m |= 1u << g;                     // shares its filter slot: exact set
-                else if ((cand >> g) & 1u) lo_m |= 1u << g;    // unique (weight 1) and light
-            }
-        }
-        // reserve cells in the stage: one shared-memory atomic per warp and side
-        {
-            const uint32_t lane = lane_id();
-            uint32_t v = __popc(lo_m) | (__popc(hi_m) << 16), incl = v;
+        for (int g = 0; g < kG; g++)
+            if (w[g] & flag[g]) coll |= 1u << g;
+        m_coll |= coll << (blk * kG);
+        m_cand |= (cand & act) << (blk * kG);
+        m_light |= (cand & act & ~coll) << (blk * kG);
+    }
+    // ---- emission: reserve stage cells (one shared atomic per warp and side)
+    const uint32_t lane = lane_id();
+    const uint32_t v = __popc(m_light) | (__popc(m_coll) << 16);
+    uint32_t incl = v;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (uint32_t)d) incl += up;
-            }
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t blo = 0, bhi = 0;
-            if (lane == 31) {
-                if (tot & 0xFFFFu) blo = atomicAdd(&s_nlo, tot & 0xFFFFu);
-                if (tot >> 16) bhi = atomicAdd(&s_nhi, tot >> 16);
-            }
-            blo = __shfl_sync(0xffffffffu, blo, 31) + ((incl - v) & 0xFFFFu);
-            bhi = __shfl_sync(0xffffffffu, bhi, 31) + ((incl - v) >> 16);
-#pragma unroll
-            for (int g = 0; g < kG; g++) {
-                if (lo_m & (1u << g)) {
-                    ListEntry e;
-                    e.kmer = (uint64_t)kmer[g];
-                    e.slot = kNoSlot;
-                    e.kind = 0;
-                    s_lo[blo++] = e;
-                } else if (hi_m & (1u << g)) {
-                    OvfEntry e;
-                    e.kmer = (uint64_t)kmer[g];
-                    e.pos1 = fp[g] | (cx.p0 + blk * kG + g + 1);
-                    e.cand = (cand >> g) & 1u;
-                    s_hi[kStageCap - 1 - bhi++] = e;
-                }
-            }
-        }
-        __syncthreads();
-        if (s_nlo + s_nhi > kStageCap - kK2Threads * kG || blk + 1 == kRun / kG) {
-            const uint32_t nlo = s_nlo, nhi = s_nhi;
-            if (threadIdx.x == 0) s_blo = nlo ? atomicAdd(job.list_n, nlo) : 0u;
-            if (threadIdx.x == 32) s_bhi = nhi ? atomicAdd(job.ovf_n, nhi) : 0u;
-            __syncthreads();
-            const uint32_t glo = s_blo, ghi = s_bhi;
-            for (uint32_t t = threadIdx.x; t < nlo; t += kK2Threads) {
-                if (glo + t < job.list_cap) job.list[glo + t] = s_lo[t];
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t blo = 0, bhi = 0;
+    if (lane == 31) {
+        if (tot & 0xFFFFu) blo = atomicAdd(&s_nlo, tot & 0xFFFFu);
+        if (tot >> 16) bhi = atomicAdd(&s_nhi, tot >> 16);
+    }
+    blo = __shfl_sync(0xffffffffu, blo, 31) + ((incl - v) & 0xFFFFu);
+    bhi = __shfl_sync(0xffffffffu, bhi, 31) + ((incl - v) >> 16);
+    uint32_t todo = m_light | m_coll;
+    while (todo) {
+        const uint32_t i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t pos = cx.p0 + i;
+        const KT kmer = Src::kmer_at(cx.sv, pos, sc.k);
+        if ((m_coll >> i) & 1u) {
+            OvfEntry e;
+            e.kmer = (uint64_t)kmer;
+            e.pos1 = pos + 1;
+            e.cand = (m_cand >> i) & 1u;
+            if (bhi < kStageHalf) {
+                s_hi[bhi] = e;
+            } else {  // stage full (very repetitive chunk): straight to the global list
+                const uint32_t at = atomicAdd(job.ovf_n, 1u);
+                if (at < job.ovf_cap) job.ovf[at] = e;
                 else atomicOr(&overflow[j], 1u);
             }
-            for (uint32_t t = threadIdx.x; t < nhi; t += kK2Threads) {
-                if (ghi + t < job.ovf_cap) job.ovf[ghi + t] = s_hi[kStageCap - 1 - t];
+            bhi++;
+        } else {
+            ListEntry e;
+            e.kmer = (uint64_t)kmer;
+            e.slot = kNoSlot;
+            e.kind = 0;
+            if (blo < kStageHalf) {
+                s_lo[blo] = e;
+            } else {
+                const uint32_t at = atomicAdd(job.list_n, 1u);
+                if (at < job.list_cap) job.list[at] = e;
                 else atomicOr(&overflow[j], 1u);
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                s_nlo = 0;
-                s_nhi = 0;
-            }
-            __syncthreads();
+            blo++;
         }
     }
+    __syncthreads();
+    const uint32_t nlo = s_nlo < kStageHalf ? s_nlo : kStageHalf;
+    const uint32_t nhi = s_nhi < kStageHalf ? s_nhi : kStageHalf;
+    if (threadIdx.x == 0) s_blo = nlo ? atomicAdd(job.list_n, nlo) : 0u;
+    if (threadIdx.x == 32) s_bhi = nhi ? atomicAdd(job.ovf_n, nhi) : 0u;
+    __syncthreads();
+    const uint32_t glo = s_blo, ghi = s_bhi;
+    for (uint32_t t = threadIdx.x; t < nlo; t += kK2Threads) {
+        if (glo + t < job.list_cap) job.list[glo + t] = s_lo[t];
+        else atomicOr(&overflow[j], 1u);
+    }
+    for (uint32_t t = threadIdx.x; t < nhi; t += kK2Threads) {
+        if (ghi + t < job.ovf_cap) job.ovf[ghi + t] = s_hi[t];
+        else atomicOr(&overflow[j], 1u);
+    }
+}
+
+// ---- between classify and the exact set: size and clear the set from the number of flagged
+// occurrences (every distinct k-mer among them takes one entry; load factor <= 1/2)
+__global__ void __launch_bounds__(256)
+k2_prob_mid(const ProbJob *__restrict__ jobs, uint32_t njobs) {
+    const uint32_t j = blockIdx.y;
+    if (j >= njobs) return;
+    const ProbJob job = jobs[j];
+    uint32_t novf = *job.ovf_n;
+    if (novf > job.ovf_cap) novf = job.ovf_cap;
+    const uint64_t want = 2ull * (uint64_t)novf + 1024ull;
+    const uint32_t cap2 = (uint32_t)(want < job.cap2_max ? want : job.cap2_max);
+    uint4 *t4 = reinterpret_cast<uint4 *>(job.table);
+    const size_t n4 = ((size_t)cap2 + 3) / 4;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        t4[i] = z;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *job.cap2 = cap2;
 }
 
 // exact-set insertions for the occurrences that share a filter slot: one per thread,
@@ -558,9 +581,9 @@ k2_prob_overflow(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileDes
         if (act) {
             const OvfEntry oe = job.ovf[e];
             kmer = (KT)oe.kmer;
-            entry = oe.pos1;
             cand = oe.cand != 0;
             const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
+            entry = ((uint32_t)s0 << 24) | oe.pos1;
             slot = __umulhi((uint32_t)(s0 >> 32), cap2);
         }
         while (act) {

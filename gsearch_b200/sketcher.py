@@ -85,7 +85,8 @@ class Sketcher:
 
     def kernel_times(self):
         """-> {family: (total ms, timed spans)} measured with CUDA events on the launch stream"""
-        ms = np.zeros(4, dtype=np.float64)
-        n = np.zeros(4, dtype=np.uint64)
+        ms = np.zeros(8, dtype=np.float64)
+        n = np.zeros(8, dtype=np.uint64)
         _lib.lib().gsb_sketcher_kernel_times(self._h, _ptr(ms), _ptr(n))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("k1_pack", "k2_scan", "k3_slots", "reset"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(
+            ("k1_pack", "k2_scan", "k3_slots", "reset", "k2_mark", "k2_classify", "k2_exact", "k1_summary"))}

@@ -146,11 +146,14 @@ GSB_API uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h);
 /* number of genomes whose early-stop bound had to be widened and re-run so far */
 GSB_API uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h);
 /* Optional device timing of the kernel families (CUDA events on the launching stream):
- * index 0 = K1 FASTA pack, 1 = K2 k-mer scan (the dominant kernel), 2 = K3 slot update +
- * finalize, 3 = per-group reset.  enable(…, 1) also zeroes the accumulators.           */
+ * index 0 = K1 FASTA pack, 1 = K2 k-mer scan (the dominant kernel family), 2 = K3 slot
+ * update + finalize, 3 = per-group reset; 4..6 split K2 into its filter-mark, classify and
+ * exact-set kernels, 7 = the tile-summary part of K1.  enable(…, 1) also zeroes the
+ * accumulators.                                                                          */
+#define GSB_NB_TIMERS 8
 GSB_API void gsb_sketcher_enable_timing(gsb_sketcher *h, int on);
-GSB_API void gsb_sketcher_kernel_times(const gsb_sketcher *h, double *ms_out /*[4]*/,
-                                       uint64_t *launches_out /*[4]*/);
+GSB_API void gsb_sketcher_kernel_times(const gsb_sketcher *h, double *ms_out /*[GSB_NB_TIMERS]*/,
+                                       uint64_t *launches_out /*[GSB_NB_TIMERS]*/);
 
 /* ------------------------------------------------------------------------- */
 /* distance                                                                   */
