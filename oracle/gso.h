@@ -122,6 +122,11 @@ gso_hnsw *gso_hnsw_new(uint32_t max_nb_conn, uint64_t capacity, uint32_t max_lay
 void gso_hnsw_free(gso_hnsw *h);
 /* sequential insertion in the given order; sigs are copied */
 int gso_hnsw_insert(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n);
+/* deterministic wave insertion (see hnsw.c): what the GPU builder is checked against;
+ * wave_max = 1 is identical to gso_hnsw_insert */
+int gso_hnsw_insert_waves(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
+                          uint32_t wave_max);
+uint32_t gso_hnsw_wave_size(uint64_t nb_point, uint32_t wave_max);
 uint64_t gso_hnsw_nb_point(const gso_hnsw *h);
 uint64_t gso_hnsw_nb_eval(const gso_hnsw *h); /* distance evaluations so far */
 /* search one query; returns number of neighbours written (<= knbn) */

@@ -446,6 +446,168 @@ int gso_hnsw_insert(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t
     return rc;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Wave insertion: the deterministic restatement of `parallel_insert` that the GPU builder
+ * follows (gsearch_b200/csrc/hnsw_insert.cuh).  The reference inserts with rayon threads that
+ * see each other's partial updates in scheduling order (src/dna/dnasketch.rs:435); here the
+ * points are taken in waves, in the given order:
+ *   wave size  W = clamp(nb_point / 4, 1, wave_max) (so a wave of 1 == sequential insertion);
+ *   phase A    every point of the wave searches the graph as it was BEFORE the wave (greedy
+ *              descent, search_layer(ef_c) per layer) and then also sees the EARLIER points
+ *              of its own wave, by exact distance, as if search_layer had met them last;
+ *              select_neighbours as usual (points of the wave have no lists yet); the entry of
+ *              the next lower layer is the nearest selected point that is not of this wave;
+ *   phase B    in order: the point's lists are written, reverse updates applied
+ *              (list_add_sorted_shrink keeps the M / 2M smallest by (distance, index), so the
+ *              result does not depend on the order of arrivals), entry point updated.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint32_t n[17];
+    sel *l[17];
+} wave_sel;
+
+static int add_point(gso_hnsw *h, const void *sig, uint64_t id) {
+    if (h->n >= h->capacity) return 8;
+    if (grow(h, h->n + 1)) return 4;
+    const uint32_t np = (uint32_t)h->n;
+    const uint32_t level = gen_level(h);
+    memcpy(h->data + (uint64_t)np * h->row, sig, h->row);
+    h->ids[np] = id;
+    h->level[np] = (uint8_t)level;
+    h->rank[np] = h->layer_count[level]++;
+    h->nbrs[np] = (nlist *)calloc(level + 1, sizeof(nlist));
+    for (uint32_t l = 0; l <= level; l++) {
+        uint32_t cap = (l > 0 ? h->M : 2 * h->M) + 1;
+        h->nbrs[np][l].idx = (uint32_t *)malloc(cap * sizeof(uint32_t));
+        h->nbrs[np][l].dist = (float *)malloc(cap * sizeof(float));
+        h->nbrs[np][l].n = 0;
+    }
+    h->n++;
+    return 0;
+}
+
+static void wave_phase_a(gso_hnsw *h, uint32_t np, uint32_t first, uint32_t entry, heap *ret,
+                         heap *cand, sel *selbuf, wave_sel *ws) {
+    const uint32_t level = h->level[np];
+    const void *q = pt(h, np);
+    uint32_t ep = entry;
+    const uint32_t max_level_observed = h->level[ep];
+    float dist_to_entry = dist_qp(h, q, ep);
+    for (int l = (int)max_level_observed; l >= (int)level + 1; l--) {
+        search_layer(h, q, ep, 1, (uint32_t)l, ret, cand);
+        if (ret->n > 0) {
+            hitem e = heap_pop(ret);
+            float tmp = dist_qp(h, q, e.p);
+            if (tmp < dist_to_entry) {
+                ep = e.p;
+                dist_to_entry = tmp;
+            }
+        }
+    }
+    const int top = (int)(level < max_level_observed ? level : max_level_observed);
+    for (int l = top; l >= 0; l--) {
+        search_layer(h, q, ep, h->ef_c, (uint32_t)l, ret, cand);
+        for (uint32_t m = first; m < np; m++) { /* earlier points of this wave */
+            if (h->level[m] < (uint32_t)l) continue;
+            const float fd = ret->a[0].d;
+            const float ed = dist_qp(h, q, m);
+            if (ed < fd || ret->n < h->ef_c) {
+                heap_push(ret, (hitem){ed, m});
+                if (ret->n > h->ef_c) (void)heap_pop(ret);
+            }
+        }
+        cand->n = 0;
+        for (uint32_t i = 0; i < ret->n; i++) heap_push(cand, (hitem){-ret->a[i].d, ret->a[i].p});
+        const uint32_t nb_conn = l == 0 ? 2 * h->M : h->M;
+        const int extend_c = l == 0 ? (int)h->extend_candidates : 0;
+        uint32_t ns = select_neighbours(h, q, cand, nb_conn, extend_c, (uint32_t)l, selbuf);
+        qsort(selbuf, ns, sizeof(sel), cmp_sel);
+        ws->n[l] = ns;
+        ws->l[l] = (sel *)malloc((ns ? ns : 1) * sizeof(sel));
+        memcpy(ws->l[l], selbuf, ns * sizeof(sel));
+        for (uint32_t i = 0; i < ns; i++)
+            if (selbuf[i].p < first) {
+                ep = selbuf[i].p;
+                break;
+            }
+    }
+}
+
+static void wave_phase_b(gso_hnsw *h, uint32_t np, wave_sel *ws) {
+    const uint32_t level = h->level[np];
+    for (uint32_t l = 0; l <= level && l < 17; l++) {
+        nlist *nl = &h->nbrs[np][l];
+        /* arrivals from earlier points of the wave may already be there: merge */
+        for (uint32_t i = 0; i < ws->n[l]; i++) {
+            /* own selection: sorted insert without the duplicate test hitting (distinct points) */
+            uint32_t pos = nl->n;
+            const float d = ws->l[l][i].d;
+            const uint32_t p = ws->l[l][i].p;
+            while (pos > 0 && (nl->dist[pos - 1] > d || (nl->dist[pos - 1] == d && nl->idx[pos - 1] > p))) {
+                nl->dist[pos] = nl->dist[pos - 1];
+                nl->idx[pos] = nl->idx[pos - 1];
+                pos--;
+            }
+            nl->dist[pos] = d;
+            nl->idx[pos] = p;
+            nl->n++;
+        }
+    }
+    for (int l = (int)level; l >= 0; l--) {
+        for (uint32_t i = 0; i < ws->n[l]; i++) {
+            const uint32_t qp = ws->l[l][i].p;
+            if (qp == np) continue;
+            if ((uint32_t)l > h->level[qp]) continue;
+            list_add_sorted_shrink(h, qp, (uint32_t)l, np, ws->l[l][i].d);
+        }
+    }
+    if (level > h->level[h->entry]) h->entry = np;
+}
+
+uint32_t gso_hnsw_wave_size(uint64_t nb_point, uint32_t wave_max) {
+    uint64_t w = nb_point / 4;
+    if (w < 1) w = 1;
+    if (w > wave_max) w = wave_max;
+    return (uint32_t)w;
+}
+
+int gso_hnsw_insert_waves(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
+                          uint32_t wave_max) {
+    heap ret = {0}, cand = {0};
+    sel *selbuf = (sel *)malloc((2 * h->M + 2) * sizeof(sel));
+    int rc = 0;
+    uint64_t i = 0;
+    if (wave_max < 1) wave_max = 1;
+    while (i < n && !rc) {
+        if (h->entry < 0) { /* first point of the index: becomes the entry point */
+            rc = add_point(h, (const uint8_t *)sigs + i * h->row, ids[i]);
+            if (!rc) h->entry = (int64_t)(h->n - 1);
+            i++;
+            continue;
+        }
+        uint64_t W = gso_hnsw_wave_size(h->n, wave_max);
+        if (W > n - i) W = n - i;
+        const uint32_t first = (uint32_t)h->n;
+        for (uint64_t t = 0; t < W && !rc; t++)
+            rc = add_point(h, (const uint8_t *)sigs + (i + t) * h->row, ids[i + t]);
+        if (rc) break;
+        wave_sel *ws = (wave_sel *)calloc(W, sizeof(wave_sel));
+        const uint32_t entry = (uint32_t)h->entry;
+        for (uint64_t t = 0; t < W; t++)
+            wave_phase_a(h, first + (uint32_t)t, first, entry, &ret, &cand, selbuf, &ws[t]);
+        for (uint64_t t = 0; t < W; t++) {
+            wave_phase_b(h, first + (uint32_t)t, &ws[t]);
+            for (int l = 0; l < 17; l++) free(ws[t].l[l]);
+        }
+        free(ws);
+        i += W;
+    }
+    free(selbuf);
+    free(ret.a);
+    free(cand.a);
+    return rc;
+}
+
 static uint32_t search_one(gso_hnsw *h, const void *q, uint32_t knbn, uint32_t ef_arg,
                            gso_neighbour *out, heap *ret, heap *cand) {
     if (h->entry < 0) return 0;

@@ -64,6 +64,9 @@ def L():
                                      C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
         lib.gso_hnsw_free.argtypes = [C.c_void_p]
         lib.gso_hnsw_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.gso_hnsw_insert_waves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        lib.gso_hnsw_wave_size.argtypes = [C.c_uint64, C.c_uint32]
+        lib.gso_hnsw_wave_size.restype = C.c_uint32
         lib.gso_hnsw_nb_point.restype = C.c_uint64
         lib.gso_hnsw_nb_point.argtypes = [C.c_void_p]
         lib.gso_hnsw_nb_eval.restype = C.c_uint64
@@ -214,6 +217,12 @@ class Hnsw:
         sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
         ids = np.ascontiguousarray(ids, dtype=np.uint64)
         rc = L().gso_hnsw_insert(self.h, _p(sigs), _p(ids), len(ids))
+        assert rc == 0, rc
+
+    def insert_waves(self, sigs, ids, wave_max):
+        sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        rc = L().gso_hnsw_insert_waves(self.h, _p(sigs), _p(ids), len(ids), wave_max)
         assert rc == 0, rc
 
     def nb_point(self):

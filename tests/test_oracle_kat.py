@@ -231,3 +231,60 @@ def test_sig_type_table():
     assert [O.sig_type(k, 64, 0, 0) for k in (8, 14, 15, 16, 17, 21, 31)] == [0, 0, 1, 0, 1, 1, 1]
     assert [O.sig_type(k, 64, 0, 1) for k in (3, 6, 7, 12)] == [0, 0, 1, 1]
     assert O.sig_type(21, 64, 2, 0) == 2 and O.sig_type(7, 64, 2, 1) == 2
+
+
+def _family_sigs(n, S, seed=0, fam=8):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(1, 2**40, (n, S)).astype(np.uint64)
+    for f in range(0, n, fam):
+        for j in range(1, min(fam, n - f)):
+            keep = rng.random(S) < (0.9 - 0.8 * j / fam)
+            base[f + j] = np.where(keep, base[f], base[f + j])
+    return base
+
+
+def _tree_sigs(n, S, seed=0):
+    """signatures with graded distances: every point copies a random share of the slots of a
+    random earlier point (a random recursive tree), then the order is shuffled"""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(1, 2**40, (n, S)).astype(np.uint64)
+    for i in range(1, n):
+        par = int(rng.integers(0, i))
+        keep = rng.random(S) < rng.uniform(0.5, 0.95)
+        base[i] = np.where(keep, base[par], base[i])
+    return base[rng.permutation(n)]
+
+
+def test_hnsw_wave_insert_of_one_is_sequential_insert(oracle):
+    """gso_hnsw_insert_waves(wave_max=1) must rebuild exactly the graph of the sequential insert."""
+    base = _family_sigs(400, 128)
+    ids = np.arange(400, dtype=np.uint64) + 1000
+    a = oracle.Hnsw(8, 32, 128, np.uint64)
+    a.insert(base, ids)
+    b = oracle.Hnsw(8, 32, 128, np.uint64)
+    b.insert_waves(base, ids, 1)
+    ga, gb = a.export(), b.export()
+    assert ga["entry_point"] == gb["entry_point"]
+    for k in ("levels", "ranks", "ids", "nbr_offsets", "nbr_index", "nbr_dist"):
+        assert np.array_equal(ga[k], gb[k]), k
+
+
+def test_hnsw_wave_insert_keeps_recall(oracle):
+    """Points of one wave do not see each other's lists, only each other's data; recall against
+    brute force must stay at the level of the sequential build."""
+    base = _tree_sigs(800, 128, seed=3)
+    ids = np.arange(800, dtype=np.uint64)
+    qi = np.arange(0, 800, 12)[:64]
+    D = oracle.hamming_matrix(base[qi], base)
+    k = 4
+    recalls = []
+    for wave in (1, 148):
+        h = oracle.Hnsw(12, 48, 128, np.uint64)
+        h.insert_waves(base, ids, wave)
+        out, cnt, _ = h.search(base[qi], k, 96)
+        hit = 0
+        for i in range(64):
+            kth = np.sort(D[i])[k - 1]
+            hit += sum(1 for j in range(cnt[i]) if out["distance"][i][j] <= kth)
+        recalls.append(hit / (64 * k))
+    assert recalls[1] >= recalls[0] - 0.02 and recalls[1] > 0.97, recalls
