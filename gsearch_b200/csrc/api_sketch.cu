@@ -18,8 +18,10 @@ using namespace gsb;
 
 namespace {
 
-constexpr int kMaxSlots = 8;
-// genomes in flight on the prob path (hash sets sized for L2); GSB_PROB_SLOTS overrides (1..8)
+constexpr int kMaxSlots = 16;  // two sets (one per group stream) of up to 8 genomes
+// genomes per group on the prob path; two groups are in flight, one per group stream, so that
+// the atomic-bound mark kernel of one overlaps the ALU-bound classify kernel of the other (filters
+// sized for L2); GSB_PROB_SLOTS overrides (1..8)
 // filter slots per input byte; GSB_PROB_LOAD overrides (2 .. 32)
 static double prob_load() {
     static double v = 0;
@@ -31,13 +33,19 @@ static double prob_load() {
     }
     return v;
 }
+// resident CTAs per SM of the persistent scan kernels (GSB_MARK_R / GSB_CLS_R override)
+static int env_int(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    int v = e ? atoi(e) : dflt;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
 static int prob_slots() {
     static int v = 0;
     if (!v) {
         const char *e = getenv("GSB_PROB_SLOTS");
-        v = e ? atoi(e) : 8;
+        v = e ? atoi(e) : 4;
         if (v < 1) v = 1;
-        if (v > kMaxSlots) v = kMaxSlots;
+        if (v > kMaxSlots / 2) v = kMaxSlots / 2;
     }
     return v;
 }
@@ -130,6 +138,10 @@ struct gsb_sketcher {
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     uint32_t file_base = 0;  // index of the sub-batch's first file in the caller's batch (messages)
+    cudaStream_t gstream[2] = {nullptr, nullptr};  // group streams of the prob path
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_k1;  // one per group: its files are packed
+    int nsm = 148;
 };
 
 namespace {
@@ -235,6 +247,10 @@ extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, 
         delete h;
         return GSB_ERR_CUDA;
     }
+    for (auto &g : h->gstream) cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    for (auto &e2 : h->ev_join) cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
+    cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device);
     *out = h;
     return GSB_OK;
 }
@@ -266,6 +282,12 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
     }
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (auto g : h->gstream)
+        if (g) cudaStreamDestroy(g);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto e2 : h->ev_k1) cudaEventDestroy(e2);
+    for (auto e2 : h->ev_join)
+        if (e2) cudaEventDestroy(e2);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     for (cudaEvent_t e : h->ev_h2d)
@@ -294,28 +316,48 @@ extern "C" void gsb_sketcher_kernel_times(const gsb_sketcher *h, double *ms_out,
 
 namespace {
 
+// K1 for the files [f0, f0 + nf) of the batch (tiles [tile0, tile0 + ntiles))
 template <int DATA_T, bool SEQ_SEP>
-void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t n, uint32_t ntiles,
-               bool want_bounds, uint32_t bd_cap, cudaStream_t st) {
+void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t f0, uint32_t nf, uint32_t tile0,
+               uint32_t ntiles, bool want_bounds, uint32_t bd_cap, cudaStream_t st) {
     Timed t_(h, CAT_K1, st);
+    const FileDesc *files = h->d_files.as<FileDesc>() + f0;
+    const uint32_t *tprefix = h->d_tile_prefix.as<uint32_t>() + f0;
+    FileResult *res = h->d_res.as<FileResult>() + f0;
     {
         Timed ts_(h, CAT_K1_SUMMARY, st);
         k1a_tile_summary<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
-            d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
-            h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>());
+            d_bytes, total, files, tprefix, nf, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(),
+            h->d_tnrec.as<uint16_t>(), tile0);
     }
-    k1b_resolve<<<(n * 32 + 127) / 128, 128, 0, st>>>(
-        h->d_files.as<FileDesc>(), n, d_bytes, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(),
-        h->d_tnrec.as<uint16_t>(), h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(),
-        h->d_trecbase.as<uint32_t>(), h->d_res.as<FileResult>(), h->d_misc.as<uint32_t>(), bd_cap,
-        want_bounds ? 1 : 0, (DATA_T == 1 && SEQ_SEP) ? 1 : 0);
+    k1b_resolve<<<(nf * 32 + 127) / 128, 128, 0, st>>>(
+        files, nf, d_bytes, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>(),
+        h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(), h->d_trecbase.as<uint32_t>(), res,
+        h->d_misc.as<uint32_t>(), bd_cap, want_bounds ? 1 : 0, (DATA_T == 1 && SEQ_SEP) ? 1 : 0);
     k1c_pack<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
-        d_bytes, total, h->d_files.as<FileDesc>(), h->d_tile_prefix.as<uint32_t>(), n,
-        h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(), h->d_trecbase.as<uint32_t>(),
-        h->d_res.as<FileResult>(), DATA_T == 0 ? h->d_packed.as<uint32_t>() : nullptr,
-        DATA_T == 1 ? h->d_packed.as<uint8_t>() : nullptr,
-        want_bounds ? h->d_bounds.as<uint32_t>() : nullptr);
+        d_bytes, total, files, tprefix, nf, h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(),
+        h->d_trecbase.as<uint32_t>(), res, DATA_T == 0 ? h->d_packed.as<uint32_t>() : nullptr,
+        DATA_T == 1 ? h->d_packed.as<uint8_t>() : nullptr, want_bounds ? h->d_bounds.as<uint32_t>() : nullptr,
+        tile0);
     h->launches += 3;
+}
+
+// what K1 needs to know about the batch (set by gsb_sketch_fasta_batch_dev before the first pass)
+struct K1Plan {
+    const uint8_t *d_bytes = nullptr;
+    uint64_t total = 0;
+    uint32_t bd_cap = 0;
+    bool pending = false;  // K1 has not run yet for this batch
+};
+
+void launch_k1_range(gsb_sketcher *h, const K1Plan &kp, uint32_t f0, uint32_t nf, cudaStream_t st) {
+    const uint32_t *htp = h->h_tile_prefix.as<uint32_t>();
+    const uint32_t tile0 = htp[f0], ntiles = htp[f0 + nf] - tile0;
+    if (!ntiles) return;
+    const bool dna = h->p.data_t == GSB_DATA_DNA, seq = !h->p.block_flag;
+    if (dna) launch_k1<0, false>(h, kp.d_bytes, kp.total, f0, nf, tile0, ntiles, seq, kp.bd_cap, st);
+    else if (seq) launch_k1<1, true>(h, kp.d_bytes, kp.total, f0, nf, tile0, ntiles, false, 0, st);
+    else launch_k1<1, false>(h, kp.d_bytes, kp.total, f0, nf, tile0, ntiles, false, 0, st);
 }
 
 template <class Src, typename KT>
@@ -330,13 +372,13 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
         k_prob_reset<<<dim3(296, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf);
     }
     if (nchunks) {
-        Timed t_(h, CAT_K2, st);
         {
             Timed tm_(h, CAT_K2_MARK, st);
-            k2_prob_mark<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+            const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * env_int("GSB_MARK_R", 2, 1, 8)));
+            k2_prob_mark<Src, KT><<<grid, kK2Threads, 0, st>>>(
                 jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
                 dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
         }
         static bool attr_set = false;
         if (!attr_set) {
@@ -346,10 +388,11 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
         }
         {
             Timed tc_(h, CAT_K2_CLASSIFY, st);
-            k2_prob_classify<Src, KT><<<nchunks, kK2Threads, kStageCap * sizeof(ListEntry), st>>>(
+            const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * env_int("GSB_CLS_R", 3, 1, 8)));
+            k2_prob_classify<Src, KT><<<grid, kK2Threads, kStageCap * sizeof(ListEntry), st>>>(
                 jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
                 dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf);
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, ovf, nchunks);
         }
         {
             Timed te_(h, CAT_K2_EXACT, st);
@@ -378,10 +421,11 @@ void launch_dens(gsb_sketcher *h, uint32_t njobs, uint32_t nchunks, bool dna, bo
     const FileResult *res = h->d_res.as<FileResult>();
     if (nchunks) {
         Timed t_(h, CAT_K2, st);
-        k2_optdens<Src, KT><<<nchunks, kK2Threads, 0, st>>>(
+        const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * 8));
+        k2_optdens<Src, KT><<<grid, kK2Threads, 0, st>>>(
             jobs, h->d_chunk_prefix.as<uint32_t>(), njobs, h->d_files.as<FileDesc>(), res,
             dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc);
+            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
     }
     Timed t3_(h, CAT_K3, st);
     k3_optdens_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (float *)d_sig, d_nb,
@@ -390,7 +434,7 @@ void launch_dens(gsb_sketcher *h, uint32_t njobs, uint32_t nchunks, bool dna, bo
 }
 
 int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vector<double> &tmult,
-             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st, K1Plan &kp) {
     const bool dna = h->p.data_t == GSB_DATA_DNA;
     const bool want_bounds = dna && !h->p.block_flag;
     const uint32_t n = (uint32_t)todo.size();
@@ -407,7 +451,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     const size_t filter_bytes_max = (((size_t)(prob_load() * (double)max_len) + 64) / 16 + 8) * 4;
     const size_t light_cap = (size_t)(3.0 * h->sc.m * h->sc.lnm8) + 65536;
     const size_t list_cap_max = std::min<size_t>(max_len + 64, light_cap + max_len / 2) + 64;
-    for (int s = 0; s < kSlots && s < (int)n; s++) {
+    for (int s = 0; s < 2 * kSlots && s < (int)n; s++) {
         ProbSlot &sl = h->slot[s];
         int rc;
         const void *old_cnt = sl.cnt.p, *old_list = sl.list.p, *old_misc = sl.misc.p;
@@ -445,7 +489,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
             if (s < kSlots && i < n) {
                 const uint32_t f = todo[i];
                 const size_t len = h_offsets[f + 1] - h_offsets[f];
-                ProbSlot &sl = h->slot[s];
+                ProbSlot &sl = h->slot[(g & 1) * kSlots + s];
                 ProbJob &j = hj[i];
                 j.file = f;
                 j.nslot1 = (uint32_t)(((size_t)(prob_load() * (double)len) + 64) & ~(size_t)15);
@@ -473,23 +517,48 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, hj, (size_t)n * sizeof(ProbJob), cudaMemcpyHostToDevice, st));
     GSB_CUDA_TRY(cudaMemcpyAsync(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (kSlots + 1) * 4,
                                  cudaMemcpyHostToDevice, st));
-    for (uint32_t g = 0; g < ngroups; g++) {
-        const uint32_t joff = g * kSlots, nj = std::min<uint32_t>(kSlots, n - joff);
-        const uint32_t cpoff = g * (kSlots + 1);
-        if (dna) {
-            if (h->kt32)
-                launch_prob_group<SrcDNA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, true,
-                                                              want_bounds, d_sig, d_nb, st);
-            else
-                launch_prob_group<SrcDNA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, true,
-                                                              want_bounds, d_sig, d_nb, st);
-        } else {
-            if (h->kt32)
-                launch_prob_group<SrcAA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, false, false,
-                                                             d_sig, d_nb, st);
-            else
-                launch_prob_group<SrcAA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, false, false,
-                                                             d_sig, d_nb, st);
+    // groups alternate between two streams (and two slot sets); everything before (K1, job
+    // descriptors) happened on `st`, everything after waits for both
+    GSB_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    for (auto gs : h->gstream) GSB_CUDA_TRY(cudaStreamWaitEvent(gs, h->ev_fork, 0));
+    {
+        Timed tp_(h, CAT_K2, st);
+        for (uint32_t g = 0; g < ngroups; g++) {
+            const uint32_t joff = g * kSlots, nj = std::min<uint32_t>(kSlots, n - joff);
+            const uint32_t cpoff = g * (kSlots + 1);
+            cudaStream_t gs = h->gstream[g & 1];
+            if (kp.pending) {
+                // first pass: todo is the whole batch in order, so group g = files [joff, joff + nj).
+                // K1 runs ahead on `st`, one group at a time, under the scan kernels of earlier groups.
+                launch_k1_range(h, kp, joff, nj, st);
+                if (h->ev_k1.size() <= g) {
+                    cudaEvent_t e = nullptr;
+                    GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->ev_k1.push_back(e);
+                }
+                GSB_CUDA_TRY(cudaEventRecord(h->ev_k1[g], st));
+                GSB_CUDA_TRY(cudaStreamWaitEvent(gs, h->ev_k1[g], 0));
+            }
+            if (dna) {
+                if (h->kt32)
+                    launch_prob_group<SrcDNA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, true,
+                                                                  want_bounds, d_sig, d_nb, gs);
+                else
+                    launch_prob_group<SrcDNA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, true,
+                                                                  want_bounds, d_sig, d_nb, gs);
+            } else {
+                if (h->kt32)
+                    launch_prob_group<SrcAA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, false,
+                                                                 false, d_sig, d_nb, gs);
+                else
+                    launch_prob_group<SrcAA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, false,
+                                                                 false, d_sig, d_nb, gs);
+            }
+        }
+        kp.pending = false;
+        for (int i = 0; i < 2; i++) {
+            GSB_CUDA_TRY(cudaEventRecord(h->ev_join[i], h->gstream[i]));
+            GSB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[i], 0));
         }
     }
     GSB_CUDA_TRY(cudaGetLastError());
@@ -613,22 +682,28 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_retry.p, 0, (size_t)n * 4, st));
     if (dna) GSB_CUDA_TRY(cudaMemsetAsync(h->d_packed.p, 0, packed_bytes, st));
-    if (ntiles) {
-        if (dna) launch_k1<0, false>(h, d_bytes, total, n, (uint32_t)ntiles, want_bounds, bd_cap, st);
-        else if (seq) launch_k1<1, true>(h, d_bytes, total, n, (uint32_t)ntiles, false, 0, st);
-        else launch_k1<1, false>(h, d_bytes, total, n, (uint32_t)ntiles, false, 0, st);
+    K1Plan kp;
+    kp.d_bytes = d_bytes;
+    kp.total = total;
+    kp.bd_cap = bd_cap;
+    kp.pending = true;
+    const bool prob = h->p.algo == GSB_ALGO_PROB3A;
+    // files of a group without any tile are not visited by K1: their result is "empty"
+    GSB_CUDA_TRY(cudaMemsetAsync(h->d_res.p, 0, (size_t)n * sizeof(FileResult), st));
+    if (!ntiles) {
+        kp.pending = false;
+    } else if (!prob) {
+        launch_k1_range(h, kp, 0, n, st);
+        kp.pending = false;
         GSB_CUDA_TRY(cudaGetLastError());
-    } else {
-        GSB_CUDA_TRY(cudaMemsetAsync(h->d_res.p, 0, (size_t)n * sizeof(FileResult), st));
     }
 
     // ---- K2/K3 with bound retries
     std::vector<uint32_t> todo(n);
     std::vector<double> tmult(n, 1.0);
     for (uint32_t i = 0; i < n; i++) todo[i] = i;
-    const bool prob = h->p.algo == GSB_ALGO_PROB3A;
     for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++) {
-        rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st)
+        rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp)
                   : run_dens(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st);
         if (rc) return rc;
         GSB_CUDA_TRY(cudaMemcpyAsync(h->h_retry.p, h->d_retry.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

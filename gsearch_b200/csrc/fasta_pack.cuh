@@ -291,13 +291,13 @@ __global__ void __launch_bounds__(kK1Threads)
 k1a_tile_summary(const uint8_t *__restrict__ bytes, uint64_t total,
                  const FileDesc *__restrict__ files, const uint32_t *__restrict__ tile_prefix,
                  uint32_t nfiles, uint64_t *__restrict__ t_counts4, uint8_t *__restrict__ t_trans,
-                 uint16_t *__restrict__ t_nrec) {
+                 uint16_t *__restrict__ t_nrec, uint32_t tile0) {
     __shared__ __align__(16) uint8_t sm[kTile + 32];
     __shared__ uint8_t aa_lut[256];
     __shared__ uint32_t wtot[kK1Threads / 32];
     __shared__ unsigned long long wsum[kK1Threads / 32];
     if (DATA_T == 1) init_aa_lut(aa_lut);
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x + tile0;  // files/tile_prefix/res point at the range's first file
     const uint32_t fi = find_file(tile_prefix, nfiles, tile);
     const FileDesc fd = files[fi];
     const uint32_t lt = tile - fd.tile_first;
@@ -419,13 +419,13 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
          const uint8_t *__restrict__ t_state, const uint32_t *__restrict__ t_base,
          const uint32_t *__restrict__ t_recbase, const FileResult *__restrict__ res,
          uint32_t *__restrict__ out_dna, uint8_t *__restrict__ out_aa,
-         uint32_t *__restrict__ boundaries /* DNA seq mode, else null */) {
+         uint32_t *__restrict__ boundaries /* DNA seq mode, else null */, uint32_t tile0) {
     __shared__ __align__(16) uint8_t sm[kTile + 32];
     __shared__ __align__(16) uint8_t stage[kTile + 256 + 16];
     __shared__ uint8_t aa_lut[256];
     __shared__ uint32_t wtot[kK1Threads / 32];
     if (DATA_T == 1) init_aa_lut(aa_lut);
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x + tile0;  // files/tile_prefix/res point at the range's first file
     const uint32_t fi = find_file(tile_prefix, nfiles, tile);
     const FileDesc fd = files[fi];
     const FileResult fr = res[fi];

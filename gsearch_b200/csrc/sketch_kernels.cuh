@@ -314,11 +314,12 @@ __device__ __forceinline__ ChunkCtx chunk_ctx(const uint32_t *__restrict__ chunk
                                               const FileResult *__restrict__ res,
                                               const uint32_t *__restrict__ packed_dna,
                                               const uint8_t *__restrict__ packed_aa,
-                                              const uint32_t *__restrict__ boundaries, uint32_t j) {
+                                              const uint32_t *__restrict__ boundaries, uint32_t j,
+                                              uint32_t chunk) {
     ChunkCtx c;
     c.j = j;
     const FileResult fr = res[file_of_job];
-    const uint32_t cbase = (blockIdx.x - chunk_prefix[j]) * kChunk;
+    const uint32_t cbase = (chunk - chunk_prefix[j]) * kChunk;
     c.live = fr.status == 0 && cbase < fr.nsym;  // grid is sized from the byte-length upper bound
     const FileDesc fd = files[file_of_job];
     c.sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
@@ -363,11 +364,14 @@ __global__ void __launch_bounds__(kK2Threads)
 k2_prob_mark(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
              const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
              const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
-             const uint32_t *__restrict__ boundaries, SketchConsts sc) {
-    const uint32_t j = find_file(chunk_prefix, njobs, blockIdx.x);
+             const uint32_t *__restrict__ boundaries, SketchConsts sc, uint32_t nchunks) {
+  // persistent CTAs (grid-stride over chunks): a bounded grid leaves room on every SM for the
+  // kernels of the other group stream (this kernel waits on L2 atomics, classify on the ALU)
+  for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const uint32_t j = find_file(chunk_prefix, njobs, chunk);
     const ProbJob job = jobs[j];
-    const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j);
-    if (!cx.live) return;
+    const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j, chunk);
+    if (!cx.live) continue;
     const uint32_t nwords = job.nslot1 >> 4;
     Src src;
     src.init(cx.sv, cx.p0, sc.k);
@@ -399,6 +403,7 @@ k2_prob_mark(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chun
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) ncoll += __shfl_xor_sync(0xffffffffu, ncoll, d);
     if (lane_id() == 0 && ncoll) atomicAdd(job.n_coll, ncoll);
+  }
 }
 
 // ---- pass B: classify.  A k-mer whose flag is down is unique (weight 1, exactly) and is kept
@@ -414,16 +419,18 @@ k2_prob_classify(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ 
                  const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
                  const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
                  const uint32_t *__restrict__ boundaries, const ProbBound *__restrict__ bound,
-                 SketchConsts sc, uint32_t *__restrict__ overflow) {
-    const uint32_t j = find_file(chunk_prefix, njobs, blockIdx.x);
+                 SketchConsts sc, uint32_t *__restrict__ overflow, uint32_t nchunks) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  ListEntry *s_lo = reinterpret_cast<ListEntry *>(s_raw);              // [kStageHalf] unique light k-mers
+  OvfEntry *s_hi = reinterpret_cast<OvfEntry *>(s_raw) + kStageHalf;   // [kStageHalf] flagged occurrences
+  __shared__ uint32_t s_nlo, s_nhi, s_blo, s_bhi;
+  for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {  // persistent CTAs
+    const uint32_t j = find_file(chunk_prefix, njobs, chunk);
     const ProbJob job = jobs[j];
-    const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j);
-    if (!cx.live) return;
+    const ChunkCtx cx = chunk_ctx(chunk_prefix, njobs, job.file, files, res, packed_dna, packed_aa, boundaries, j, chunk);
+    if (!cx.live) continue;  // uniform for the CTA
     const ProbBound pb = bound[j];
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    ListEntry *s_lo = reinterpret_cast<ListEntry *>(s_raw);              // [kStageHalf] unique light k-mers
-    OvfEntry *s_hi = reinterpret_cast<OvfEntry *>(s_raw) + kStageHalf;   // [kStageHalf] flagged occurrences
-    __shared__ uint32_t s_nlo, s_nhi, s_blo, s_bhi;
+    __syncthreads();  // the previous chunk's flush has finished reading the stage
     if (threadIdx.x == 0) {
         s_nlo = 0;
         s_nhi = 0;
@@ -527,6 +534,7 @@ k2_prob_classify(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ 
         if (ghi + t < job.ovf_cap) job.ovf[ghi + t] = s_hi[t];
         else atomicOr(&overflow[j], 1u);
     }
+  }
 }
 
 // ---- between classify and the exact set: size and clear the set from the number of flagged
@@ -710,14 +718,15 @@ k2_optdens(const DensJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_
            uint32_t njobs, const FileDesc *__restrict__ files,
            const FileResult *__restrict__ res, const uint32_t *__restrict__ packed_dna,
            const uint8_t *__restrict__ packed_aa, const uint32_t *__restrict__ boundaries,
-           SketchConsts sc) {
-    const uint32_t j = find_file(chunk_prefix, njobs, blockIdx.x);
+           SketchConsts sc, uint32_t nchunks) {
+  for (uint32_t gchunk = blockIdx.x; gchunk < nchunks; gchunk += gridDim.x) {  // persistent CTAs
+    const uint32_t j = find_file(chunk_prefix, njobs, gchunk);
     const DensJob job = jobs[j];
     const FileResult fr = res[job.file];
-    if (fr.status != 0) return;
-    const uint32_t chunk = blockIdx.x - chunk_prefix[j];
+    if (fr.status != 0) continue;
+    const uint32_t chunk = gchunk - chunk_prefix[j];
     const uint32_t cbase = chunk * kChunk;
-    if (cbase >= fr.nsym) return;
+    if (cbase >= fr.nsym) continue;
     const FileDesc fd = files[job.file];
     SeqView sv;
     sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
@@ -747,6 +756,7 @@ k2_optdens(const DensJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_
         const uint32_t k = uniform_usize(rng, sc.m, sc.zone);
         atomicMin(&job.bins[k], __float_as_uint(r));
     }
+  }
 }
 
 // per genome: check the bound, densify empty bins (cold path), write f32 signature
