@@ -53,7 +53,10 @@ SYMBOLS = {
     "gsb_index_insert_batch": (_int, [_vp, _vp, _vp, _u64]),
     "gsb_index_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "gsb_index_nb_point": (_u64, [_vp]),
-    "gsb_index_load_graph": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _u64]),
+    "gsb_index_load_graph": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64]),
+    "gsb_index_graph_sizes": (_int, [_vp, _vp, _vp]),
+    "gsb_index_export_graph": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_index_set_wave_max": (_int, [_vp, _u32]),
     "gsb_index_dump": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "gsb_index_load": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "gsb_synth_max_bytes": (_u64, [_u64, _u32]),

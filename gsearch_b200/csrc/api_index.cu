@@ -1,24 +1,120 @@
-// api_index.cu -- C-ABI of the index (gsb_index_*): device-resident HNSW graph + search.
+// api_index.cu -- C-ABI of the index (gsb_index_*): device-resident, mutable HNSW graph with
+// on-device construction (wave insertion) and search.  Host code here only sizes buffers,
+// draws the levels (hnsw_rs LayerGenerator, restated in oracle/hnsw.c) and launches kernels.
+#include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "api_common.h"
-#include "hnsw_search.cuh"
+#include "hnsw_device.cuh"
 
 using namespace gsb;
+
+namespace {
+
+// xoshiro256++ seeded through SplitMix64 (rand_xoshiro seed_from_u64) and the two rand-0.8
+// uniform draws the level generator needs -- host twins of common.cuh
+struct HostXoshiro {
+    uint64_t s[4];
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    void seed(uint64_t z) {
+        for (int i = 0; i < 4; i++) {
+            z += 0x9e3779b97f4a7c15ULL;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+            x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+            s[i] = x ^ (x >> 31);
+        }
+    }
+    uint64_t next() {
+        const uint64_t result = rotl(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0];
+        s[3] ^= s[1];
+        s[1] ^= s[2];
+        s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return result;
+    }
+    double uniform_f64() {
+        const uint64_t bits = (next() >> 12) | 0x3FF0000000000000ULL;
+        double d;
+        memcpy(&d, &bits, 8);
+        return d - 1.0;
+    }
+    uint64_t uniform_usize(uint64_t m) {
+        const uint64_t zone = UINT64_MAX - ((UINT64_MAX - m + 1) % m);
+        for (;;) {
+            const uint64_t v = next();
+            const unsigned __int128 p = (unsigned __int128)v * (unsigned __int128)m;
+            if ((uint64_t)p <= zone) return (uint64_t)(p >> 64);
+        }
+    }
+};
+
+// device buffer that keeps its content when it grows, new space zero-filled
+struct GrowBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, cudaStream_t st) {
+        if (bytes <= cap) return GSB_OK;
+        size_t want = std::max(bytes, cap * 2) + 256;
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return GSB_ERR_OOM;
+        }
+        cudaStreamSynchronize(st);
+        if (cap) cudaMemcpy(q, p, cap, cudaMemcpyDeviceToDevice);
+        cudaMemset((uint8_t *)q + cap, 0, want - cap);
+        if (p) cudaFree(p);
+        p = q;
+        cap = want;
+        return GSB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace
 
 struct gsb_index {
     gsb_index_params p;
     int device = 0;
+    int nsm = 148;
     uint32_t elem = 4;
-    uint64_t n = 0;
+    uint32_t M = 0;
+    uint64_t n = 0;        // points in the graph
+    uint64_t nU = 0;       // upper-layer lists in use
     uint32_t entry = 0;
-    uint32_t max_list = 0;
-    DevBuf d_sigs, d_ids, d_levels, d_ranks, d_list_base, d_nbr_off, d_nbr_idx;
-    DevBuf d_queries, d_out, d_counts, d_neval, d_ws, d_counter;
+    bool has_dist = true;  // false after load_graph without distances: search only
+    uint32_t wave_max = 0;
+    HostXoshiro level_rng;
+    double level_scale = 1.0;
+    std::vector<uint8_t> levels;      // host mirror (entry-point bookkeeping, export)
+    std::vector<uint32_t> upper_off;  // host mirror
+    uint32_t layer_count[kMaxLayers] = {0};
+    GrowBuf d_sigs, d_ids, d_levels, d_ranks, d_nbr0, d_dist0, d_cnt0, d_upper_off, d_nbrU, d_distU, d_cntU,
+        d_lock0, d_lockU;
+    DevBuf d_queries, d_out, d_counts, d_neval, d_counter, d_sel_n, d_sel_idx, d_sel_d;
+    DevBuf d_ws;  // per-CTA workspaces (zeroed when reallocated: the visit stamps live there)
+    WsLayout wl{};
+    uint32_t ws_ctas = 0, ws_ef = 0;
+    uint64_t ws_npts = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -37,8 +133,8 @@ extern "C" int gsb_index_create(const gsb_index_params *params, int device, gsb_
         set_error("gsb_index_create: NULL argument");
         return GSB_ERR_INVALID_ARG;
     }
-    if (params->max_nb_connection < 1 || params->max_nb_connection > 255) {
-        set_error("max_nb_connection %u out of range 1..255 (src/bin/gsearch.rs:266-268)",
+    if (params->max_nb_connection < 2 || params->max_nb_connection > 255) {
+        set_error("max_nb_connection %u out of range 2..255 (src/bin/gsearch.rs:266-268)",
                   params->max_nb_connection);
         return GSB_ERR_INVALID_ARG;
     }
@@ -57,7 +153,13 @@ extern "C" int gsb_index_create(const gsb_index_params *params, int device, gsb_
     idx->p = *params;
     idx->device = device;
     idx->elem = elem_of(params->sig_type);
+    idx->M = params->max_nb_connection;
+    idx->level_rng.seed(params->level_seed);
+    idx->level_scale = (params->scale_modification > 0 ? params->scale_modification : 1.0) /
+                       log((double)params->max_nb_connection);
     cudaSetDevice(device);
+    cudaDeviceGetAttribute(&idx->nsm, cudaDevAttrMultiProcessorCount, device);
+    idx->wave_max = (uint32_t)idx->nsm;
     if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete idx;
@@ -71,9 +173,12 @@ extern "C" void gsb_index_destroy(gsb_index *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&idx->d_sigs, &idx->d_ids, &idx->d_levels, &idx->d_ranks, &idx->d_list_base,
-                      &idx->d_nbr_off, &idx->d_nbr_idx, &idx->d_queries, &idx->d_out, &idx->d_counts,
-                      &idx->d_neval, &idx->d_ws, &idx->d_counter};
+    GrowBuf *gb[] = {&idx->d_sigs, &idx->d_ids, &idx->d_levels, &idx->d_ranks, &idx->d_nbr0, &idx->d_dist0,
+                     &idx->d_cnt0, &idx->d_upper_off, &idx->d_nbrU, &idx->d_distU, &idx->d_cntU, &idx->d_lock0,
+                     &idx->d_lockU};
+    for (GrowBuf *b : gb) b->release();
+    DevBuf *bufs[] = {&idx->d_queries, &idx->d_out, &idx->d_counts, &idx->d_neval, &idx->d_counter,
+                      &idx->d_sel_n, &idx->d_sel_idx, &idx->d_sel_d, &idx->d_ws};
     for (DevBuf *b : bufs) b->release();
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
@@ -81,74 +186,198 @@ extern "C" void gsb_index_destroy(gsb_index *idx) {
 
 extern "C" uint64_t gsb_index_nb_point(const gsb_index *idx) { return idx ? idx->n : 0; }
 
+extern "C" int gsb_index_set_wave_max(gsb_index *idx, uint32_t wave_max) {
+    if (!idx || wave_max < 1 || wave_max > (uint32_t)kMaxList) {
+        set_error("wave_max must be in 1..%d", kMaxList);
+        return GSB_ERR_INVALID_ARG;
+    }
+    idx->wave_max = wave_max;
+    return GSB_OK;
+}
+
+namespace {
+
+int ensure_points(gsb_index *idx, uint64_t npts) {
+    const size_t row = (size_t)idx->p.sketch_size * idx->elem;
+    const size_t M2 = 2 * (size_t)idx->M;
+    cudaStream_t st = idx->stream;
+    int rc;
+    if ((rc = idx->d_sigs.ensure(npts * row + 64, st))) return rc;
+    if ((rc = idx->d_ids.ensure(npts * 8 + 8, st))) return rc;
+    if ((rc = idx->d_levels.ensure(npts + 8, st))) return rc;
+    if ((rc = idx->d_ranks.ensure(npts * 4 + 8, st))) return rc;
+    if ((rc = idx->d_upper_off.ensure(npts * 4 + 8, st))) return rc;
+    if ((rc = idx->d_nbr0.ensure(npts * M2 * 4 + 8, st))) return rc;
+    if ((rc = idx->d_dist0.ensure(npts * M2 * 4 + 8, st))) return rc;
+    if ((rc = idx->d_cnt0.ensure(npts * 4 + 8, st))) return rc;
+    if ((rc = idx->d_lock0.ensure(npts * 4 + 8, st))) return rc;
+    return GSB_OK;
+}
+
+int ensure_upper(gsb_index *idx, uint64_t nlists) {
+    const size_t M = idx->M;
+    cudaStream_t st = idx->stream;
+    int rc;
+    if ((rc = idx->d_nbrU.ensure(nlists * M * 4 + 8, st))) return rc;
+    if ((rc = idx->d_distU.ensure(nlists * M * 4 + 8, st))) return rc;
+    if ((rc = idx->d_cntU.ensure(nlists * 4 + 8, st))) return rc;
+    if ((rc = idx->d_lockU.ensure(nlists * 4 + 8, st))) return rc;
+    return GSB_OK;
+}
+
+GraphView graph_view(const gsb_index *idx) {
+    GraphView g;
+    g.sigs = idx->d_sigs.as<uint8_t>();
+    g.ids = idx->d_ids.as<uint64_t>();
+    g.levels = idx->d_levels.as<uint8_t>();
+    g.ranks = idx->d_ranks.as<uint32_t>();
+    g.nbr0 = idx->d_nbr0.as<uint32_t>();
+    g.dist0 = idx->d_dist0.as<float>();
+    g.cnt0 = idx->d_cnt0.as<uint32_t>();
+    g.upper_off = idx->d_upper_off.as<uint32_t>();
+    g.nbrU = idx->d_nbrU.as<uint32_t>();
+    g.distU = idx->d_distU.as<float>();
+    g.cntU = idx->d_cntU.as<uint32_t>();
+    g.lock0 = idx->d_lock0.as<uint32_t>();
+    g.lockU = idx->d_lockU.as<uint32_t>();
+    g.M = idx->M;
+    g.n = (uint32_t)idx->n;
+    g.entry = idx->entry;
+    g.S = idx->p.sketch_size;
+    return g;
+}
+
+constexpr size_t kSmemMax = 216 * 1024;  // dynamic; the kernels add < 10 KB of static shared memory
+
+// per-CTA workspace for `nctas` CTAs over `npts` points with a result heap of `ef`; grown
+// geometrically (and zeroed: the visit stamps live there) so that a growing index does not
+// reallocate at every wave
+int ensure_workspace(gsb_index *idx, uint32_t nctas, uint64_t npts, uint32_t ef) {
+    if (idx->d_ws.p && npts <= idx->ws_npts && ef <= idx->ws_ef && nctas <= idx->ws_ctas) return GSB_OK;
+    const size_t M = idx->M;
+    const uint64_t cap_pts = std::max<uint64_t>(std::max<uint64_t>(2 * npts, idx->ws_npts), 1024);
+    const uint32_t cap_ef = std::max(ef, idx->ws_ef);
+    const uint32_t nc = std::max<uint32_t>(std::max(nctas, idx->ws_ctas), (uint32_t)idx->nsm);
+    WsLayout wl;
+    size_t off = 0;
+    wl.off_ctr = off;
+    off += 16;
+    wl.off_cand = off;
+    off += (std::max<size_t>(cap_pts, (size_t)cap_ef + 4 * M * M) + 4) * sizeof(HItem);
+    wl.off_stamp = off;
+    off += ((cap_pts + 4) * 4 + 15) & ~(size_t)15;
+    wl.off_ret = off;
+    off += ((size_t)cap_ef + 2) * sizeof(HItem);
+    wl.off_newc = off;
+    off += (4 * M * M + 16) * 4;
+    wl.stride = (off + 255) & ~(size_t)255;
+    cudaStreamSynchronize(idx->stream);
+    idx->d_ws.release();
+    int rc = idx->d_ws.ensure(wl.stride * nc);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(idx->d_ws.p, 0, idx->d_ws.cap, idx->stream);
+    if (e != cudaSuccess) {
+        set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+        return GSB_ERR_CUDA;
+    }
+    idx->wl = wl;
+    idx->ws_ctas = nc;
+    idx->ws_npts = cap_pts;
+    idx->ws_ef = cap_ef;
+    return GSB_OK;
+}
+
+}  // namespace
+
 extern "C" int gsb_index_load_graph(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n,
                                     const uint8_t *levels, const uint32_t *ranks, const uint64_t *nbr_offsets,
-                                    const uint32_t *nbr_index, uint64_t entry_point) {
+                                    const uint32_t *nbr_index, const float *nbr_dist, uint64_t entry_point) {
     if (!idx || (n && (!sigs || !ids || !levels || !ranks || !nbr_offsets || !nbr_index))) {
         set_error("gsb_index_load_graph: NULL argument");
         return GSB_ERR_INVALID_ARG;
     }
-    if (n > idx->p.capacity || n >= 0xFFFFFFFFull) {
+    if (n > idx->p.capacity || n >= 0xFFFFFFF0ull) {
         set_error("%llu points exceed the index capacity %llu", (unsigned long long)n,
                   (unsigned long long)idx->p.capacity);
         return GSB_ERR_CAPACITY;
     }
     GSB_CUDA_TRY(cudaSetDevice(idx->device));
-    std::vector<uint64_t> list_base(n + 1);
-    uint64_t tl = 0;
+    const uint32_t M = idx->M;
+    std::vector<uint32_t> upper_off(n, 0);
+    uint64_t tl = 0, nU = 0;
     for (uint64_t p = 0; p < n; p++) {
         if (levels[p] >= idx->p.max_layer) {
             set_error("point %llu has level %u >= max_layer %u", (unsigned long long)p, levels[p],
                       idx->p.max_layer);
             return GSB_ERR_INVALID_ARG;
         }
-        list_base[p] = tl;
+        upper_off[p] = (uint32_t)nU;
+        nU += levels[p];
         tl += (uint64_t)levels[p] + 1;
     }
-    list_base[n] = tl;
-    uint32_t max_list = 0;
-    for (uint64_t l = 0; l < tl; l++) {
-        if (nbr_offsets[l + 1] < nbr_offsets[l]) {
-            set_error("nbr_offsets must be non-decreasing");
-            return GSB_ERR_INVALID_ARG;
-        }
-        max_list = std::max<uint32_t>(max_list, (uint32_t)(nbr_offsets[l + 1] - nbr_offsets[l]));
-    }
-    const uint64_t tn = n ? nbr_offsets[tl] : 0;
-    if (max_list > (uint32_t)kMaxList) {
-        set_error("neighbour list of %u entries exceeds the kernel limit %d", max_list, kMaxList);
-        return GSB_ERR_CAPACITY;
-    }
-    for (uint64_t i = 0; i < tn; i++)
-        if (nbr_index[i] >= n) {
-            set_error("neighbour index %u out of range", nbr_index[i]);
-            return GSB_ERR_INVALID_ARG;
-        }
     if (n && entry_point >= n) {
         set_error("entry point out of range");
         return GSB_ERR_INVALID_ARG;
     }
+    // CSR image -> fixed-capacity adjacency
+    std::vector<uint32_t> nbr0((size_t)n * 2 * M, 0), cnt0(n, 0), nbrU((size_t)nU * M, 0), cntU(nU, 0);
+    std::vector<float> dist0((size_t)n * 2 * M, 0.f), distU((size_t)nU * M, 0.f);
+    uint64_t li = 0;
+    for (uint64_t p = 0; p < n; p++) {
+        for (uint32_t l = 0; l <= levels[p]; l++, li++) {
+            const uint64_t b = nbr_offsets[li], e = nbr_offsets[li + 1];
+            if (e < b || e - b > (l == 0 ? 2u * M : M)) {
+                set_error("neighbour list (%llu, layer %u) has %lld entries, limit %u", (unsigned long long)p, l,
+                          (long long)(e - b), l == 0 ? 2u * M : M);
+                return GSB_ERR_INVALID_ARG;
+            }
+            uint32_t *di = l == 0 ? &nbr0[(size_t)p * 2 * M] : &nbrU[(size_t)(upper_off[p] + l - 1) * M];
+            float *dd = l == 0 ? &dist0[(size_t)p * 2 * M] : &distU[(size_t)(upper_off[p] + l - 1) * M];
+            for (uint64_t i = b; i < e; i++) {
+                if (nbr_index[i] >= n) {
+                    set_error("neighbour index %u out of range", nbr_index[i]);
+                    return GSB_ERR_INVALID_ARG;
+                }
+                di[i - b] = nbr_index[i];
+                dd[i - b] = nbr_dist ? nbr_dist[i] : 0.f;
+            }
+            if (l == 0) cnt0[p] = (uint32_t)(e - b);
+            else cntU[upper_off[p] + l - 1] = (uint32_t)(e - b);
+        }
+    }
+    // a fresh graph replaces whatever the index held
+    GrowBuf *gb[] = {&idx->d_sigs, &idx->d_ids, &idx->d_levels, &idx->d_ranks, &idx->d_nbr0, &idx->d_dist0,
+                     &idx->d_cnt0, &idx->d_upper_off, &idx->d_nbrU, &idx->d_distU, &idx->d_cntU, &idx->d_lock0,
+                     &idx->d_lockU};
+    cudaStreamSynchronize(idx->stream);
+    for (GrowBuf *b : gb) b->release();
     const size_t row = (size_t)idx->p.sketch_size * idx->elem;
     int rc;
-    if ((rc = idx->d_sigs.ensure(n * row + 64))) return rc;
-    if ((rc = idx->d_ids.ensure(n * 8 + 8))) return rc;
-    if ((rc = idx->d_levels.ensure(n + 8))) return rc;
-    if ((rc = idx->d_ranks.ensure(n * 4 + 8))) return rc;
-    if ((rc = idx->d_list_base.ensure((n + 1) * 8))) return rc;
-    if ((rc = idx->d_nbr_off.ensure((tl + 1) * 8))) return rc;
-    if ((rc = idx->d_nbr_idx.ensure(tn * 4 + 8))) return rc;
+    if ((rc = ensure_points(idx, std::max<uint64_t>(n, 1)))) return rc;
+    if ((rc = ensure_upper(idx, std::max<uint64_t>(nU, 1)))) return rc;
     if (n) {
         GSB_CUDA_TRY(cudaMemcpy(idx->d_sigs.p, sigs, n * row, cudaMemcpyHostToDevice));
         GSB_CUDA_TRY(cudaMemcpy(idx->d_ids.p, ids, n * 8, cudaMemcpyHostToDevice));
         GSB_CUDA_TRY(cudaMemcpy(idx->d_levels.p, levels, n, cudaMemcpyHostToDevice));
         GSB_CUDA_TRY(cudaMemcpy(idx->d_ranks.p, ranks, n * 4, cudaMemcpyHostToDevice));
-        GSB_CUDA_TRY(cudaMemcpy(idx->d_list_base.p, list_base.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
-        GSB_CUDA_TRY(cudaMemcpy(idx->d_nbr_off.p, nbr_offsets, (tl + 1) * 8, cudaMemcpyHostToDevice));
-        if (tn) GSB_CUDA_TRY(cudaMemcpy(idx->d_nbr_idx.p, nbr_index, tn * 4, cudaMemcpyHostToDevice));
+        GSB_CUDA_TRY(cudaMemcpy(idx->d_upper_off.p, upper_off.data(), n * 4, cudaMemcpyHostToDevice));
+        GSB_CUDA_TRY(cudaMemcpy(idx->d_nbr0.p, nbr0.data(), nbr0.size() * 4, cudaMemcpyHostToDevice));
+        GSB_CUDA_TRY(cudaMemcpy(idx->d_dist0.p, dist0.data(), dist0.size() * 4, cudaMemcpyHostToDevice));
+        GSB_CUDA_TRY(cudaMemcpy(idx->d_cnt0.p, cnt0.data(), n * 4, cudaMemcpyHostToDevice));
+        if (nU) {
+            GSB_CUDA_TRY(cudaMemcpy(idx->d_nbrU.p, nbrU.data(), nbrU.size() * 4, cudaMemcpyHostToDevice));
+            GSB_CUDA_TRY(cudaMemcpy(idx->d_distU.p, distU.data(), distU.size() * 4, cudaMemcpyHostToDevice));
+            GSB_CUDA_TRY(cudaMemcpy(idx->d_cntU.p, cntU.data(), nU * 4, cudaMemcpyHostToDevice));
+        }
     }
     idx->n = n;
+    idx->nU = nU;
     idx->entry = (uint32_t)entry_point;
-    idx->max_list = max_list;
+    idx->has_dist = nbr_dist != nullptr || n == 0;
+    idx->levels.assign(levels, levels + n);
+    idx->upper_off = upper_off;
+    memset(idx->layer_count, 0, sizeof idx->layer_count);
+    for (uint64_t p = 0; p < n; p++) idx->layer_count[levels[p]]++;
     return GSB_OK;
 }
 
@@ -157,43 +386,26 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
     const size_t row = (size_t)idx->p.sketch_size * ELEM;
     const size_t row128 = (row + 127) & ~(size_t)127;
     const size_t ret_bytes = ((size_t)ef + 2) * sizeof(HItem);
-    const size_t smem_max = 220 * 1024;
-    if (row128 > smem_max) {
+    if (row128 > kSmemMax) {
         set_error("signature row of %zu bytes does not fit in shared memory", row);
         return GSB_ERR_UNSUPPORTED;
     }
-    const int ret_in_smem = row128 + ret_bytes <= smem_max ? 1 : 0;
+    const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
     const size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
     GSB_CUDA_TRY(cudaFuncSetAttribute(k7_hnsw_search<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_max));
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, idx->device);
-    const uint32_t nctas = std::min<uint32_t>(nq, (uint32_t)nsm);
-    const size_t n = idx->n;
-    size_t stride = (n + 1) * sizeof(HItem) + ((n + 15) & ~(size_t)15) + (ret_in_smem ? 0 : ret_bytes);
-    stride = (stride + 255) & ~(size_t)255;
+                                      (int)kSmemMax));
+    const uint32_t nctas = std::min<uint32_t>(nq, (uint32_t)idx->nsm);
     int rc;
-    if ((rc = idx->d_ws.ensure(stride * nctas))) return rc;
+    if ((rc = ensure_workspace(idx, nctas, idx->n, ef))) return rc;
     if ((rc = idx->d_counter.ensure(256))) return rc;
     GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
-    GraphView g;
-    g.sigs = idx->d_sigs.as<uint8_t>();
-    g.ids = idx->d_ids.as<uint64_t>();
-    g.levels = idx->d_levels.as<uint8_t>();
-    g.ranks = idx->d_ranks.as<uint32_t>();
-    g.list_base = idx->d_list_base.as<uint64_t>();
-    g.nbr_off = idx->d_nbr_off.as<uint64_t>();
-    g.nbr_idx = idx->d_nbr_idx.as<uint32_t>();
-    g.n = (uint32_t)idx->n;
-    g.entry = idx->entry;
-    g.S = idx->p.sketch_size;
     SearchOut so;
     so.out = idx->d_out.as<gsb_neighbour>();
     so.counts = idx->d_counts.as<uint32_t>();
     so.nb_eval = idx->d_neval.as<unsigned long long>();
     k7_hnsw_search<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(
-        g, idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, idx->d_ws.as<uint8_t>(), stride, so,
-        idx->d_counter.as<uint32_t>());
+        graph_view(idx), idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, idx->d_ws.as<uint8_t>(), idx->wl,
+        so, idx->d_counter.as<uint32_t>());
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;
 }
@@ -242,27 +454,350 @@ extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint3
     return GSB_OK;
 }
 
-extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n) {
-    (void)idx;
-    (void)sigs;
-    (void)ids;
-    (void)n;
-    set_error("gsb_index_insert_batch: on-device HNSW construction is not built yet (SURVEY 8f f2)");
-    return GSB_ERR_UNSUPPORTED;
+// ------------------------------------------------------------------------------ construction
+namespace {
+
+// hnsw_rs LayerGenerator::generate: floor(-ln(U) * scale), re-drawn uniformly if >= max_layer
+uint32_t gen_level(gsb_index *idx) {
+    const double xsi = idx->level_rng.uniform_f64();
+    const double lv = -log(xsi) * idx->level_scale;
+    if (!(lv < (double)idx->p.max_layer)) return (uint32_t)idx->level_rng.uniform_usize(idx->p.max_layer);
+    return (uint32_t)floor(lv);
 }
 
+uint32_t wave_size(uint64_t nb_point, uint32_t wave_max) {  // == gso_hnsw_wave_size
+    uint64_t w = nb_point / 4;
+    if (w < 1) w = 1;
+    if (w > wave_max) w = wave_max;
+    return (uint32_t)w;
+}
+
+template <int ELEM, bool F32>
+int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
+    const uint32_t ef_c = idx->p.ef_construction;
+    const size_t row = (size_t)idx->p.sketch_size * ELEM;
+    const size_t row128 = (row + 127) & ~(size_t)127;
+    const size_t ret_bytes = ((size_t)ef_c + 2) * sizeof(HItem);
+    if (row128 > kSmemMax) {
+        set_error("signature row of %zu bytes does not fit in shared memory", row);
+        return GSB_ERR_UNSUPPORTED;
+    }
+    const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
+    const size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
+    static bool attr = false;
+    if (!attr) {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(k8_hnsw_insert_select<ELEM, F32>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+        attr = true;
+    }
+    const uint32_t nctas = std::min<uint32_t>(W, (uint32_t)idx->nsm);
+    int rc;
+    if ((rc = ensure_workspace(idx, nctas, (uint64_t)first + W, ef_c))) return rc;
+    WaveView wv;
+    wv.first = first;
+    wv.W = W;
+    wv.entry = idx->entry;
+    wv.ef_c = ef_c;
+    wv.extend = idx->p.extend_candidates;
+    wv.sel_n = idx->d_sel_n.as<uint32_t>();
+    wv.sel_idx = idx->d_sel_idx.as<uint32_t>();
+    wv.sel_d = idx->d_sel_d.as<float>();
+    wv.counter = idx->d_counter.as<uint32_t>();
+    GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
+    GraphView g = graph_view(idx);
+    g.n = first + W;
+    k8_hnsw_insert_select<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(g, wv, ret_in_smem,
+                                                                         idx->d_ws.as<uint8_t>(), idx->wl);
+    k9_write_own_lists<<<W, 256, 0, st>>>(g, wv);
+    k9_reverse_updates<<<W, 256, 0, st>>>(g, wv);
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace
+
+extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n) {
+    if (!idx || (n && (!sigs || !ids))) {
+        set_error("gsb_index_insert_batch: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    if (n == 0) return GSB_OK;
+    if (idx->n + n > idx->p.capacity || idx->n + n >= 0xFFFFFFF0ull) {
+        set_error("%llu points exceed the index capacity %llu", (unsigned long long)(idx->n + n),
+                  (unsigned long long)idx->p.capacity);
+        return GSB_ERR_CAPACITY;
+    }
+    if (!idx->has_dist) {
+        set_error("this graph was loaded without neighbour distances: it can be searched, not extended");
+        return GSB_ERR_UNSUPPORTED;
+    }
+    if (idx->p.keep_pruned) {
+        set_error("keep_pruned = true is not built (the reference calls set_keeping_pruned(false), "
+                  "src/dna/dnasketch.rs:160)");
+        return GSB_ERR_UNSUPPORTED;
+    }
+    GSB_CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    const size_t row = (size_t)idx->p.sketch_size * idx->elem;
+    const uint64_t n0 = idx->n, n1 = n0 + n;
+    // ---- levels, ranks and upper-list slots of the new points (in order: one level draw each)
+    std::vector<uint8_t> lv(n);
+    std::vector<uint32_t> rk(n), uo(n);
+    uint64_t nU = idx->nU;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t level = gen_level(idx);
+        lv[i] = (uint8_t)level;
+        rk[i] = idx->layer_count[level]++;
+        uo[i] = (uint32_t)nU;
+        nU += level;
+    }
+    int rc;
+    if ((rc = ensure_points(idx, n1))) return rc;
+    if ((rc = ensure_upper(idx, std::max<uint64_t>(nU, 1)))) return rc;
+    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_sigs.as<uint8_t>() + n0 * row, sigs, n * row, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_ids.as<uint64_t>() + n0, ids, n * 8, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_levels.as<uint8_t>() + n0, lv.data(), n, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_ranks.as<uint32_t>() + n0, rk.data(), n * 4, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_upper_off.as<uint32_t>() + n0, uo.data(), n * 4, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));  // lv/rk/uo are pageable: the copies must be done before they go
+    idx->levels.insert(idx->levels.end(), lv.begin(), lv.end());
+    idx->upper_off.insert(idx->upper_off.end(), uo.begin(), uo.end());
+    idx->nU = nU;
+    const uint32_t wmax = idx->wave_max;
+    const size_t M = idx->M;
+    if ((rc = idx->d_sel_n.ensure((size_t)wmax * kMaxLayers * 4))) return rc;
+    if ((rc = idx->d_sel_idx.ensure((size_t)wmax * 18 * M * 4))) return rc;
+    if ((rc = idx->d_sel_d.ensure((size_t)wmax * 18 * M * 4))) return rc;
+    if ((rc = idx->d_counter.ensure(256))) return rc;
+    // ---- waves
+    uint64_t i = 0;
+    while (i < n) {
+        if (idx->n == 0) {  // first point of the index: becomes the entry point
+            idx->entry = 0;
+            idx->n = 1;
+            i++;
+            continue;
+        }
+        uint32_t W = wave_size(idx->n, wmax);
+        if (W > n - i) W = (uint32_t)(n - i);
+        const uint32_t first = (uint32_t)idx->n;
+        switch (idx->p.sig_type) {
+        case GSB_SIG_U64: rc = launch_wave<8, false>(idx, first, W, st); break;
+        case GSB_SIG_U32: rc = launch_wave<4, false>(idx, first, W, st); break;
+        case GSB_SIG_F32: rc = launch_wave<4, true>(idx, first, W, st); break;
+        default: rc = launch_wave<2, false>(idx, first, W, st); break;
+        }
+        if (rc) return rc;
+        for (uint32_t t = 0; t < W; t++)
+            if (idx->levels[first + t] > idx->levels[idx->entry]) idx->entry = first + t;
+        idx->n += W;
+        i += W;
+    }
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+// ------------------------------------------------------------------------------ export / dump
+namespace {
+struct HostGraph {
+    std::vector<uint8_t> levels;
+    std::vector<uint32_t> ranks, cnt0, nbr0, upper_off, cntU, nbrU;
+    std::vector<float> dist0, distU;
+    std::vector<uint64_t> ids;
+};
+int fetch_graph(const gsb_index *idx, HostGraph &hg) {
+    const uint64_t n = idx->n, nU = idx->nU;
+    const size_t M = idx->M;
+    cudaSetDevice(idx->device);
+    cudaStreamSynchronize(idx->stream);
+    hg.levels.resize(n);
+    hg.ranks.resize(n);
+    hg.ids.resize(n);
+    hg.cnt0.resize(n);
+    hg.upper_off.resize(n);
+    hg.nbr0.resize(n * 2 * M);
+    hg.dist0.resize(n * 2 * M);
+    hg.cntU.resize(nU);
+    hg.nbrU.resize(nU * M);
+    hg.distU.resize(nU * M);
+    if (!n) return GSB_OK;
+    GSB_CUDA_TRY(cudaMemcpy(hg.levels.data(), idx->d_levels.p, n, cudaMemcpyDeviceToHost));
+    GSB_CUDA_TRY(cudaMemcpy(hg.ranks.data(), idx->d_ranks.p, n * 4, cudaMemcpyDeviceToHost));
+    GSB_CUDA_TRY(cudaMemcpy(hg.ids.data(), idx->d_ids.p, n * 8, cudaMemcpyDeviceToHost));
+    GSB_CUDA_TRY(cudaMemcpy(hg.cnt0.data(), idx->d_cnt0.p, n * 4, cudaMemcpyDeviceToHost));
+    GSB_CUDA_TRY(cudaMemcpy(hg.upper_off.data(), idx->d_upper_off.p, n * 4, cudaMemcpyDeviceToHost));
+    GSB_CUDA_TRY(cudaMemcpy(hg.nbr0.data(), idx->d_nbr0.p, n * 2 * M * 4, cudaMemcpyDeviceToHost));
+    GSB_CUDA_TRY(cudaMemcpy(hg.dist0.data(), idx->d_dist0.p, n * 2 * M * 4, cudaMemcpyDeviceToHost));
+    if (nU) {
+        GSB_CUDA_TRY(cudaMemcpy(hg.cntU.data(), idx->d_cntU.p, nU * 4, cudaMemcpyDeviceToHost));
+        GSB_CUDA_TRY(cudaMemcpy(hg.nbrU.data(), idx->d_nbrU.p, nU * M * 4, cudaMemcpyDeviceToHost));
+        GSB_CUDA_TRY(cudaMemcpy(hg.distU.data(), idx->d_distU.p, nU * M * 4, cudaMemcpyDeviceToHost));
+    }
+    return GSB_OK;
+}
+}  // namespace
+
+extern "C" int gsb_index_graph_sizes(const gsb_index *idx, uint64_t *total_lists, uint64_t *total_nbrs) {
+    if (!idx || !total_lists || !total_nbrs) {
+        set_error("gsb_index_graph_sizes: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    HostGraph hg;
+    int rc = fetch_graph(idx, hg);
+    if (rc) return rc;
+    uint64_t tl = 0, tn = 0;
+    for (uint64_t p = 0; p < idx->n; p++) {
+        tl += (uint64_t)hg.levels[p] + 1;
+        tn += hg.cnt0[p];
+        for (uint32_t l = 1; l <= hg.levels[p]; l++) tn += hg.cntU[hg.upper_off[p] + l - 1];
+    }
+    *total_lists = tl;
+    *total_nbrs = tn;
+    return GSB_OK;
+}
+
+extern "C" int gsb_index_export_graph(const gsb_index *idx, uint8_t *levels, uint32_t *ranks, uint64_t *ids,
+                                      uint64_t *nbr_offsets, uint32_t *nbr_index, float *nbr_dist,
+                                      uint64_t *entry_point) {
+    if (!idx || !nbr_offsets || !entry_point) {
+        set_error("gsb_index_export_graph: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    HostGraph hg;
+    int rc = fetch_graph(idx, hg);
+    if (rc) return rc;
+    const size_t M = idx->M;
+    uint64_t li = 0, off = 0;
+    for (uint64_t p = 0; p < idx->n; p++) {
+        if (levels) levels[p] = hg.levels[p];
+        if (ranks) ranks[p] = hg.ranks[p];
+        if (ids) ids[p] = hg.ids[p];
+        for (uint32_t l = 0; l <= hg.levels[p]; l++) {
+            nbr_offsets[li++] = off;
+            const uint32_t cnt = l == 0 ? hg.cnt0[p] : hg.cntU[hg.upper_off[p] + l - 1];
+            const uint32_t *src = l == 0 ? &hg.nbr0[p * 2 * M] : &hg.nbrU[(size_t)(hg.upper_off[p] + l - 1) * M];
+            const float *sd = l == 0 ? &hg.dist0[p * 2 * M] : &hg.distU[(size_t)(hg.upper_off[p] + l - 1) * M];
+            for (uint32_t i = 0; i < cnt; i++) {
+                if (nbr_index) nbr_index[off] = src[i];
+                if (nbr_dist) nbr_dist[off] = sd[i];
+                off++;
+            }
+        }
+    }
+    nbr_offsets[li] = off;
+    *entry_point = idx->n ? idx->entry : UINT64_MAX;
+    return GSB_OK;
+}
+
+// file_dump / reload.  Two files like hnsw_rs::hnswio (<basename>.hnsw.graph, <basename>.hnsw.data)
+// but in THIS library's own layout (little endian, documented in DESIGN.md): the byte layout of
+// hnswio is only recalled, not verifiable here, so compatibility is not claimed.
+namespace {
+constexpr uint64_t kMagicGraph = 0x31485247425347ULL;  // "GSBGRH1"
+constexpr uint64_t kMagicData = 0x31544144425347ULL;   // "GSBDAT1"
+template <class T>
+bool wr(FILE *f, const T *p, size_t n) {
+    return n == 0 || fwrite(p, sizeof(T), n, f) == n;
+}
+template <class T>
+bool rd(FILE *f, T *p, size_t n) {
+    return n == 0 || fread(p, sizeof(T), n, f) == n;
+}
+}  // namespace
+
 extern "C" int gsb_index_dump(const gsb_index *idx, const char *dir, const char *basename) {
-    (void)idx;
-    (void)dir;
-    (void)basename;
-    set_error("gsb_index_dump: hnswio on-disk format is not built yet (SURVEY 8f f1)");
-    return GSB_ERR_UNSUPPORTED;
+    if (!idx || !dir || !basename) {
+        set_error("gsb_index_dump: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    HostGraph hg;
+    int rc = fetch_graph(idx, hg);
+    if (rc) return rc;
+    const uint64_t n = idx->n;
+    uint64_t tl = 0;
+    for (uint64_t p = 0; p < n; p++) tl += (uint64_t)hg.levels[p] + 1;
+    std::vector<uint64_t> off(tl + 1);
+    uint64_t tn = 0;
+    {
+        uint64_t li = 0;
+        for (uint64_t p = 0; p < n; p++)
+            for (uint32_t l = 0; l <= hg.levels[p]; l++) {
+                off[li++] = tn;
+                tn += l == 0 ? hg.cnt0[p] : hg.cntU[hg.upper_off[p] + l - 1];
+            }
+        off[li] = tn;
+    }
+    std::vector<uint32_t> nidx(tn);
+    std::vector<float> ndist(tn);
+    uint64_t entry = 0;
+    rc = gsb_index_export_graph(idx, nullptr, nullptr, nullptr, off.data(), nidx.data(), ndist.data(), &entry);
+    if (rc) return rc;
+    const std::string base = std::string(dir) + "/" + basename;
+    FILE *fg = fopen((base + ".hnsw.graph").c_str(), "wb");
+    FILE *fd = fopen((base + ".hnsw.data").c_str(), "wb");
+    bool ok = fg && fd;
+    if (ok) {
+        const uint64_t hdr[10] = {kMagicGraph, n, idx->M, idx->p.max_layer, idx->p.ef_construction,
+                                  idx->p.sig_type, idx->p.sketch_size, entry, tl, tn};
+        ok = wr(fg, hdr, 10) && wr(fg, &idx->p.scale_modification, 1) && wr(fg, hg.levels.data(), n) &&
+             wr(fg, hg.ranks.data(), n) && wr(fg, off.data(), tl + 1) && wr(fg, nidx.data(), tn) &&
+             wr(fg, ndist.data(), tn);
+        const uint64_t dh[4] = {kMagicData, n, idx->p.sketch_size, idx->elem};
+        std::vector<uint8_t> sig((size_t)n * idx->p.sketch_size * idx->elem);
+        if (n && cudaMemcpy(sig.data(), idx->d_sigs.p, sig.size(), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+        ok = ok && wr(fd, dh, 4) && wr(fd, hg.ids.data(), n) && wr(fd, sig.data(), sig.size());
+    }
+    if (fg) ok = (fclose(fg) == 0) && ok;
+    if (fd) ok = (fclose(fd) == 0) && ok;
+    if (!ok) {
+        set_error("gsb_index_dump: cannot write %s.hnsw.{graph,data}", base.c_str());
+        return GSB_ERR_IO;
+    }
+    return GSB_OK;
 }
 
 extern "C" int gsb_index_load(gsb_index *idx, const char *dir, const char *basename) {
-    (void)idx;
-    (void)dir;
-    (void)basename;
-    set_error("gsb_index_load: hnswio on-disk format is not built yet (SURVEY 8f f1)");
-    return GSB_ERR_UNSUPPORTED;
+    if (!idx || !dir || !basename) {
+        set_error("gsb_index_load: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    const std::string base = std::string(dir) + "/" + basename;
+    FILE *fg = fopen((base + ".hnsw.graph").c_str(), "rb");
+    FILE *fd = fopen((base + ".hnsw.data").c_str(), "rb");
+    int rc = GSB_ERR_IO;
+    do {
+        if (!fg || !fd) {
+            set_error("gsb_index_load: cannot open %s.hnsw.{graph,data}", base.c_str());
+            break;
+        }
+        uint64_t hdr[10], dh[4];
+        double scale;
+        if (!rd(fg, hdr, 10) || !rd(fg, &scale, 1) || !rd(fd, dh, 4) || hdr[0] != kMagicGraph || dh[0] != kMagicData) {
+            set_error("gsb_index_load: %s is not a gsearch_b200 dump", base.c_str());
+            break;
+        }
+        const uint64_t n = hdr[1], tl = hdr[8], tn = hdr[9];
+        if (hdr[2] != idx->M || hdr[5] != idx->p.sig_type || hdr[6] != idx->p.sketch_size || dh[1] != n ||
+            dh[2] != idx->p.sketch_size || dh[3] != idx->elem) {
+            set_error("gsb_index_load: dump (M=%llu, sig_type=%llu, S=%llu) does not match this index",
+                      (unsigned long long)hdr[2], (unsigned long long)hdr[5], (unsigned long long)hdr[6]);
+            rc = GSB_ERR_INVALID_ARG;
+            break;
+        }
+        std::vector<uint8_t> levels(n), sig((size_t)n * idx->p.sketch_size * idx->elem);
+        std::vector<uint32_t> ranks(n), nidx(tn);
+        std::vector<uint64_t> off(tl + 1), ids(n);
+        std::vector<float> ndist(tn);
+        if (!rd(fg, levels.data(), n) || !rd(fg, ranks.data(), n) || !rd(fg, off.data(), tl + 1) ||
+            !rd(fg, nidx.data(), tn) || !rd(fg, ndist.data(), tn) || !rd(fd, ids.data(), n) ||
+            !rd(fd, sig.data(), sig.size())) {
+            set_error("gsb_index_load: truncated dump %s", base.c_str());
+            break;
+        }
+        rc = gsb_index_load_graph(idx, sig.data(), ids.data(), n, levels.data(), ranks.data(), off.data(),
+                                  nidx.data(), ndist.data(), hdr[7]);
+    } while (0);
+    if (fg) fclose(fg);
+    if (fd) fclose(fd);
+    return rc;
 }

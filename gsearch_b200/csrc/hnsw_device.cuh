@@ -1,0 +1,714 @@
+// hnsw_device.cuh -- K7/K8: on-device HNSW search and construction with DistHamming (sm_100a).
+//
+// Replaces hnsw_rs::Hnsw::<Sig,DistHamming>::{search, search_layer, parallel_search,
+// parallel_insert} [U] as called at src/dna/dnarequest.rs:353 (ef_search = 5000,
+// src/bin/gsearch.rs:893) and src/dna/dnasketch.rs:435 (ef_construction = --ef, extend_candidates
+// = true, keep_pruned = false, :159-160).
+//
+// One CTA owns one query (search) or one new point (insert) at a time; persistent CTAs pull work
+// from a counter (the reference's rayon par_iter).  The query signature stays in shared memory
+// (TMA bulk copy), the result heap too, and every neighbour expansion evaluates its <= 2M
+// unvisited candidates with all warps streaming candidate signatures from HBM (K6's inner loop).
+// Heap order, visit order and tie behaviour reproduce Rust's std BinaryHeap exactly (see
+// oracle/hnsw.c), so that on the same graph the returned ids are identical to the CPU
+// restatement.
+//
+// The graph is mutable and device resident: fixed-capacity adjacency (2M entries per point on
+// layer 0, M per upper layer, with the distances kept beside the indices because
+// reverse_update_neighborhood_simple keeps lists sorted by distance and drops the farthest).
+//
+// Construction follows the deterministic wave semantics of oracle/hnsw.c
+// (gso_hnsw_insert_waves): phase A = every point of a wave searches the graph as it was before
+// the wave and also sees the earlier points of its wave; phase B = own lists, then reverse
+// updates (order independent: a list keeps its M / 2M smallest by (distance, index)).
+#pragma once
+
+#include "common.cuh"
+#include "hamming.cuh"
+
+namespace gsb {
+
+constexpr int kSearchThreads = 512;
+constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255) and >= wave size
+constexpr int kMaxLayers = 17;   // levels 0..16
+
+struct HItem {
+    float d;
+    uint32_t p;
+};
+
+struct DHeap {
+    HItem *a;
+    uint32_t n;
+    __device__ __forceinline__ void sift_up(uint32_t start, uint32_t pos) {
+        const HItem e = a[pos];
+        while (pos > start) {
+            const uint32_t parent = (pos - 1) >> 1;
+            if (e.d <= a[parent].d) break;
+            a[pos] = a[parent];
+            pos = parent;
+        }
+        a[pos] = e;
+    }
+    __device__ __forceinline__ void push(float d, uint32_t p) {
+        a[n].d = d;
+        a[n].p = p;
+        n++;
+        sift_up(0, n - 1);
+    }
+    __device__ __forceinline__ void sift_down_to_bottom(uint32_t pos) {
+        const uint32_t end = n, start = pos;
+        const HItem e = a[pos];
+        uint32_t child = 2 * pos + 1;
+        while (end >= 2 && child <= end - 2) {
+            child += (a[child].d <= a[child + 1].d) ? 1u : 0u;
+            a[pos] = a[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (end >= 1 && child == end - 1) {
+            a[pos] = a[child];
+            pos = child;
+        }
+        a[pos] = e;
+        sift_up(start, pos);
+    }
+    __device__ __forceinline__ HItem pop() {
+        HItem item = a[n - 1];
+        n--;
+        if (n > 0) {
+            const HItem t = a[0];
+            a[0] = item;
+            item = t;
+            sift_down_to_bottom(0);
+        }
+        return item;
+    }
+    __device__ __forceinline__ void sift_down_range(uint32_t pos, uint32_t end) {
+        const HItem e = a[pos];
+        uint32_t child = 2 * pos + 1;
+        while (end >= 2 && child <= end - 2) {
+            child += (a[child].d <= a[child + 1].d) ? 1u : 0u;
+            if (e.d >= a[child].d) {
+                a[pos] = e;
+                return;
+            }
+            a[pos] = a[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (end >= 1 && child == end - 1 && e.d < a[child].d) {
+            a[pos] = a[child];
+            pos = child;
+        }
+        a[pos] = e;
+    }
+    __device__ __forceinline__ void into_sorted() {
+        uint32_t end = n;
+        while (end > 1) {
+            end--;
+            const HItem t = a[0];
+            a[0] = a[end];
+            a[end] = t;
+            sift_down_range(0, end);
+        }
+    }
+};
+
+struct GraphView {
+    const uint8_t *sigs;        // n x S x elem
+    const uint64_t *ids;        // origin ids
+    const uint8_t *levels;      // level of each point
+    const uint32_t *ranks;      // rank in its layer
+    uint32_t *nbr0;             // [cap x 2M] layer-0 neighbour indices, sorted by (distance, index)
+    float *dist0;               // [cap x 2M]
+    uint32_t *cnt0;             // [cap]
+    const uint32_t *upper_off;  // [cap] list index of (p, layer 1) in the upper pool
+    uint32_t *nbrU;             // [capU x M]
+    float *distU;               // [capU x M]
+    uint32_t *cntU;             // [capU]
+    uint32_t *lock0, *lockU;    // per-list locks (phase B)
+    uint32_t M, n, entry, S;
+};
+
+__device__ __forceinline__ const uint32_t *list_of(const GraphView &g, uint32_t p, uint32_t layer, uint32_t &len) {
+    if (layer == 0) {
+        len = __ldcg(&g.cnt0[p]);
+        return g.nbr0 + (size_t)p * 2 * g.M;
+    }
+    const uint32_t li = g.upper_off[p] + layer - 1;
+    len = __ldcg(&g.cntU[li]);
+    return g.nbrU + (size_t)li * g.M;
+}
+
+struct SearchOut {
+    gsb_neighbour *out;   // nq x knbn
+    uint32_t *counts;     // nq
+    unsigned long long *nb_eval;  // nq (may be null)
+};
+
+// scratch of one CTA
+struct HnswShared {
+    uint32_t E[kMaxList];
+    float D[kMaxList];
+    uint32_t wcnt[kSearchThreads / 32];
+    uint32_t done, node, flag, work;
+    float fval;
+    DHeap cand, ret;  // owned by thread 0
+};
+
+template <int ELEM, bool F32>
+__device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView &g, const uint32_t *E,
+                                          uint32_t nE, float *D) {
+    const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const size_t row = (size_t)g.S * ELEM;
+    const float fS = (float)g.S;
+    for (uint32_t i = warp; i < nE; i += nwarps) {
+        const uint32_t cnt = warp_row_count<ELEM, F32>(smem_q, g.sigs + (size_t)E[i] * row, g.S);
+        if (lane_id() == 0) D[i] = __fdiv_rn((float)cnt, fS);
+    }
+}
+
+// stage one signature row in shared memory (TMA bulk copy when alignment allows); all threads
+// must have finished reading the previous content (caller synchronises before)
+__device__ __forceinline__ void stage_row(uint8_t *smem, const uint8_t *grow, size_t row, uint64_t *bar,
+                                          uint32_t &phase) {
+    if ((row & 15) == 0 && (((uintptr_t)grow) & 15) == 0) {
+        fence_proxy_async();
+        stage_query(smem, grow, (uint32_t)row, bar, phase);
+        phase ^= 1;
+    } else {
+        for (uint32_t i = threadIdx.x; i < row; i += blockDim.x) smem[i] = grow[i];
+    }
+    __syncthreads();
+}
+
+// hnsw_rs search_layer: best-first search on one layer from `ep` (distance d_ep known), result in
+// sh.ret (max-heap of at most ef), candidates in sh.cand.  `stamps[p] == stamp` marks visited.
+template <int ELEM, bool F32>
+__device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint32_t ep, float d_ep,
+                                 uint32_t ef, uint32_t layer, HnswShared &sh, uint32_t *stamps,
+                                 uint32_t stamp, unsigned long long &neval) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sh.cand.n = 0;
+        sh.ret.n = 0;
+        stamps[ep] = stamp;
+        sh.cand.push(-d_ep, ep);
+        sh.ret.push(d_ep, ep);
+        neval += 1;  // the reference evaluates the distance to the layer's entry point again
+    }
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sh.done = 0;
+            if (sh.cand.n == 0) {
+                sh.done = 1;
+            } else {
+                const HItem c = sh.cand.pop();
+                if (-c.d > sh.ret.a[0].d) sh.done = 1;
+                sh.node = c.p;
+            }
+        }
+        __syncthreads();
+        if (sh.done) break;
+        // gather the unvisited neighbours of the popped node in list order
+        uint32_t len;
+        const uint32_t *lst = list_of(g, sh.node, layer, len);
+        uint32_t nb = 0xFFFFFFFFu;
+        bool unv = false;
+        if (threadIdx.x < len) {
+            nb = __ldcg(&lst[threadIdx.x]);
+            unv = stamps[nb] != stamp;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, unv);
+        if (lane_id() == 0) sh.wcnt[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+        for (uint32_t w = 0; w < kSearchThreads / 32; w++) {
+            if (w < (threadIdx.x >> 5)) pre += sh.wcnt[w];
+            tot += sh.wcnt[w];
+        }
+        if (unv) {
+            sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = nb;
+            stamps[nb] = stamp;
+        }
+        __syncthreads();
+        eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            neval += tot;
+            for (uint32_t i = 0; i < tot; i++) {
+                const float ed = sh.D[i];
+                if (ed < sh.ret.a[0].d || sh.ret.n < ef) {
+                    sh.cand.push(-ed, sh.E[i]);
+                    sh.ret.push(ed, sh.E[i]);
+                    if (sh.ret.n > ef) (void)sh.ret.pop();
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// per-CTA workspace layout in global memory
+struct WsLayout {
+    size_t stride;     // bytes per CTA
+    size_t off_ctr;    // uint32_t: this CTA's visit-stamp counter, kept across launches
+    size_t off_cand;   // HItem[cand_cap]
+    size_t off_stamp;  // uint32_t[ncap], zeroed when (re)allocated
+    size_t off_ret;    // HItem[ef + 2] when the result heap does not fit in shared memory
+    size_t off_newc;   // uint32_t[newc_cap] (insert: candidate extension)
+};
+
+// smem: [row: row bytes rounded to 128][ret heap: (ef+2) items if ret_in_smem]
+template <int ELEM, bool F32>
+__global__ void __launch_bounds__(kSearchThreads, 1)
+k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, uint32_t knbn, uint32_t ef,
+               int ret_in_smem, uint8_t *__restrict__ ws, WsLayout wl, SearchOut so,
+               uint32_t *__restrict__ qcounter) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ HnswShared sh;
+    __shared__ uint32_t s_q;
+    const size_t row = (size_t)g.S * ELEM;
+    const size_t row128 = (row + 127) & ~(size_t)127;
+    uint8_t *my = ws + (size_t)blockIdx.x * wl.stride;
+    uint32_t *stamps = reinterpret_cast<uint32_t *>(my + wl.off_stamp);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        sh.cand.a = reinterpret_cast<HItem *>(my + wl.off_cand);
+        sh.ret.a = ret_in_smem ? reinterpret_cast<HItem *>(smem + row128) : reinterpret_cast<HItem *>(my + wl.off_ret);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    uint32_t stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
+    for (;;) {
+        if (threadIdx.x == 0) s_q = atomicAdd(qcounter, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= nq) break;
+        stage_row(smem, queries + (size_t)q * row, row, &bar, phase);
+        unsigned long long neval = 0;
+        uint32_t pivot = g.entry;
+        if (threadIdx.x == 0) sh.E[0] = pivot;
+        __syncthreads();
+        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D);
+        __syncthreads();
+        float dist_to_entry = sh.D[0];
+        neval += 1;
+        // ---- one greedy hop per upper layer (hnsw_rs `search`)
+        const int top = g.levels[g.entry];
+        for (int layer = top; layer >= 1; layer--) {
+            uint32_t len;
+            const uint32_t *lst = list_of(g, pivot, (uint32_t)layer, len);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldcg(&lst[i]);
+            __syncthreads();
+            eval_list<ELEM, F32>(smem, g, sh.E, len, sh.D);
+            __syncthreads();
+            neval += len;
+            // every thread scans the same shared arrays: uniform result, no broadcast needed
+            uint32_t newp = pivot;
+            for (uint32_t i = 0; i < len; i++) {
+                if (sh.D[i] < dist_to_entry) {
+                    dist_to_entry = sh.D[i];
+                    newp = sh.E[i];
+                }
+            }
+            pivot = newp;
+        }
+        // ---- search_layer(q, pivot, ef, 0)
+        stamp++;
+        search_layer_dev<ELEM, F32>(g, smem, pivot, dist_to_entry, ef, 0, sh, stamps, stamp, neval);
+        if (threadIdx.x == 0) {
+            sh.ret.into_sorted();
+            uint32_t last = knbn < ef ? knbn : ef;
+            if (sh.ret.n < last) last = sh.ret.n;
+            for (uint32_t i = 0; i < last; i++) {
+                const uint32_t p = sh.ret.a[i].p;
+                gsb_neighbour nbq;
+                nbq.d_id = g.ids[p];
+                nbq.distance = sh.ret.a[i].d;
+                nbq.layer = g.levels[p];
+                nbq.pad_[0] = nbq.pad_[1] = nbq.pad_[2] = 0;
+                nbq.rank = (int32_t)g.ranks[p];
+                so.out[(size_t)q * knbn + i] = nbq;
+            }
+            so.counts[q] = last;
+            if (so.nb_eval) so.nb_eval[q] = neval;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = stamp;
+}
+
+// =========================================================================== construction
+struct WaveView {
+    uint32_t first, W;       // the wave = points [first, first + W)
+    uint32_t entry;          // entry point before the wave
+    uint32_t ef_c, extend;   // ef_construction, extend_candidates (layer 0 only)
+    uint32_t *sel_n;         // [W x kMaxLayers] selected neighbours per layer
+    uint32_t *sel_idx;       // [W x 18M] layer 0 at 0 (2M entries), layer l >= 1 at 2M + (l-1) M
+    float *sel_d;
+    uint32_t *counter;       // work counter of the wave
+};
+
+__device__ __forceinline__ size_t sel_off(uint32_t M, uint32_t t, uint32_t l) {
+    return (size_t)t * 18 * M + (l == 0 ? 0 : 2 * M + (size_t)(l - 1) * M);
+}
+
+// Phase A.  One CTA per new point: greedy descent, search_layer(ef_c) per layer, earlier points
+// of the wave merged in, select_neighbours (Malkov heuristic, extension on layer 0), sort.
+template <int ELEM, bool F32>
+__global__ void __launch_bounds__(kSearchThreads, 1)
+k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__restrict__ ws, WsLayout wl) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ HnswShared sh;
+    __shared__ uint32_t s_t, s_ep, s_nout, s_mode, s_nnew;
+    __shared__ float s_dep;
+    __shared__ uint32_t outP[kMaxList];
+    __shared__ float outD[kMaxList];
+    const size_t row = (size_t)g.S * ELEM;
+    const size_t row128 = (row + 127) & ~(size_t)127;
+    const float fS = (float)g.S;
+    uint8_t *my = ws + (size_t)blockIdx.x * wl.stride;
+    uint32_t *stamps = reinterpret_cast<uint32_t *>(my + wl.off_stamp);
+    uint32_t *newc = reinterpret_cast<uint32_t *>(my + wl.off_newc);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        sh.cand.a = reinterpret_cast<HItem *>(my + wl.off_cand);
+        sh.ret.a = ret_in_smem ? reinterpret_cast<HItem *>(smem + row128) : reinterpret_cast<HItem *>(my + wl.off_ret);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    uint32_t stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
+    unsigned long long neval = 0;
+    const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_t = atomicAdd(wv.counter, 1u);
+        __syncthreads();
+        const uint32_t t = s_t;
+        if (t >= wv.W) break;
+        const uint32_t np = wv.first + t;
+        const uint32_t level = g.levels[np];
+        const uint8_t *qrow = g.sigs + (size_t)np * row;
+        if (threadIdx.x < kMaxLayers) wv.sel_n[(size_t)t * kMaxLayers + threadIdx.x] = 0;
+        stage_row(smem, qrow, row, &bar, phase);
+        uint32_t ep = wv.entry;
+        const uint32_t lmax = g.levels[wv.entry];
+        if (threadIdx.x == 0) sh.E[0] = ep;
+        __syncthreads();
+        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D);
+        __syncthreads();
+        float d_ep = sh.D[0];
+        // ---- greedy descent through the layers above the point's level: search_layer(ef = 1)
+        for (int l = (int)lmax; l >= (int)level + 1; l--) {
+            stamp++;
+            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, 1, (uint32_t)l, sh, stamps, stamp, neval);
+            if (threadIdx.x == 0) {
+                s_ep = ep;
+                s_dep = d_ep;
+                if (sh.ret.n > 0) {
+                    const HItem e = sh.ret.pop();
+                    if (e.d < d_ep) {
+                        s_ep = e.p;
+                        s_dep = e.d;
+                    }
+                }
+            }
+            __syncthreads();
+            ep = s_ep;
+            d_ep = s_dep;
+        }
+        const int top = (int)(level < lmax ? level : lmax);
+        for (int l = top; l >= 0; l--) {
+            stamp++;
+            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, wv.ef_c, (uint32_t)l, sh, stamps, stamp, neval);
+            // ---- earlier points of this wave, in order, as if search_layer had met them last
+            {
+                const uint32_t m = wv.first + threadIdx.x;
+                const bool on = m < np && g.levels[m] >= (uint32_t)l;
+                const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                if (lane_id() == 0) sh.wcnt[warp] = __popc(bal);
+                __syncthreads();
+                uint32_t pre = 0, tot = 0;
+                for (uint32_t w = 0; w < kSearchThreads / 32; w++) {
+                    if (w < warp) pre += sh.wcnt[w];
+                    tot += sh.wcnt[w];
+                }
+                if (on) sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = m;
+                __syncthreads();
+                eval_list<ELEM, F32>(smem, g, sh.E, tot, sh.D);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (uint32_t i = 0; i < tot; i++) {
+                        const float ed = sh.D[i];
+                        if (ed < sh.ret.a[0].d || sh.ret.n < wv.ef_c) {
+                            sh.ret.push(ed, sh.E[i]);
+                            if (sh.ret.n > wv.ef_c) (void)sh.ret.pop();
+                        }
+                    }
+                    // from_positive_binaryheap_to_negative_binary_heap: push in underlying-vec order
+                    sh.cand.n = 0;
+                    for (uint32_t i = 0; i < sh.ret.n; i++) sh.cand.push(-sh.ret.a[i].d, sh.ret.a[i].p);
+                }
+                __syncthreads();
+            }
+            // ---- select_neighbours
+            const uint32_t nb_asked = l == 0 ? 2 * g.M : g.M;
+            const bool extend_asked = l == 0 && wv.extend != 0;
+            if (threadIdx.x == 0) {
+                s_nout = 0;
+                s_mode = 1;  // heuristic
+                if (sh.cand.n <= nb_asked) s_mode = extend_asked ? 2u : 0u;
+                if (s_mode == 0) {  // few candidates, no extension: take them all, nearest first
+                    while (sh.cand.n > 0) {
+                        const HItem p = sh.cand.pop();
+                        outP[s_nout] = p.p;
+                        outD[s_nout] = -p.d;
+                        s_nout++;
+                    }
+                }
+                if (s_mode == 2) {  // extension: the neighbours of the candidates join them
+                    stamp++;        // (thread 0's copy; re-broadcast below)
+                    const uint32_t n0 = sh.cand.n;
+                    for (uint32_t i = 0; i < n0; i++) stamps[sh.cand.a[i].p] = stamp;
+                    uint32_t nnew = 0;
+                    for (uint32_t i = 0; i < n0; i++) {
+                        uint32_t len;
+                        const uint32_t *lst = list_of(g, sh.cand.a[i].p, (uint32_t)l, len);
+                        for (uint32_t j = 0; j < len; j++) {
+                            const uint32_t e = __ldcg(&lst[j]);
+                            if (stamps[e] == stamp) continue;
+                            stamps[e] = stamp;
+                            newc[nnew++] = e;
+                        }
+                    }
+                    s_nnew = nnew;
+                }
+                sh.work = stamp;
+            }
+            __syncthreads();
+            stamp = sh.work;
+            if (s_mode == 2) {
+                const uint32_t nnew = s_nnew;
+                for (uint32_t c0 = 0; c0 < nnew; c0 += kMaxList) {
+                    const uint32_t nc = nnew - c0 < (uint32_t)kMaxList ? nnew - c0 : (uint32_t)kMaxList;
+                    __syncthreads();
+                    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) sh.E[i] = newc[c0 + i];
+                    __syncthreads();
+                    eval_list<ELEM, F32>(smem, g, sh.E, nc, sh.D);
+                    __syncthreads();
+                    if (threadIdx.x == 0)
+                        for (uint32_t i = 0; i < nc; i++) sh.cand.push(-sh.D[i], sh.E[i]);
+                }
+                __syncthreads();
+            }
+            if (s_mode != 0) {
+                // Malkov heuristic: a candidate is kept unless an already selected point is
+                // at least as close to it as the new point is
+                for (;;) {
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        sh.done = 0;
+                        if (sh.cand.n == 0 || s_nout >= nb_asked) {
+                            sh.done = 1;
+                        } else {
+                            const HItem e = sh.cand.pop();
+                            sh.node = e.p;
+                            sh.fval = -e.d;
+                        }
+                        sh.flag = 0;
+                    }
+                    __syncthreads();
+                    if (sh.done) break;
+                    const uint32_t nout = s_nout;
+                    if (nout > 0) {
+                        stage_row(smem, g.sigs + (size_t)sh.node * row, row, &bar, phase);
+                        const float ed = sh.fval;
+                        for (uint32_t c0 = 0; c0 < nout; c0 += nwarps) {
+                            const uint32_t i = c0 + warp;
+                            if (i < nout) {
+                                const uint32_t cnt =
+                                    warp_row_count<ELEM, F32>(smem, g.sigs + (size_t)outP[i] * row, g.S);
+                                if (lane_id() == 0 && __fdiv_rn((float)cnt, fS) <= ed) sh.flag = 1;
+                            }
+                            __syncthreads();
+                            if (sh.flag) break;
+                        }
+                    }
+                    if (threadIdx.x == 0 && !sh.flag) {
+                        outP[s_nout] = sh.node;
+                        outD[s_nout] = sh.fval;
+                        s_nout++;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- sort by (distance, index) and publish; next entry = nearest selected point
+            // that is not of this wave
+            const uint32_t nout = s_nout;
+            if (threadIdx.x == 0) {
+                s_ep = ep;
+                s_dep = d_ep;
+                sh.work = 0xFFFFFFFFu;  // best rank of an old point
+            }
+            __syncthreads();
+            const size_t so = sel_off(g.M, t, (uint32_t)l);
+            if (threadIdx.x < nout) {
+                const float d = outD[threadIdx.x];
+                const uint32_t p = outP[threadIdx.x];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < nout; j++) {
+                    const float dj = outD[j];
+                    const uint32_t pj = outP[j];
+                    rank += (dj < d || (dj == d && pj < p)) ? 1u : 0u;
+                }
+                wv.sel_idx[so + rank] = p;
+                wv.sel_d[so + rank] = d;
+                if (p < wv.first) atomicMin(&sh.work, rank);
+            }
+            __syncthreads();
+            if (threadIdx.x < nout) {
+                const float d = outD[threadIdx.x];
+                const uint32_t p = outP[threadIdx.x];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < nout; j++) {
+                    const float dj = outD[j];
+                    const uint32_t pj = outP[j];
+                    rank += (dj < d || (dj == d && pj < p)) ? 1u : 0u;
+                }
+                if (rank == sh.work) {
+                    s_ep = p;
+                    s_dep = d;
+                }
+            }
+            if (threadIdx.x == 0) wv.sel_n[(size_t)t * kMaxLayers + l] = nout;
+            __syncthreads();
+            ep = s_ep;
+            d_ep = s_dep;
+            if (l > 0 && s_mode != 0) stage_row(smem, qrow, row, &bar, phase);  // the heuristic replaced q
+        }
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = stamp;
+}
+
+// Phase B, step 1: the selections become the lists of the new points
+__global__ void __launch_bounds__(256)
+k9_write_own_lists(GraphView g, WaveView wv) {
+    const uint32_t t = blockIdx.x;
+    if (t >= wv.W) return;
+    const uint32_t np = wv.first + t;
+    const uint32_t level = g.levels[np];
+    for (uint32_t l = 0; l <= level; l++) {
+        const uint32_t ns = wv.sel_n[(size_t)t * kMaxLayers + l];
+        const size_t so = sel_off(g.M, t, l);
+        uint32_t *idx;
+        float *dst;
+        if (l == 0) {
+            idx = g.nbr0 + (size_t)np * 2 * g.M;
+            dst = g.dist0 + (size_t)np * 2 * g.M;
+            if (threadIdx.x == 0) g.cnt0[np] = ns;
+        } else {
+            const uint32_t li = g.upper_off[np] + l - 1;
+            idx = g.nbrU + (size_t)li * g.M;
+            dst = g.distU + (size_t)li * g.M;
+            if (threadIdx.x == 0) g.cntU[li] = ns;
+        }
+        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+            idx[i] = wv.sel_idx[so + i];
+            dst[i] = wv.sel_d[so + i];
+        }
+    }
+}
+
+// Phase B, step 2: reverse_update_neighborhood_simple.  One warp per arrival; the target list is
+// locked, the new point inserted at its (distance, index) position, the farthest dropped when the
+// list is full.  Keeping the M / 2M smallest of a totally ordered set does not depend on the
+// order of arrivals, so the result equals the sequential one.
+__global__ void __launch_bounds__(256)
+k9_reverse_updates(GraphView g, WaveView wv) {
+    const uint32_t t = blockIdx.x;
+    if (t >= wv.W) return;
+    const uint32_t np = wv.first + t;
+    const uint32_t level = g.levels[np];
+    const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = lane_id();
+    for (uint32_t l = 0; l <= level; l++) {
+        const uint32_t ns = wv.sel_n[(size_t)t * kMaxLayers + l];
+        const size_t so = sel_off(g.M, t, l);
+        const uint32_t thr = l == 0 ? 2 * g.M : g.M;
+        for (uint32_t i = warp; i < ns; i += nwarps) {
+            const uint32_t qp = wv.sel_idx[so + i];
+            const float d = wv.sel_d[so + i];
+            if (qp == np || l > g.levels[qp]) continue;
+            volatile uint32_t *idx;
+            volatile float *dst;
+            volatile uint32_t *cnt;
+            uint32_t *lock;
+            if (l == 0) {
+                idx = g.nbr0 + (size_t)qp * 2 * g.M;
+                dst = g.dist0 + (size_t)qp * 2 * g.M;
+                cnt = g.cnt0 + qp;
+                lock = g.lock0 + qp;
+            } else {
+                const uint32_t li = g.upper_off[qp] + l - 1;
+                idx = g.nbrU + (size_t)li * g.M;
+                dst = g.distU + (size_t)li * g.M;
+                cnt = g.cntU + li;
+                lock = g.lockU + li;
+            }
+            if (lane == 0) {
+                while (atomicCAS(lock, 0u, 1u) != 0u) {
+                }
+                __threadfence();
+            }
+            __syncwarp();
+            const uint32_t n = *cnt;
+            // this lane's entries (n <= 510 -> at most 16 per lane), and the insertion position
+            uint32_t ri[16];
+            float rd[16];
+            uint32_t pos = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t j = lane + 32 * k;
+                if (j < n) {
+                    ri[k] = idx[j];
+                    rd[k] = dst[j];
+                    pos += (rd[k] < d || (rd[k] == d && ri[k] < np)) ? 1u : 0u;
+                }
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, s);
+            __syncwarp();
+            if (!(n == thr && pos == n)) {  // otherwise the new point would be the one dropped
+                const uint32_t nn = n == thr ? n : n + 1;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t j = lane + 32 * k;
+                    if (j < n && j >= pos && j + 1 < nn) {
+                        idx[j + 1] = ri[k];
+                        dst[j + 1] = rd[k];
+                    }
+                }
+                if (lane == 0) {
+                    idx[pos] = np;
+                    dst[pos] = d;
+                    *cnt = nn;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(lock, 0u);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace gsb

@@ -46,7 +46,28 @@ class Hnsw:
         _lib.check(_lib.lib().gsb_index_insert_batch(self._h, C.c_void_p(sigs.ctypes.data),
                                                      C.c_void_p(ids.ctypes.data), len(ids)))
 
-    def load_graph(self, sigs, ids, levels, ranks, nbr_offsets, nbr_index, entry_point):
+    def set_wave_max(self, wave_max):
+        _lib.check(_lib.lib().gsb_index_set_wave_max(self._h, int(wave_max)))
+
+    def export_graph(self):
+        """graph image (same keys as the oracle's export): levels, ranks, ids, CSR lists, entry"""
+        n = self.get_nb_point()
+        tl, tn = C.c_uint64(), C.c_uint64()
+        _lib.check(_lib.lib().gsb_index_graph_sizes(self._h, C.byref(tl), C.byref(tn)))
+        levels = np.zeros(max(n, 1), dtype=np.uint8)
+        ranks = np.zeros(max(n, 1), dtype=np.uint32)
+        ids = np.zeros(max(n, 1), dtype=np.uint64)
+        off = np.zeros(tl.value + 1, dtype=np.uint64)
+        idx = np.zeros(max(tn.value, 1), dtype=np.uint32)
+        dist = np.zeros(max(tn.value, 1), dtype=np.float32)
+        entry = C.c_uint64()
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(_lib.lib().gsb_index_export_graph(self._h, p(levels), p(ranks), p(ids), p(off), p(idx), p(dist),
+                                                     C.byref(entry)))
+        return dict(levels=levels[:n], ranks=ranks[:n], ids=ids[:n], nbr_offsets=off, nbr_index=idx[:tn.value],
+                    nbr_dist=dist[:tn.value], entry_point=entry.value)
+
+    def load_graph(self, sigs, ids, levels, ranks, nbr_offsets, nbr_index, entry_point, nbr_dist=None):
         sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
         ids = np.ascontiguousarray(ids, dtype=np.uint64)
         levels = np.ascontiguousarray(levels, dtype=np.uint8)
@@ -54,8 +75,12 @@ class Hnsw:
         nbr_offsets = np.ascontiguousarray(nbr_offsets, dtype=np.uint64)
         nbr_index = np.ascontiguousarray(nbr_index, dtype=np.uint32)
         p = lambda a: C.c_void_p(a.ctypes.data)
+        if nbr_dist is not None:
+            nbr_dist = np.ascontiguousarray(nbr_dist, dtype=np.float32)
         _lib.check(_lib.lib().gsb_index_load_graph(self._h, p(sigs), p(ids), len(ids), p(levels), p(ranks),
-                                                   p(nbr_offsets), p(nbr_index), int(entry_point)))
+                                                   p(nbr_offsets), p(nbr_index),
+                                                   p(nbr_dist) if nbr_dist is not None else C.c_void_p(0),
+                                                   int(entry_point)))
 
     def search_raw(self, queries, knbn, ef):
         """-> (structured neighbour array nq x knbn, counts, nb_eval)"""

@@ -219,13 +219,26 @@ GSB_API int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t
                                    uint32_t *counts_out, uint64_t *nb_eval_out);
 /* get_nb_point() */
 GSB_API uint64_t gsb_index_nb_point(const gsb_index *idx);
-/* Load an externally built graph (CSR-like, see DESIGN.md "graph image") so a graph
- * built elsewhere (the oracle, or a converted hnswdump) can be searched on device. */
+/* Load an externally built graph (CSR-like image) so a graph built elsewhere
+ * (the oracle, or a converted hnswdump) can be searched on device.  nbr_dist (the distance of
+ * every listed neighbour) may be NULL: the graph can then be searched but not extended.     */
 GSB_API int gsb_index_load_graph(gsb_index *idx, const void *sigs, const uint64_t *ids,
                                  uint64_t n, const uint8_t *levels, const uint32_t *ranks,
-                                 const uint64_t *nbr_offsets /* n*(level+1)+1 prefix */,
-                                 const uint32_t *nbr_index, uint64_t entry_point);
-/* file_dump(dir, basename) / HnswIo::load_hnsw */
+                                 const uint64_t *nbr_offsets /* sum(level+1) + 1 prefix */,
+                                 const uint32_t *nbr_index, const float *nbr_dist,
+                                 uint64_t entry_point);
+/* The same image back: sizes first (sum over points of level+1, total neighbours), then fill.
+ * Any output pointer except nbr_offsets / entry_point may be NULL.                          */
+GSB_API int gsb_index_graph_sizes(const gsb_index *idx, uint64_t *total_lists, uint64_t *total_nbrs);
+GSB_API int gsb_index_export_graph(const gsb_index *idx, uint8_t *levels, uint32_t *ranks,
+                                   uint64_t *ids, uint64_t *nbr_offsets, uint32_t *nbr_index,
+                                   float *nbr_dist, uint64_t *entry_point);
+/* Points inserted together by gsb_index_insert_batch (the reference inserts with one rayon
+ * task per point, src/dna/dnasketch.rs:435; here a wave of at most wave_max points searches
+ * the graph as it was before the wave).  Default = number of SMs; 1 = sequential insertion. */
+GSB_API int gsb_index_set_wave_max(gsb_index *idx, uint32_t wave_max);
+/* file_dump(dir, basename) / HnswIo::load_hnsw: <basename>.hnsw.graph + <basename>.hnsw.data in
+ * this library's own layout; hnswio byte compatibility is not claimed         */
 GSB_API int gsb_index_dump(const gsb_index *idx, const char *dir, const char *basename);
 GSB_API int gsb_index_load(gsb_index *idx, const char *dir, const char *basename);
 

@@ -457,9 +457,10 @@ int gso_hnsw_insert(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t
  *              of its own wave, by exact distance, as if search_layer had met them last;
  *              select_neighbours as usual (points of the wave have no lists yet); the entry of
  *              the next lower layer is the nearest selected point that is not of this wave;
- *   phase B    in order: the point's lists are written, reverse updates applied
- *              (list_add_sorted_shrink keeps the M / 2M smallest by (distance, index), so the
- *              result does not depend on the order of arrivals), entry point updated.
+ *   phase B    the lists of all points of the wave are written, then, in order, reverse updates
+ *              are applied (list_add_sorted_shrink keeps the M / 2M smallest by (distance,
+ *              index), so the result does not depend on the order of arrivals) and the entry
+ *              point is updated.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     uint32_t n[17];
@@ -533,26 +534,22 @@ static void wave_phase_a(gso_hnsw *h, uint32_t np, uint32_t first, uint32_t entr
     }
 }
 
-static void wave_phase_b(gso_hnsw *h, uint32_t np, wave_sel *ws) {
+/* phase B, step 1: the point's own selection becomes its lists (already sorted by (d, index)) */
+static void wave_phase_b_own(gso_hnsw *h, uint32_t np, wave_sel *ws) {
     const uint32_t level = h->level[np];
     for (uint32_t l = 0; l <= level && l < 17; l++) {
         nlist *nl = &h->nbrs[np][l];
-        /* arrivals from earlier points of the wave may already be there: merge */
+        nl->n = ws->n[l];
         for (uint32_t i = 0; i < ws->n[l]; i++) {
-            /* own selection: sorted insert without the duplicate test hitting (distinct points) */
-            uint32_t pos = nl->n;
-            const float d = ws->l[l][i].d;
-            const uint32_t p = ws->l[l][i].p;
-            while (pos > 0 && (nl->dist[pos - 1] > d || (nl->dist[pos - 1] == d && nl->idx[pos - 1] > p))) {
-                nl->dist[pos] = nl->dist[pos - 1];
-                nl->idx[pos] = nl->idx[pos - 1];
-                pos--;
-            }
-            nl->dist[pos] = d;
-            nl->idx[pos] = p;
-            nl->n++;
+            nl->idx[i] = ws->l[l][i].p;
+            nl->dist[i] = ws->l[l][i].d;
         }
     }
+}
+
+/* phase B, step 2: reverse updates and entry point, after ALL own lists of the wave are set */
+static void wave_phase_b_reverse(gso_hnsw *h, uint32_t np, wave_sel *ws) {
+    const uint32_t level = h->level[np];
     for (int l = (int)level; l >= 0; l--) {
         for (uint32_t i = 0; i < ws->n[l]; i++) {
             const uint32_t qp = ws->l[l][i].p;
@@ -595,8 +592,9 @@ int gso_hnsw_insert_waves(gso_hnsw *h, const void *sigs, const uint64_t *ids, ui
         const uint32_t entry = (uint32_t)h->entry;
         for (uint64_t t = 0; t < W; t++)
             wave_phase_a(h, first + (uint32_t)t, first, entry, &ret, &cand, selbuf, &ws[t]);
+        for (uint64_t t = 0; t < W; t++) wave_phase_b_own(h, first + (uint32_t)t, &ws[t]);
         for (uint64_t t = 0; t < W; t++) {
-            wave_phase_b(h, first + (uint32_t)t, &ws[t]);
+            wave_phase_b_reverse(h, first + (uint32_t)t, &ws[t]);
             for (int l = 0; l < 17; l++) free(ws[t].l[l]);
         }
         free(ws);

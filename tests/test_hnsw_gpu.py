@@ -46,7 +46,7 @@ def load(h, sigs, M, ef_c):
     gr = h.export()
     idx = g.Hnsw(g.HnswParams(max_nb_conn=M, ef=ef_c), sigs.shape[1], sigs.dtype)
     idx.load_graph(sigs, gr["ids"], gr["levels"], gr["ranks"], gr["nbr_offsets"], gr["nbr_index"],
-                   gr["entry_point"])
+                   gr["entry_point"], gr["nbr_dist"])
     return idx
 
 
