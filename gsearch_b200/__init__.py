@@ -7,7 +7,7 @@ every compute call raises :class:`GsbError` when no B200 is visible.
 """
 from ._lib import GsbError, lib, lib_path, version, device_count  # noqa: F401
 from .params import (  # noqa: F401
-    ALGO_PROB3A, ALGO_SUPER, ALGO_OPTDENS, DATA_DNA, DATA_AA,
+    ALGO_PROB3A, ALGO_SUPER, ALGO_OPTDENS, ALGO_REVOPTDENS, ALGO_SUPER2, ALGO_HLL, DATA_DNA, DATA_AA,
     SIG_U32, SIG_U64, SIG_F32, SIG_U16, SPEC_NOHASH_IDENTITY, SPEC_OPTDENS_F64_DRAW,
     SeqSketcherParams, HnswParams, sig_dtype,
 )

@@ -213,8 +213,8 @@ extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, 
         set_error("sketch_size %u out of range 2..65535", p.sketch_size);
         return GSB_ERR_INVALID_ARG;
     }
-    if (p.algo != GSB_ALGO_PROB3A && p.algo != GSB_ALGO_OPTDENS) {
-        set_error("algo %u is not built on the device path yet (prob, optdens are)", p.algo);
+    if (p.algo != GSB_ALGO_PROB3A && p.algo != GSB_ALGO_OPTDENS && p.algo != GSB_ALGO_SUPER) {
+        set_error("algo %u is not built on the device path yet (prob, optdens, super are)", p.algo);
         return p.algo <= GSB_ALGO_HLL ? GSB_ERR_UNSUPPORTED : GSB_ERR_INVALID_ARG;
     }
     int rc = check_device(device);
@@ -429,7 +429,7 @@ void launch_dens(gsb_sketcher *h, uint32_t njobs, uint32_t nchunks, bool dna, bo
     }
     Timed t3_(h, CAT_K3, st);
     k3_optdens_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (float *)d_sig, d_nb,
-                                               h->d_retry.as<uint32_t>());
+                                               h->d_retry.as<uint32_t>(), h->p.algo == GSB_ALGO_SUPER ? 1 : 0);
     h->launches += nchunks ? 2 : 1;
 }
 
@@ -563,6 +563,38 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     }
     GSB_CUDA_TRY(cudaGetLastError());
     GSB_CUDA_TRY(cudaMemcpyAsync(h->h_overflow.p, h->d_overflow.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    return GSB_OK;
+}
+
+// SuperMinHash cold path: files whose k-mers do not reach every slot at the first level
+template <class Src, typename KT>
+void launch_super_seq(gsb_sketcher *h, uint32_t nlist, bool dna, bool want_bounds, void *d_sig, cudaStream_t st) {
+    k_super_sequential<Src, KT><<<(nlist + 31) / 32, 32, 0, st>>>(
+        h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(),
+        dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+        want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, (float *)d_sig, h->d_bins.as<uint32_t>());
+    h->launches += 1;
+}
+
+int run_super_sequential(gsb_sketcher *h, const std::vector<uint32_t> &list, void *d_sig, cudaStream_t st) {
+    const bool dna = h->p.data_t == GSB_DATA_DNA;
+    const bool want_bounds = dna && !h->p.block_flag;
+    const uint32_t nl = (uint32_t)list.size();
+    int rc;
+    if ((rc = h->h_jobs.ensure((size_t)nl * 4))) return rc;
+    if ((rc = h->d_jobs.ensure((size_t)nl * 4))) return rc;
+    if ((rc = h->d_bins.ensure((size_t)nl * 3 * h->sc.m * 4))) return rc;
+    memcpy(h->h_jobs.p, list.data(), (size_t)nl * 4);
+    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, h->h_jobs.p, (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+    if (dna) {
+        if (h->kt32) launch_super_seq<SrcDNA<uint32_t>, uint32_t>(h, nl, true, want_bounds, d_sig, st);
+        else launch_super_seq<SrcDNA<uint64_t>, uint64_t>(h, nl, true, want_bounds, d_sig, st);
+    } else {
+        if (h->kt32) launch_super_seq<SrcAA<uint32_t>, uint32_t>(h, nl, false, false, d_sig, st);
+        else launch_super_seq<SrcAA<uint64_t>, uint64_t>(h, nl, false, false, d_sig, st);
+    }
+    GSB_CUDA_TRY(cudaGetLastError());
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));
     return GSB_OK;
 }
 
@@ -702,6 +734,7 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     std::vector<uint32_t> todo(n);
     std::vector<double> tmult(n, 1.0);
     for (uint32_t i = 0; i < n; i++) todo[i] = i;
+    std::vector<uint32_t> seq_files;  // SuperMinHash: files for the sequential cold path
     for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++) {
         rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp)
                   : run_dens(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st);
@@ -738,6 +771,7 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
                 next.push_back(f);
                 next_t.push_back(prob ? tmult[i] * 8.0 : 1e30);
             }
+            if (hr[f] & 2u) seq_files.push_back(f);
         }
         h->retries += next.size();
         todo.swap(next);
@@ -746,6 +780,10 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     if (!todo.empty()) {
         set_error("early-stop bound did not converge for %zu file(s)", todo.size());
         return GSB_ERR_CUDA;
+    }
+    if (!seq_files.empty()) {
+        h->retries += seq_files.size();
+        if ((rc = run_super_sequential(h, seq_files, d_sig_out, st))) return rc;
     }
     return GSB_OK;
 }

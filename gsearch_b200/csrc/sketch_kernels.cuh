@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(256)
 k3_optdens_finalize(const DensJob *__restrict__ jobs, uint32_t njobs,
                     const FileResult *__restrict__ res, SketchConsts sc,
                     float *__restrict__ sig_out, uint64_t *__restrict__ nb_bases_out,
-                    uint32_t *__restrict__ retry) {
+                    uint32_t *__restrict__ retry, int super_mode) {
     const uint32_t j = blockIdx.x;
     if (j >= njobs) return;
     const DensJob job = jobs[j];
@@ -794,15 +794,18 @@ k3_optdens_finalize(const DensJob *__restrict__ jobs, uint32_t njobs,
     const bool ok_status = fr.status == 0;
     // with a bound in force every bin must have ended strictly below it
     const bool need_retry = ok_status && nk > 0 && bounded && !(__uint_as_float(smax[0]) < Tf);
+    const uint32_t nempty = snempty;
+    // SuperMinHash: the bins ARE the signature when every slot was reached by a first-level
+    // value (r + 0 < 1 <= any later level); otherwise the file goes to the sequential kernel
+    const bool need_seq = super_mode && ok_status && nk > 0 && !need_retry && nempty != 0;
     if (threadIdx.x == 0) {
-        retry[job.file] = (need_retry ? 1u : 0u) | (fr.status << 8);
+        retry[job.file] = (need_retry ? 1u : 0u) | (need_seq ? 2u : 0u) | (fr.status << 8);
         if (nb_bases_out) nb_bases_out[job.file] = fr.nbases;
     }
     float *out = sig_out + (size_t)job.file * sc.m;
-    const uint32_t nempty = snempty;
     for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
         uint32_t b = job.bins[k];
-        if (b == kDensLargeBits && nempty != sc.m && !need_retry) {
+        if (b == kDensLargeBits && nempty != sc.m && !need_retry && !super_mode) {
             // end_sketch(): densification of an empty bin (SPEC: rng seeded by the bin index,
             // draw j until bin j was filled before densification)
             Xoshiro rng;
@@ -817,6 +820,82 @@ k3_optdens_finalize(const DensJob *__restrict__ jobs, uint32_t njobs,
             }
         }
         out[k] = __uint_as_float(b);
+    }
+}
+
+// ------------------------------------------------------------------ SuperMinHash, cold path
+// probminhash SuperMinHash::sketch [U; oracle/sketch.c gso_superminhash] restated
+// sequentially for the files whose k-mers do not reach every slot at the first level (fewer
+// k-mers than about m ln m: tiny inputs).  One thread per file; q/p/b live in global scratch.
+template <class Src, typename KT>
+__global__ void k_super_sequential(const uint32_t *__restrict__ file_list, uint32_t nlist,
+                                   const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+                                   const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+                                   const uint32_t *__restrict__ boundaries, SketchConsts sc,
+                                   float *__restrict__ sig_out, uint32_t *__restrict__ scratch) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nlist) return;
+    const uint32_t f = file_list[li];
+    const FileResult fr = res[f];
+    const FileDesc fd = files[f];
+    const uint32_t m = sc.m;
+    float *sig = sig_out + (size_t)f * m;
+    uint32_t *q = scratch + (size_t)li * 3 * m, *p = q + m;
+    int32_t *b = reinterpret_cast<int32_t *>(p + m);
+    for (uint32_t i = 0; i < m; i++) {
+        sig[i] = __uint_as_float(kDensLargeBits);
+        q[i] = 0xFFFFFFFFu;
+        p[i] = 0;
+        b[i] = 0;
+    }
+    b[m - 1] = (int32_t)m;
+    uint32_t a_upper = m - 1;
+    SeqView sv;
+    sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
+    sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
+    sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
+    sv.nbounds = boundaries ? fr.nrec : 0;
+    sv.N = fr.nsym;
+    for (uint32_t p0 = 0; p0 < fr.nsym; p0 += kRun) {
+        Src src;
+        src.init(sv, p0, sc.k);
+        for (uint32_t i = 0; i < kRun; i++) {
+            KT val;
+            if (!src.step(i, val)) continue;
+            const uint32_t irank = p0 + i;
+            Xoshiro rng;
+            rng.seed((uint64_t)val * kFxSeed64);
+            uint32_t j = 0;
+            while (j <= a_upper) {
+                const float r = u01_f32_from_bits(rng.next());
+                const uint64_t range = (uint64_t)(m - j);
+                const uint32_t k = j + uniform_usize(rng, range, UINT64_MAX - ((UINT64_MAX - range + 1) % range));
+                if (q[j] != irank) {
+                    q[j] = irank;
+                    p[j] = j;
+                }
+                if (q[k] != irank) {
+                    q[k] = irank;
+                    p[k] = k;
+                }
+                const uint32_t t = p[j];
+                p[j] = p[k];
+                p[k] = t;
+                const float rpj = __fadd_rn(r, (float)j);
+                const uint32_t slot = p[j];
+                if (rpj < sig[slot]) {
+                    const float old = sig[slot];
+                    const uint32_t j2 = (old >= (float)(m - 1)) ? (m - 1) : (uint32_t)old;
+                    sig[slot] = rpj;
+                    if (j < j2) {
+                        b[j2] -= 1;
+                        b[j] += 1;
+                        while (b[a_upper] == 0) a_upper--;
+                    }
+                }
+                j++;
+            }
+        }
     }
 }
 

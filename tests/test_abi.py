@@ -41,7 +41,7 @@ def test_parameter_validation_happens_before_device_probe():
             g.Sketcher(bad)
         assert e.value.status == 1
     with pytest.raises(g.GsbError) as e:
-        g.Sketcher(g.SeqSketcherParams(21, 1000, algo=g.ALGO_SUPER))
+        g.Sketcher(g.SeqSketcherParams(21, 1000, algo=g.ALGO_HLL))
     assert e.value.status == 6
 
 
@@ -62,7 +62,7 @@ def test_no_cpu_fallback():
 def test_sig_type_table_matches_oracle(oracle):
     for data_t, ks in ((g.DATA_DNA, range(1, 32)), (g.DATA_AA, range(1, 13))):
         for k in ks:
-            for algo in (g.ALGO_PROB3A, g.ALGO_OPTDENS):
+            for algo in (g.ALGO_PROB3A, g.ALGO_OPTDENS, g.ALGO_SUPER):
                 assert g.SeqSketcherParams(k, 64, algo, data_t).sig_type() == oracle.sig_type(k, 64, algo, data_t)
 
 

@@ -112,3 +112,20 @@ def test_estimates_jaccard_between_family_members(oracle):
     d = g.DistHamming().matrix(sig, sig)
     assert (np.diag(d) == 0).all()
     assert d[0, 1] < d[0, 2] < 0.9 < d[0, 3]     # substitution rates 0.5 % < 1 % ; stranger ~ 1
+
+
+@pytest.mark.parametrize("k,S", [(21, 1800), (16, 256)])
+def test_super_dna(oracle, k, S):
+    # adversarial files are small: most of them take the sequential cold path of SuperMinHash
+    assert_same(*run_both(oracle, adversarial_dna_files(k), k, S, g.ALGO_SUPER))
+
+
+def test_super_fast_path_and_aa(oracle):
+    # enough k-mers to reach every slot at the first level: the one-pass bin-min path
+    files = [g.synth.dna_genome(i, 400_000) for i in range(3)]
+    sk = g.Sketcher(g.SeqSketcherParams(21, 2048, g.ALGO_SUPER))
+    got, nb = sk.sketch_files(files)
+    assert sk.retry_count == 0
+    want, wnb = oracle.sketch_files(files, 21, 2048, g.ALGO_SUPER, nthreads=3)
+    assert_same(got, nb, want, wnb)
+    assert_same(*run_both(oracle, adversarial_aa_files(2), 7, 500, g.ALGO_SUPER, g.DATA_AA))
