@@ -45,6 +45,15 @@ def parse_args():
     ap.add_argument("--sketch", type=int, default=18000)
     ap.add_argument("--algo", default="prob", choices=["prob", "optdens"])
     ap.add_argument("--cpu-sample", type=int, default=32, help="genomes in the CPU baseline sample")
+    # secondary workload (BASELINE configs[2] shape): build an HNSW index on device, then search it
+    ap.add_argument("--workload", default="sketch", choices=["sketch", "request"])
+    ap.add_argument("--db", type=int, default=4096, help="request: signatures in the index")
+    ap.add_argument("--queries", type=int, default=296, help="request: queries per step")
+    ap.add_argument("--nbng", type=int, default=128, help="request: max_nb_connection (-n of tohnsw)")
+    ap.add_argument("--ef", type=int, default=1600, help="request: ef_construction (--ef of tohnsw)")
+    ap.add_argument("--ef-search", type=int, default=1600)
+    ap.add_argument("--knbn", type=int, default=50)
+    ap.add_argument("--cpu-queries", type=int, default=16, help="request: queries in the CPU baseline sample")
     return ap.parse_args()
 
 
@@ -326,9 +335,102 @@ def cpu_baseline(a):
             "sample": f"{sample} x {a.genome_len} bp genomes, one genome per thread (oracle/, C restatement)"}
 
 
+# --------------------------------------------------------------------------- request workload
+def tree_signatures(torch, n, S, dev, seed):
+    """synthetic u64 signatures with graded distances (a random recursive tree: every point keeps
+    a random 50-95 % of the slots of a random earlier point), generated on the device"""
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    base = torch.randint(1, 2**40, (n, S), dtype=torch.int64, device=dev, generator=gen)
+    par = (torch.rand(n, device=dev, generator=gen) * torch.arange(n, device=dev)).long().clamp_(min=0)
+    keep = 0.5 + 0.45 * torch.rand(n, device=dev, generator=gen)
+    par_h, keep_h = par.tolist(), keep.tolist()
+    for i in range(1, n):
+        m = torch.rand(S, device=dev, generator=gen) < keep_h[i]
+        base[i] = torch.where(m, base[par_h[i]], base[i])
+    return base
+
+
+def run_request(a):
+    """queries/sec of `request` on one GPU: index built on device by gsb_index_insert_batch_dev
+    (timed: genomes/s inserted), then searched with gsb_index_search_batch (host queries in,
+    host neighbours out).  Roofline: every distance evaluation streams one candidate signature
+    (S * 8 bytes) from HBM; the kernel reports the evaluations it performed."""
+    import torch
+    import gsearch_b200 as g
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the library has no CPU path")
+    dev = torch.device("cuda", 0)
+    S, n, nq = a.sketch, a.db, a.queries
+    base = tree_signatures(torch, n, S, dev, 1234)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    pick = torch.randint(0, n, (nq,), device=dev, generator=gen)
+    fresh = torch.randint(1, 2**40, (nq, S), dtype=torch.int64, device=dev, generator=gen)
+    queries = torch.where(torch.rand(nq, S, device=dev, generator=gen) < 0.9, base[pick], fresh)
+    h_q = queries.cpu().numpy().view(np.uint64)
+    torch.cuda.synchronize()
+    idx = g.Hnsw(g.HnswParams(max_nb_conn=a.nbng, ef=a.ef), S, np.uint64)
+    t0 = time.perf_counter()
+    idx.insert_device(base.data_ptr(), np.arange(n, dtype=np.uint64))
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    clocks = ClockSampler(0)
+    for _ in range(max(1, min(a.warmup, 2))):
+        out, cnt, neval = idx.search_raw(h_q, a.knbn, a.ef_search)
+    steps = max(1, min(a.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out, cnt, neval = idx.search_raw(h_q, a.knbn, a.ef_search)
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    qps = nq * steps / dt
+    peak, peak_src = measured_peak_gbs()
+    bytes_step = float(neval.sum()) * S * 8
+    achieved = bytes_step * steps / 1e9 / dt
+    # recall against brute force on a few queries (size-independent sanity inside the bench)
+    d = g.DistHamming().matrix(h_q[:8], base.cpu().numpy().view(np.uint64))
+    hits = sum(int((out["distance"][i][:cnt[i]] <= np.sort(d[i])[a.knbn - 1]).sum()) for i in range(8))
+    line = {
+        "metric": "queries/sec (request)", "value": qps, "unit": "queries/s", "n_gpus": 1, "steps": steps,
+        "warmup": max(1, min(a.warmup, 2)), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"configs[2] shape at reduced size: {nq} queries vs {n}-signature HNSW built on "
+                               f"device (s={S} n={a.nbng} ef={a.ef}), ef_search={a.ef_search}, knbn={a.knbn}",
+                   "l2": f"index signatures {n * S * 8 / 1e9:.2f} GB, larger than L2"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * S * 8),
+                "d2h_bytes_per_step": int(nq * a.knbn * 24 + nq * 12),
+                "note": "the timed call takes host queries and returns host neighbours"},
+        "gpu_launches": steps, "clocks": clk,
+        "roofline": {"kernel": "k7_hnsw_search", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_query": bytes_step / nq, "mean_evaluations_per_query": float(neval.mean())},
+        "build": {"genomes_per_s_inserted": n / t_build, "seconds": t_build, "kernel": "k8_hnsw_insert_select"},
+        "recall_at_knbn_on_8_queries": hits / (8 * a.knbn),
+    }
+    # CPU arm: the oracle's search on the SAME graph, one query per host thread (parallel_search)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    cores = host_threads()
+    h = O.Hnsw(a.nbng, a.ef, S, np.uint64)
+    h.import_graph(base.cpu().numpy().view(np.uint64), idx.export_graph())
+    cq = max(1, min(nq, a.cpu_queries))
+    t0 = time.perf_counter()
+    want, wcnt, _ = h.search(h_q[:cq], a.knbn, a.ef_search, nthreads=cores)
+    dtc = time.perf_counter() - t0
+    assert want["d_id"].tolist() == out["d_id"][:cq].tolist(), "GPU and CPU answers differ on the same graph"
+    line["cpu_baseline"] = {"value": cq / dtc, "unit": "queries/s", "cores": cores, "kind": "port",
+                            "sample": f"{cq} queries, one per thread, oracle search on the graph the GPU built"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload == "request":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_request(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_own(args)

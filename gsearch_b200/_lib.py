@@ -51,6 +51,7 @@ SYMBOLS = {
     "gsb_index_create": (_int, [C.POINTER(IndexParams), _int, C.POINTER(_vp)]),
     "gsb_index_destroy": (None, [_vp]),
     "gsb_index_insert_batch": (_int, [_vp, _vp, _vp, _u64]),
+    "gsb_index_insert_batch_dev": (_int, [_vp, _vp, _vp, _u64]),
     "gsb_index_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "gsb_index_nb_point": (_u64, [_vp]),
     "gsb_index_load_graph": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64]),

@@ -554,7 +554,9 @@ extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const ui
     int rc;
     if ((rc = ensure_points(idx, n1))) return rc;
     if ((rc = ensure_upper(idx, std::max<uint64_t>(nU, 1)))) return rc;
-    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_sigs.as<uint8_t>() + n0 * row, sigs, n * row, cudaMemcpyHostToDevice, st));
+    // cudaMemcpyDefault: `sigs` may be a host pointer (gsb_index_insert_batch) or a device pointer
+    // (gsb_index_insert_batch_dev: signatures straight from the sketcher / the all-gather buffer)
+    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_sigs.as<uint8_t>() + n0 * row, sigs, n * row, cudaMemcpyDefault, st));
     GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_ids.as<uint64_t>() + n0, ids, n * 8, cudaMemcpyHostToDevice, st));
     GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_levels.as<uint8_t>() + n0, lv.data(), n, cudaMemcpyHostToDevice, st));
     GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_ranks.as<uint32_t>() + n0, rk.data(), n * 4, cudaMemcpyHostToDevice, st));
@@ -595,6 +597,10 @@ extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const ui
     }
     GSB_CUDA_TRY(cudaStreamSynchronize(st));
     return GSB_OK;
+}
+
+extern "C" int gsb_index_insert_batch_dev(gsb_index *idx, const void *d_sigs, const uint64_t *ids, uint64_t n) {
+    return gsb_index_insert_batch(idx, d_sigs, ids, n);
 }
 
 // ------------------------------------------------------------------------------ export / dump

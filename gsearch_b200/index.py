@@ -46,6 +46,12 @@ class Hnsw:
         _lib.check(_lib.lib().gsb_index_insert_batch(self._h, C.c_void_p(sigs.ctypes.data),
                                                      C.c_void_p(ids.ctypes.data), len(ids)))
 
+    def insert_device(self, d_sigs_ptr, ids):
+        """parallel_insert with the signatures already in device memory (raw pointer, n x S)"""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        _lib.check(_lib.lib().gsb_index_insert_batch_dev(self._h, C.c_void_p(d_sigs_ptr),
+                                                         C.c_void_p(ids.ctypes.data), len(ids)))
+
     def set_wave_max(self, wave_max):
         _lib.check(_lib.lib().gsb_index_set_wave_max(self._h, int(wave_max)))
 

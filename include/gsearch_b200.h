@@ -210,6 +210,10 @@ GSB_API void gsb_index_destroy(gsb_index *idx);
 /* parallel_insert(&[(&Vec<Sig>, usize)]) : n signatures (row-major n x S) with ids */
 GSB_API int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids,
                                    uint64_t n);
+/* same with the signatures already in device memory (the sketcher's output or the all-gather
+ * buffer of a multi-GPU tohnsw); ids stay a host array                                     */
+GSB_API int gsb_index_insert_batch_dev(gsb_index *idx, const void *d_sigs, const uint64_t *ids,
+                                       uint64_t n);
 /* parallel_search(&[Vec<Sig>], knbn, ef) -> Vec<Vec<Neighbour>> :
  *   out        nq * knbn entries, row i sorted by ascending distance
  *   counts_out nq values (<= knbn) : valid entries in each row

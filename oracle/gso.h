@@ -135,6 +135,10 @@ uint32_t gso_hnsw_search(gso_hnsw *h, const void *q, uint32_t knbn, uint32_t ef,
 void gso_hnsw_search_batch(gso_hnsw *h, const void *queries, uint32_t nq, uint32_t knbn,
                            uint32_t ef, gso_neighbour *out, uint32_t *counts,
                            uint64_t *nb_eval_out, int nthreads);
+/* graph image import into an empty handle (inverse of gso_hnsw_export) */
+int gso_hnsw_import(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
+                    const uint8_t *levels, const uint32_t *ranks, const uint64_t *nbr_offsets,
+                    const uint32_t *nbr_index, const float *nbr_dist, uint64_t entry_point);
 /* graph image export: sizes first, then fill */
 uint64_t gso_hnsw_total_lists(const gso_hnsw *h); /* sum over points of (level+1) */
 uint64_t gso_hnsw_total_nbrs(const gso_hnsw *h);

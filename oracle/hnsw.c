@@ -679,6 +679,40 @@ void gso_hnsw_search_batch(gso_hnsw *h, const void *queries, uint32_t nq, uint32
     }
 }
 
+/* graph image import (inverse of gso_hnsw_export): lets the CPU search run on a graph built
+ * elsewhere (bench.py times the CPU search on the graph the GPU built) */
+int gso_hnsw_import(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
+                    const uint8_t *levels, const uint32_t *ranks, const uint64_t *nbr_offsets,
+                    const uint32_t *nbr_index, const float *nbr_dist, uint64_t entry_point) {
+    if (h->n != 0) return 1;
+    if (grow(h, n ? n : 1)) return 4;
+    memcpy(h->data, sigs, n * h->row);
+    uint64_t li = 0;
+    for (uint64_t p = 0; p < n; p++) {
+        h->ids[p] = ids[p];
+        h->level[p] = levels[p];
+        h->rank[p] = ranks[p];
+        h->layer_count[levels[p]]++;
+        h->nbrs[p] = (nlist *)calloc((size_t)levels[p] + 1, sizeof(nlist));
+        for (uint32_t l = 0; l <= levels[p]; l++, li++) {
+            const uint32_t cap = (l > 0 ? h->M : 2 * h->M) + 1;
+            const uint64_t b = nbr_offsets[li], e = nbr_offsets[li + 1];
+            if (e - b >= cap) return 1;
+            nlist *nl = &h->nbrs[p][l];
+            nl->idx = (uint32_t *)malloc(cap * sizeof(uint32_t));
+            nl->dist = (float *)malloc(cap * sizeof(float));
+            nl->n = (uint32_t)(e - b);
+            for (uint64_t i = b; i < e; i++) {
+                nl->idx[i - b] = nbr_index[i];
+                nl->dist[i - b] = nbr_dist ? nbr_dist[i] : 0.f;
+            }
+        }
+    }
+    h->n = n;
+    h->entry = n ? (int64_t)entry_point : -1;
+    return 0;
+}
+
 uint64_t gso_hnsw_total_lists(const gso_hnsw *h) {
     uint64_t t = 0;
     for (uint64_t p = 0; p < h->n; p++) t += (uint64_t)h->level[p] + 1;

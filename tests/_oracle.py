@@ -78,6 +78,8 @@ def L():
         lib.gso_hnsw_total_nbrs.restype = C.c_uint64
         lib.gso_hnsw_total_nbrs.argtypes = [C.c_void_p]
         lib.gso_hnsw_export.argtypes = [C.c_void_p] * 8
+        lib.gso_hnsw_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.gso_sketch_fasta_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                                C.c_void_p, C.c_int]
         lib.gso_hamming_matrix.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
@@ -223,6 +225,17 @@ class Hnsw:
         sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
         ids = np.ascontiguousarray(ids, dtype=np.uint64)
         rc = L().gso_hnsw_insert_waves(self.h, _p(sigs), _p(ids), len(ids), wave_max)
+        assert rc == 0, rc
+
+    def import_graph(self, sigs, gr):
+        """load a graph image (dict as returned by export / gsearch_b200.Hnsw.export_graph)"""
+        sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
+        dt = dict(ids=np.uint64, levels=np.uint8, ranks=np.uint32, nbr_offsets=np.uint64, nbr_index=np.uint32,
+                  nbr_dist=np.float32)
+        a = {k: np.ascontiguousarray(gr[k], dtype=t) for k, t in dt.items()}  # kept alive over the call
+        rc = L().gso_hnsw_import(self.h, _p(sigs), _p(a["ids"]), len(a["ids"]), _p(a["levels"]), _p(a["ranks"]),
+                                 _p(a["nbr_offsets"]), _p(a["nbr_index"]), _p(a["nbr_dist"]),
+                                 int(gr["entry_point"]))
         assert rc == 0, rc
 
     def nb_point(self):
