@@ -102,34 +102,57 @@ __device__ __forceinline__ uint32_t diff16(const uint4 a, const uint4 b) {
     }
 }
 
-// One warp computes count(q != c) for one candidate row; q in shared memory.
-// row_bytes is a multiple of 16 in the fast path; the scalar tail handles the rest.
+// One warp counts the differing elements of the 16-byte vectors [vbeg, vend) of a candidate
+// row against the query in shared memory: 8 independent 128-bit loads in flight per lane
+// (a warp alone is latency bound: bytes in flight per warp set its bandwidth).
 template <int ELEM, bool IS_F32>
-__device__ __forceinline__ uint32_t warp_row_count(const uint8_t *smem_q, const uint8_t *__restrict__ c,
-                                                   uint32_t S) {
+__device__ __forceinline__ uint32_t warp_vec_count(const uint4 *qv, const uint4 *__restrict__ cv, uint32_t vbeg,
+                                                   uint32_t vend) {
     const uint32_t lane = lane_id();
-    const uint32_t nvec = (S * ELEM) / 16;
-    const uint4 *cv = reinterpret_cast<const uint4 *>(c);
-    const uint4 *qv = reinterpret_cast<const uint4 *>(smem_q);
     uint32_t cnt = 0;
-    uint32_t i = lane;
-    // 4 independent 128-bit loads in flight per lane
-    for (; i + 96 < nvec; i += 128) {
+    uint32_t i = vbeg + lane;
+    for (; i + 224 < vend; i += 256) {
+        uint4 c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = ldg_stream(cv + i + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; u++) cnt += diff16<ELEM, IS_F32>(qv[i + 32 * u], c[u]);
+    }
+    for (; i + 96 < vend; i += 128) {
         const uint4 c0 = ldg_stream(cv + i), c1 = ldg_stream(cv + i + 32), c2 = ldg_stream(cv + i + 64),
                     c3 = ldg_stream(cv + i + 96);
         cnt += diff16<ELEM, IS_F32>(qv[i], c0) + diff16<ELEM, IS_F32>(qv[i + 32], c1) +
                diff16<ELEM, IS_F32>(qv[i + 64], c2) + diff16<ELEM, IS_F32>(qv[i + 96], c3);
     }
-    for (; i < nvec; i += 32) cnt += diff16<ELEM, IS_F32>(qv[i], ldg_stream(cv + i));
-    // scalar tail (S*ELEM not a multiple of 16)
-    const uint32_t done = nvec * (16 / ELEM);
-    for (uint32_t e = done + lane; e < S; e += 32) {
+    for (; i < vend; i += 32) cnt += diff16<ELEM, IS_F32>(qv[i], ldg_stream(cv + i));
+    return cnt;
+}
+
+// scalar tail of a row whose byte length is not a multiple of 16 (per-lane partial count)
+template <int ELEM, bool IS_F32>
+__device__ __forceinline__ uint32_t warp_tail_count(const uint8_t *smem_q, const uint8_t *__restrict__ c,
+                                                    uint32_t S) {
+    const uint32_t done = ((S * ELEM) / 16) * (16 / ELEM);
+    uint32_t cnt = 0;
+    for (uint32_t e = done + lane_id(); e < S; e += 32) {
         if (ELEM == 8) cnt += ((const uint64_t *)smem_q)[e] != ((const uint64_t *)c)[e];
         else if (ELEM == 4) {
             if (IS_F32) cnt += ((const float *)smem_q)[e] != ((const float *)c)[e];
             else cnt += ((const uint32_t *)smem_q)[e] != ((const uint32_t *)c)[e];
         } else cnt += ((const uint16_t *)smem_q)[e] != ((const uint16_t *)c)[e];
     }
+    return cnt;
+}
+
+// One warp computes count(q != c) for one candidate row; q in shared memory.
+// row_bytes is a multiple of 16 in the fast path; the scalar tail handles the rest.
+template <int ELEM, bool IS_F32>
+__device__ __forceinline__ uint32_t warp_row_count(const uint8_t *smem_q, const uint8_t *__restrict__ c,
+                                                   uint32_t S) {
+    const uint32_t nvec = (S * ELEM) / 16;
+    uint32_t cnt = warp_vec_count<ELEM, IS_F32>(reinterpret_cast<const uint4 *>(smem_q),
+                                                reinterpret_cast<const uint4 *>(c), 0, nvec);
+    cnt += warp_tail_count<ELEM, IS_F32>(smem_q, c, S);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     return cnt;

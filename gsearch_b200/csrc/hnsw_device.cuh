@@ -151,22 +151,67 @@ struct SearchOut {
 struct HnswShared {
     uint32_t E[kMaxList];
     float D[kMaxList];
+    uint32_t acc[kMaxList];  // eval_list scratch
     uint32_t wcnt[kSearchThreads / 32];
     uint32_t done, node, flag, work;
     float fval;
     DHeap cand, ret;  // owned by thread 0
 };
 
+// distances of the staged row to the nE rows E[i] -> D[i].  One warp per row when there are
+// enough rows; a short list is split so that every warp streams a segment of a row (the serial
+// chain of a graph search is made of short expansions, and a warp alone is latency bound).
+// All threads of the CTA must call it (it synchronises when it splits rows).
 template <int ELEM, bool F32>
 __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView &g, const uint32_t *E,
-                                          uint32_t nE, float *D) {
+                                          uint32_t nE, float *D, uint32_t *acc /* [kMaxList] shared scratch */) {
     const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const size_t row = (size_t)g.S * ELEM;
     const float fS = (float)g.S;
-    for (uint32_t i = warp; i < nE; i += nwarps) {
-        const uint32_t cnt = warp_row_count<ELEM, F32>(smem_q, g.sigs + (size_t)E[i] * row, g.S);
-        if (lane_id() == 0) D[i] = __fdiv_rn((float)cnt, fS);
+    const bool aligned = (row & 15) == 0;  // rows start 16-byte aligned iff the row size is a multiple of 16
+    if (nE == 0) return;
+    if (nE * 2 > nwarps || !aligned) {
+        for (uint32_t i = warp; i < nE; i += nwarps) {
+            const uint8_t *cr = g.sigs + (size_t)E[i] * row;
+            uint32_t cnt;
+            if (aligned) {
+                cnt = warp_row_count<ELEM, F32>(smem_q, cr, g.S);
+            } else {  // element-wise (row size not a multiple of 16)
+                cnt = 0;
+                for (uint32_t e = lane_id(); e < g.S; e += 32) {
+                    if (ELEM == 8) cnt += ((const uint64_t *)smem_q)[e] != ((const uint64_t *)cr)[e];
+                    else if (ELEM == 4) {
+                        if (F32) cnt += ((const float *)smem_q)[e] != ((const float *)cr)[e];
+                        else cnt += ((const uint32_t *)smem_q)[e] != ((const uint32_t *)cr)[e];
+                    } else cnt += ((const uint16_t *)smem_q)[e] != ((const uint16_t *)cr)[e];
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            }
+            if (lane_id() == 0) D[i] = __fdiv_rn((float)cnt, fS);
+        }
+        return;
     }
+    // split: `parts` warps per row
+    uint32_t parts = 1;
+    while (parts * 2 * nE <= nwarps) parts *= 2;
+    if (threadIdx.x < nE) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t r = warp / parts, part = warp % parts;
+    if (r < nE) {
+        const uint8_t *cr = g.sigs + (size_t)E[r] * row;
+        const uint32_t nvec = (uint32_t)(row / 16);
+        const uint32_t per = ((nvec + parts - 1) / parts + 31) & ~31u;
+        const uint32_t vb = part * per, ve = vb + per < nvec ? vb + per : nvec;
+        uint32_t cnt = vb < ve ? warp_vec_count<ELEM, F32>(reinterpret_cast<const uint4 *>(smem_q),
+                                                           reinterpret_cast<const uint4 *>(cr), vb, ve)
+                               : 0u;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (lane_id() == 0 && cnt) atomicAdd(&acc[r], cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x < nE) D[threadIdx.x] = __fdiv_rn((float)acc[threadIdx.x], fS);
 }
 
 // stage one signature row in shared memory (TMA bulk copy when alignment allows); all threads
@@ -234,7 +279,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
             stamps[nb] = stamp;
         }
         __syncthreads();
-        eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D);
+        eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
         __syncthreads();
         if (threadIdx.x == 0) {
             neval += tot;
@@ -294,7 +339,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
         uint32_t pivot = g.entry;
         if (threadIdx.x == 0) sh.E[0] = pivot;
         __syncthreads();
-        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D);
+        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D, sh.acc);
         __syncthreads();
         float dist_to_entry = sh.D[0];
         neval += 1;
@@ -306,7 +351,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldcg(&lst[i]);
             __syncthreads();
-            eval_list<ELEM, F32>(smem, g, sh.E, len, sh.D);
+            eval_list<ELEM, F32>(smem, g, sh.E, len, sh.D, sh.acc);
             __syncthreads();
             neval += len;
             // every thread scans the same shared arrays: uniform result, no broadcast needed
@@ -403,7 +448,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
         const uint32_t lmax = g.levels[wv.entry];
         if (threadIdx.x == 0) sh.E[0] = ep;
         __syncthreads();
-        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D);
+        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D, sh.acc);
         __syncthreads();
         float d_ep = sh.D[0];
         // ---- greedy descent through the layers above the point's level: search_layer(ef = 1)
@@ -443,7 +488,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
                 }
                 if (on) sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = m;
                 __syncthreads();
-                eval_list<ELEM, F32>(smem, g, sh.E, tot, sh.D);
+                eval_list<ELEM, F32>(smem, g, sh.E, tot, sh.D, sh.acc);
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     for (uint32_t i = 0; i < tot; i++) {
@@ -502,7 +547,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
                     __syncthreads();
                     for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) sh.E[i] = newc[c0 + i];
                     __syncthreads();
-                    eval_list<ELEM, F32>(smem, g, sh.E, nc, sh.D);
+                    eval_list<ELEM, F32>(smem, g, sh.E, nc, sh.D, sh.acc);
                     __syncthreads();
                     if (threadIdx.x == 0)
                         for (uint32_t i = 0; i < nc; i++) sh.cand.push(-sh.D[i], sh.E[i]);
@@ -531,16 +576,18 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
                     if (nout > 0) {
                         stage_row(smem, g.sigs + (size_t)sh.node * row, row, &bar, phase);
                         const float ed = sh.fval;
-                        for (uint32_t c0 = 0; c0 < nout; c0 += nwarps) {
-                            const uint32_t i = c0 + warp;
-                            if (i < nout) {
-                                const uint32_t cnt =
-                                    warp_row_count<ELEM, F32>(smem, g.sigs + (size_t)outP[i] * row, g.S);
-                                if (lane_id() == 0 && __fdiv_rn((float)cnt, fS) <= ed) sh.flag = 1;
-                            }
+                        // nearest selected points first (they reject most often), 64 rows at a time
+                        for (uint32_t c0 = 0; c0 < nout; c0 += 64) {
+                            const uint32_t nc = nout - c0 < 64u ? nout - c0 : 64u;
+                            eval_list<ELEM, F32>(smem, g, outP + c0, nc, sh.D, sh.acc);
                             __syncthreads();
-                            if (sh.flag) break;
+                            const int hit = threadIdx.x < nc && sh.D[threadIdx.x] <= ed;
+                            if (__syncthreads_or(hit)) {
+                                if (threadIdx.x == 0) sh.flag = 1;
+                                break;
+                            }
                         }
+                        __syncthreads();
                     }
                     if (threadIdx.x == 0 && !sh.flag) {
                         outP[s_nout] = sh.node;
