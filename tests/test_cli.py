@@ -1,0 +1,99 @@
+"""The gsearch command line: flags, file names and text formats of the reference
+(src/bin/gsearch.rs:417-587, src/utils/{files,idsketch,parameters}.rs, src/answer.rs).  CPU tests
+cover the host-side formats; the GPU test runs tohnsw -> request -> add end to end."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gsearch_b200 as g
+from gsearch_b200 import cli
+
+
+def test_suffix_rules_and_walk(tmp_path):
+    for name in ["a.fna", "b.fa.gz", "c.fasta.xz", "d.faa", "e.txt", "sub/f.fna.bz2", "sub/g.faa.gz"]:
+        p = tmp_path / name
+        p.parent.mkdir(exist_ok=True)
+        p.write_bytes(b"")
+    dna = [os.path.relpath(p, tmp_path) for p in cli.walk_fasta(str(tmp_path), aa=False)]
+    aa = [os.path.relpath(p, tmp_path) for p in cli.walk_fasta(str(tmp_path), aa=True)]
+    assert dna == ["a.fna", "b.fa.gz", "c.fasta.xz", "sub/f.fna.bz2"]
+    assert aa == ["d.faa", "sub/g.faa.gz"]
+
+
+def test_side_files_round_trip(tmp_path):
+    p = {"capacity": 1_500_000, "ef": 1600, "nbng": 128, "scale": 0.25, "kmer": 21, "sketch": 18000,
+         "algo": "prob", "aa": False, "block": False}
+    cli.dump_parameters(tmp_path, p)
+    doc = json.load(open(tmp_path / "parameters.json"))
+    assert doc == {"hnsw": {"capacity": 1500000, "ef": 1600, "max_nb_conn": 128, "scale_modification": 0.25},
+                   "sketch": {"kmer_size": 21, "sketch_size": 18000, "algo": "PROB3A", "data_t": "DNA"},
+                   "block_flag": False}
+    assert cli.reload_parameters(tmp_path) == p
+    items = [("/db/GCA_1.fna.gz", "", 5000123), ("/db/x y.fa", "", 7)]
+    cli.dump_seqdict(tmp_path, items)
+    raw = open(tmp_path / "seqdict.json").read()
+    assert raw.startswith('{"id":{"path":"/db/GCA_1.fna.gz","fasta_id":""},"len":5000123}{"id":')   # no separator
+    assert cli.reload_seqdict(tmp_path) == items
+    cli.dump_state(tmp_path, 2, 2, 1.5)
+    assert json.load(open(tmp_path / "processing_state.json")) == {"nb_seq": 2, "nb_file": 2, "elapsed_t": 1.5}
+
+
+def test_answer_rows_follow_answer_rs():
+    seqdict = [("/db/a.fna", "", 100), ("/db/b.fna", "", 200)]
+    txt = cli.format_answers(3, ("/q/x.fna", "", 42), [(1, 0.0), (0, 0.25), (1, 0.995)], seqdict)
+    rows = txt.split("\n")
+    assert rows[0] == ""                                   # every row starts with a newline
+    assert rows[1] == "3\t/q/x.fna\tfasta_id:\t\tlength:\t42"
+    assert rows[2] == "query_id:\t/q/x.fna\tdistance:\t0.00000E0\tanswer_fasta_path\t/db/b.fna\t \t answer_seq_len:\t 200"
+    assert rows[3] == "query_id:\t/q/x.fna\tdistance:\t2.50000E-1\tanswer_fasta_path\t/db/a.fna\t \t answer_seq_len:\t 100"
+    assert len(rows) == 4                                  # 0.995 >= 0.99 is not printed
+    assert cli.format_answers(0, ("/q/y.fna", "", 1), [(0, 0.999)], seqdict) == ""
+
+
+def test_parser_mirrors_reference_flags():
+    a = cli.build_parser().parse_args("--pio 2000 --nbthreads 24 tohnsw -d db -k 21 -s 18000 -n 128 --ef 1600 "
+                                      "--algo prob --scale_modify_f 0.25".split())
+    assert (a.pio, a.dir, a.kmer, a.sketch, a.nbng, a.ef, a.algo, a.scale_modify_f, a.aa, a.block) == \
+        (2000, "db", 21, 18000, 128, 1600, "prob", 0.25, False, False)
+    a = cli.build_parser().parse_args("tohnsw -d db -k 7 -s 12000 -n 128 --algo optdens --aa --block".split())
+    assert a.ef == 400 and a.aa and a.block                 # --ef defaults to 400 (gsearch.rs:218)
+    a = cli.build_parser().parse_args("request -b dbdir -r qdir -n 50".split())
+    assert (a.hnsw, a.query, a.nbanswers) == ("dbdir", "qdir", 50)
+    a = cli.build_parser().parse_args("add -b dbdir -n newdir".split())
+    assert (a.hnsw, a.new) == ("dbdir", "newdir")
+
+
+@pytest.mark.gpu
+def test_tohnsw_request_add_end_to_end(tmp_path, monkeypatch):
+    db, new, qd, work = tmp_path / "db", tmp_path / "new", tmp_path / "q", tmp_path / "work"
+    for d in (db, new, qd, work):
+        d.mkdir()
+    for i in range(24):
+        data = g.synth.dna_genome(i, 60_000)
+        if i % 3 == 0:
+            (db / f"g{i:03d}.fna.gz").write_bytes(gzip.compress(data))
+        else:
+            (db / f"g{i:03d}.fna").write_bytes(data)
+    for i in range(24, 28):
+        (new / f"g{i:03d}.fa").write_bytes(g.synth.dna_genome(i, 60_000))
+    (qd / "q0.fna").write_bytes(g.synth.dna_genome(5, 60_000))      # identical to a database genome
+    (qd / "q1.fna").write_bytes(g.synth.dna_genome(25, 60_000))     # only in the database after `add`
+    monkeypatch.chdir(work)
+    cli.main("tohnsw -d {} -k 16 -s 512 -n 16 --ef 64 --algo prob".format(db).split())
+    for f in ("hnswdump.hnsw.graph", "hnswdump.hnsw.data", "seqdict.json", "parameters.json",
+              "processing_state.json"):
+        assert (work / f).exists(), f
+    assert len(cli.reload_seqdict(work)) == 24
+    cli.main("request -b {} -r {} -n 5".format(work, qd).split())
+    txt = open(work / "gsearch.neighbors.txt").read()
+    assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(db / "g005.fna") in txt
+    assert str(new / "g025.fa") not in txt
+    cli.main("add -b {} -n {}".format(work, new).split())
+    assert len(cli.reload_seqdict(work)) == 28
+    assert json.load(open(work / "processing_state.json"))["nb_seq"] == 28
+    cli.main("request -b {} -r {} -n 5".format(work, qd).split())
+    txt = open(work / "gsearch.neighbors.txt").read()
+    assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(new / "g025.fa") in txt
