@@ -506,7 +506,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
     GraphView g = graph_view(idx);
     g.n = first + W;
-    k8_hnsw_insert_select<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(g, wv, ret_in_smem,
+    k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem,
                                                                          idx->d_ws.as<uint8_t>(), idx->wl);
     k9_write_own_lists<<<W, 256, 0, st>>>(g, wv);
     k9_reverse_updates<<<W, 256, 0, st>>>(g, wv);

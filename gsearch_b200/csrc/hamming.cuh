@@ -111,12 +111,30 @@ __device__ __forceinline__ uint32_t warp_vec_count(const uint4 *qv, const uint4 
     const uint32_t lane = lane_id();
     uint32_t cnt = 0;
     uint32_t i = vbeg + lane;
-    for (; i + 224 < vend; i += 256) {
-        uint4 c[8];
+    // software pipeline: two groups of four loads; while one group is compared the other is in
+    // flight, so the warp always has 4-8 requests outstanding instead of bursts of 8 then none
+    if (i + 224 < vend) {
+        uint4 a[4], b[4];
 #pragma unroll
-        for (int u = 0; u < 8; u++) c[u] = ldg_stream(cv + i + 32 * u);
+        for (int u = 0; u < 4; u++) a[u] = ldg_stream(cv + i + 32 * u);
+        for (; i + 224 < vend; i += 256) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) cnt += diff16<ELEM, IS_F32>(qv[i + 32 * u], c[u]);
+            for (int u = 0; u < 4; u++) b[u] = ldg_stream(cv + i + 128 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) cnt += diff16<ELEM, IS_F32>(qv[i + 32 * u], a[u]);
+            if (i + 256 + 96 < vend) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) a[u] = ldg_stream(cv + i + 256 + 32 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) cnt += diff16<ELEM, IS_F32>(qv[i + 128 + 32 * u], b[u]);
+        }
+        // group `a` of the next iteration may already be loaded: consume it
+        if (i + 96 < vend) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) cnt += diff16<ELEM, IS_F32>(qv[i + 32 * u], a[u]);
+            i += 128;
+        }
     }
     for (; i + 96 < vend; i += 128) {
         const uint4 c0 = ldg_stream(cv + i), c1 = ldg_stream(cv + i + 32), c2 = ldg_stream(cv + i + 64),

@@ -28,7 +28,8 @@
 
 namespace gsb {
 
-constexpr int kSearchThreads = 512;
+constexpr int kSearchThreads = 512;   // K7: 16 warps (768 measured 6 % slower: the chain of expansions, not occupancy, limits it)
+constexpr int kInsertThreads = 512;   // K8: 16 warps (the selection code needs more registers)
 constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255) and >= wave size
 constexpr int kMaxLayers = 17;   // levels 0..16
 
@@ -152,7 +153,7 @@ struct HnswShared {
     uint32_t E[kMaxList];
     float D[kMaxList];
     uint32_t acc[kMaxList];  // eval_list scratch
-    uint32_t wcnt[kSearchThreads / 32];
+    uint32_t wcnt[32];
     uint32_t done, node, flag, work;
     float fval;
     DHeap cand, ret;  // owned by thread 0
@@ -270,7 +271,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
         if (lane_id() == 0) sh.wcnt[threadIdx.x >> 5] = __popc(bal);
         __syncthreads();
         uint32_t pre = 0, tot = 0;
-        for (uint32_t w = 0; w < kSearchThreads / 32; w++) {
+        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
             if (w < (threadIdx.x >> 5)) pre += sh.wcnt[w];
             tot += sh.wcnt[w];
         }
@@ -407,7 +408,7 @@ __device__ __forceinline__ size_t sel_off(uint32_t M, uint32_t t, uint32_t l) {
 // Phase A.  One CTA per new point: greedy descent, search_layer(ef_c) per layer, earlier points
 // of the wave merged in, select_neighbours (Malkov heuristic, extension on layer 0), sort.
 template <int ELEM, bool F32>
-__global__ void __launch_bounds__(kSearchThreads, 1)
+__global__ void __launch_bounds__(kInsertThreads, 1)
 k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__restrict__ ws, WsLayout wl) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -482,7 +483,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
                 if (lane_id() == 0) sh.wcnt[warp] = __popc(bal);
                 __syncthreads();
                 uint32_t pre = 0, tot = 0;
-                for (uint32_t w = 0; w < kSearchThreads / 32; w++) {
+                for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
                     if (w < warp) pre += sh.wcnt[w];
                     tot += sh.wcnt[w];
                 }
