@@ -55,6 +55,22 @@ struct ProbSlot {
     size_t cnt_dirty = 0;
 };
 
+// Small host->device descriptor copies go through a kernel that reads the PINNED host buffer
+// directly (unified addressing) instead of cudaMemcpyAsync: a copy-engine transfer would queue
+// behind the bulk H2D copy of the next sub-batch and serialise the pipeline of
+// gsb_sketch_fasta_batch.
+__global__ void k_pull_words(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src_pinned, size_t nwords) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src_pinned[i];
+}
+static cudaError_t pull_small(void *dst, const void *src_pinned, size_t bytes, cudaStream_t st) {
+    const size_t nw = (bytes + 3) / 4;  // buffers are allocated with slack: rounding up is safe
+    if (!nw) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<size_t>((nw + 255) / 256, 64);
+    k_pull_words<<<grid, 256, 0, st>>>((uint32_t *)dst, (const uint32_t *)src_pinned, nw);
+    return cudaGetLastError();
+}
+
 __global__ void k_fill_u32(uint32_t *p, size_t n, uint32_t v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = v;
@@ -136,8 +152,10 @@ struct gsb_sketcher {
     uint64_t cat_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // host-pointer entry point: H2D of the next sub-batch overlaps the kernels of the current one
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
-    uint32_t file_base = 0;  // index of the sub-batch's first file in the caller's batch (messages)
+    std::vector<cudaEvent_t> ev_h2d;       // one per H2D chunk of the current host call
+    std::vector<uint32_t> h2d_end;         // chunk c holds the files [h2d_end[c-1], h2d_end[c])
+    bool h2d_active = false;               // batch_dev must wait for the chunk events
+    uint32_t file_base = 0;  // offset added to file indices in messages
     cudaStream_t gstream[2] = {nullptr, nullptr};  // group streams of the prob path
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_k1;  // one per group: its files are packed
@@ -290,8 +308,7 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
         if (e2) cudaEventDestroy(e2);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
-    for (cudaEvent_t e : h->ev_h2d)
-        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     delete h;
 }
 
@@ -349,6 +366,14 @@ struct K1Plan {
     uint32_t bd_cap = 0;
     bool pending = false;  // K1 has not run yet for this batch
 };
+
+// host entry point only: the bytes of files <= last arrive on the copy stream, chunk by chunk
+cudaError_t wait_files_ready(gsb_sketcher *h, cudaStream_t st, uint32_t last) {
+    if (!h->h2d_active) return cudaSuccess;
+    for (size_t c = 0; c < h->h2d_end.size(); c++)
+        if (last < h->h2d_end[c]) return cudaStreamWaitEvent(st, h->ev_h2d[c], 0);  // copies are in order
+    return cudaSuccess;
+}
 
 void launch_k1_range(gsb_sketcher *h, const K1Plan &kp, uint32_t f0, uint32_t nf, cudaStream_t st) {
     const uint32_t *htp = h->h_tile_prefix.as<uint32_t>();
@@ -514,9 +539,8 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
         }
         group_chunks[g] = acc;
     }
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, hj, (size_t)n * sizeof(ProbJob), cudaMemcpyHostToDevice, st));
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (kSlots + 1) * 4,
-                                 cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(pull_small(h->d_jobs.p, hj, (size_t)n * sizeof(ProbJob), st));
+    GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (kSlots + 1) * 4, st));
     // groups alternate between two streams (and two slot sets); everything before (K1, job
     // descriptors) happened on `st`, everything after waits for both
     GSB_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
@@ -530,6 +554,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
             if (kp.pending) {
                 // first pass: todo is the whole batch in order, so group g = files [joff, joff + nj).
                 // K1 runs ahead on `st`, one group at a time, under the scan kernels of earlier groups.
+                GSB_CUDA_TRY(wait_files_ready(h, st, joff + nj - 1));
                 launch_k1_range(h, kp, joff, nj, st);
                 if (h->ev_k1.size() <= g) {
                     cudaEvent_t e = nullptr;
@@ -585,7 +610,7 @@ int run_super_sequential(gsb_sketcher *h, const std::vector<uint32_t> &list, voi
     if ((rc = h->d_jobs.ensure((size_t)nl * 4))) return rc;
     if ((rc = h->d_bins.ensure((size_t)nl * 3 * h->sc.m * 4))) return rc;
     memcpy(h->h_jobs.p, list.data(), (size_t)nl * 4);
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, h->h_jobs.p, (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(pull_small(h->d_jobs.p, h->h_jobs.p, (size_t)nl * 4, st));
     if (dna) {
         if (h->kt32) launch_super_seq<SrcDNA<uint32_t>, uint32_t>(h, nl, true, want_bounds, d_sig, st);
         else launch_super_seq<SrcDNA<uint64_t>, uint64_t>(h, nl, true, want_bounds, d_sig, st);
@@ -626,8 +651,8 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
         set_error("batch too large: %llu k-mer chunks", (unsigned long long)acc);
         return GSB_ERR_CAPACITY;
     }
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), cudaMemcpyHostToDevice, st));
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_chunk_prefix.p, hcp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(pull_small(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), st));
+    GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)(n + 1) * 4, st));
     k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
     h->launches += 1;
     const uint32_t nchunks = (uint32_t)acc;
@@ -709,8 +734,8 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     if ((rc = h->d_retry.ensure((size_t)n * 4))) return rc;
     if ((rc = h->h_retry.ensure((size_t)n * 4))) return rc;
 
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_files.p, hf, (size_t)n * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
-    GSB_CUDA_TRY(cudaMemcpyAsync(h->d_tile_prefix.p, htp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    GSB_CUDA_TRY(pull_small(h->d_files.p, hf, (size_t)n * sizeof(FileDesc), st));
+    GSB_CUDA_TRY(pull_small(h->d_tile_prefix.p, htp, (size_t)(n + 1) * 4, st));
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_retry.p, 0, (size_t)n * 4, st));
     if (dna) GSB_CUDA_TRY(cudaMemsetAsync(h->d_packed.p, 0, packed_bytes, st));
@@ -725,7 +750,16 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     if (!ntiles) {
         kp.pending = false;
     } else if (!prob) {
-        launch_k1_range(h, kp, 0, n, st);
+        if (h->h2d_active) {  // pack chunk by chunk as the bytes arrive
+            uint32_t f0 = 0;
+            for (size_t c = 0; c < h->h2d_end.size(); c++) {
+                GSB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[c], 0));
+                launch_k1_range(h, kp, f0, h->h2d_end[c] - f0, st);
+                f0 = h->h2d_end[c];
+            }
+        } else {
+            launch_k1_range(h, kp, 0, n, st);
+        }
         kp.pending = false;
         GSB_CUDA_TRY(cudaGetLastError());
     }
@@ -810,58 +844,52 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
     if (!h->copy_stream) {
         GSB_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         GSB_CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-        for (auto &e : h->ev_h2d) GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    // Sub-batches of whole files: the H2D copy of sub-batch i+1 (copy stream) overlaps the
-    // kernels of sub-batch i (compute stream); finished signatures leave on a third stream.
-    // With pageable host memory the copies block the host instead: same result, no overlap.
-    std::vector<uint32_t> cut{0};
+    // The bytes go to the device in chunks of whole files on a copy stream, one event per chunk;
+    // the kernels of a genome group only wait for the chunk that holds the group's last file, so
+    // the H2D transfer of later files runs under the kernels of earlier ones.  With pageable host
+    // memory the copies block the host instead: same result, no overlap.
+    h->h2d_end.clear();
     {
-        const uint64_t kSubBytes = 96ull << 20;
-        const uint32_t kSubFiles = 16;
+        const uint64_t kChunkBytes = 48ull << 20;
+        const uint32_t kChunkFiles = 8;
         uint32_t b = 0;
         for (uint32_t i = 1; i <= n; i++)
-            if (i == n || i - b >= kSubFiles || offsets[i + 1] - offsets[b] > kSubBytes) {
-                cut.push_back(i);
+            if (i == n || i - b >= kChunkFiles || offsets[i + 1] - offsets[b] > kChunkBytes) {
+                h->h2d_end.push_back(i);
                 b = i;
             }
     }
-    const size_t nsub = cut.size() - 1;
-    auto h2d = [&](size_t s) -> cudaError_t {
-        const uint64_t b = offsets[cut[s]], e = offsets[cut[s + 1]];
-        cudaError_t ce = cudaSuccess;
-        if (e > b)
-            ce = cudaMemcpyAsync(h->d_bytes.as<uint8_t>() + (b - lo), bytes + b, e - b, cudaMemcpyHostToDevice,
-                                 h->copy_stream);
-        if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_h2d[s & 1], h->copy_stream);
-        return ce;
-    };
-    GSB_CUDA_TRY(h2d(0));
-    std::vector<uint64_t> rel;
-    for (size_t s = 0; s < nsub; s++) {
-        const uint32_t f0 = cut[s], nf = cut[s + 1] - f0;
-        GSB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[s & 1], 0));
-        // the event of sub-batch s+1 reuses the slot of s-1, which the compute stream has passed
-        if (s + 1 < nsub) GSB_CUDA_TRY(h2d(s + 1));
-        rel.resize(nf + 1);
-        for (uint32_t i = 0; i <= nf; i++) rel[i] = offsets[f0 + i] - lo;
-        uint8_t *d_sig = h->d_sig.as<uint8_t>() + (size_t)f0 * sig_row;
-        uint64_t *d_nb = h->d_nb.as<uint64_t>() + f0;
-        h->file_base = f0;
-        rc = gsb_sketch_fasta_batch_dev(h, h->d_bytes.as<uint8_t>(), rel.data(), nf, d_sig, d_nb, (void *)st);
-        h->file_base = 0;
-        if (rc) {
-            cudaStreamSynchronize(h->copy_stream);
-            cudaStreamSynchronize(h->d2h_stream);
-            return rc;
-        }
-        // batch_dev returned after synchronising `st`: the results are complete
-        GSB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)sig_out + (size_t)f0 * sig_row, d_sig, (size_t)nf * sig_row,
-                                     cudaMemcpyDeviceToHost, h->d2h_stream));
-        if (nb_bases_out)
-            GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out + f0, d_nb, (size_t)nf * 8, cudaMemcpyDeviceToHost,
-                                         h->d2h_stream));
+    while (h->ev_h2d.size() < h->h2d_end.size()) {
+        cudaEvent_t e = nullptr;
+        GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_h2d.push_back(e);
     }
+    {
+        uint32_t f0 = 0;
+        for (size_t c = 0; c < h->h2d_end.size(); c++) {
+            const uint64_t b = offsets[f0], e = offsets[h->h2d_end[c]];
+            if (e > b)
+                GSB_CUDA_TRY(cudaMemcpyAsync(h->d_bytes.as<uint8_t>() + (b - lo), bytes + b, e - b,
+                                             cudaMemcpyHostToDevice, h->copy_stream));
+            GSB_CUDA_TRY(cudaEventRecord(h->ev_h2d[c], h->copy_stream));
+            f0 = h->h2d_end[c];
+        }
+    }
+    std::vector<uint64_t> rel(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
+    h->h2d_active = true;
+    rc = gsb_sketch_fasta_batch_dev(h, h->d_bytes.as<uint8_t>(), rel.data(), n, h->d_sig.p, h->d_nb.as<uint64_t>(),
+                                    (void *)st);
+    h->h2d_active = false;
+    if (rc) {
+        cudaStreamSynchronize(h->copy_stream);
+        return rc;
+    }
+    // batch_dev returned after synchronising `st`: the results are complete
+    GSB_CUDA_TRY(cudaMemcpyAsync(sig_out, h->d_sig.p, (size_t)n * sig_row, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (nb_bases_out)
+        GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out, h->d_nb.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
     GSB_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     return GSB_OK;
 }
