@@ -43,7 +43,10 @@ def parse_args():
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--kmer", type=int, default=21)
     ap.add_argument("--sketch", type=int, default=18000)
-    ap.add_argument("--algo", default="prob", choices=["prob", "optdens"])
+    ap.add_argument("--algo", default="prob", choices=["prob", "optdens", "super"])
+    ap.add_argument("--aa", action="store_true", help="proteomes (BASELINE configs[3]: --aa --algo optdens "
+                                                      "--kmer 7 --sketch 12000): 4500 proteins x ~333 aa per file")
+    ap.add_argument("--nprot", type=int, default=4500)
     ap.add_argument("--cpu-sample", type=int, default=32, help="genomes in the CPU baseline sample")
     # secondary workload (BASELINE configs[2] shape): build an HNSW index on device, then search it
     ap.add_argument("--workload", default="sketch", choices=["sketch", "request"])
@@ -57,7 +60,13 @@ def parse_args():
     return ap.parse_args()
 
 
+ALGO_ID = {"prob": 0, "super": 1, "optdens": 2}
+
+
 def workload_name(a):
+    if a.aa:
+        return (f"configs[3]: {a.algo} sketch of synthetic proteomes ({a.nprot} proteins x ~333 aa), k={a.kmer} "
+                f"s={a.sketch} --aa; step = batch of {a.batch} distinct proteomes per GPU")
     return (f"configs[1]: ProbMinHash3a sketch of synthetic {a.genome_len / 1e6:g} Mbp genomes, k={a.kmer} "
             f"s={a.sketch} --algo {a.algo}; step = batch of {a.batch} distinct genomes per GPU "
             f"(slice of the 10k-genome set)")
@@ -77,6 +86,11 @@ def gen_batch_numpy(first_index, n, length):
     return g.Sketcher.concat(files)
 
 
+def gen_batch_aa_numpy(first_index, n, nprot):
+    import gsearch_b200 as g
+    return g.Sketcher.concat([g.synth.aa_proteome(first_index + i, nprot) for i in range(n)])
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
@@ -84,15 +98,16 @@ def run_reference(a):
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as O
-    algo = 0 if a.algo == "prob" else 2
+    algo = ALGO_ID[a.algo]
     cores = host_threads()
     sample = max(1, min(a.batch, a.cpu_sample))
-    buf, offs = gen_batch_numpy(0, sample, a.genome_len)
+    buf, offs = gen_batch_aa_numpy(0, sample, a.nprot) if a.aa else gen_batch_numpy(0, sample, a.genome_len)
+    dt_ = 1 if a.aa else 0
     for _ in range(max(1, min(a.warmup, 1))):
-        O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 0, False, 0, nthreads=cores)
+        O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, dt_, False, 0, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 0, False, 0, nthreads=cores)
+        O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, dt_, False, 0, nthreads=cores)
     dt = time.perf_counter() - t0
     value = sample * a.steps / dt
     line = {
@@ -183,19 +198,22 @@ def run_own(a):
         os.environ.setdefault("MASTER_PORT", "29511")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    algo = g.ALGO_PROB3A if a.algo == "prob" else g.ALGO_OPTDENS
-    params = g.SeqSketcherParams(a.kmer, a.sketch, algo)
+    algo = ALGO_ID[a.algo]
+    params = g.SeqSketcherParams(a.kmer, a.sketch, algo, g.DATA_AA if a.aa else g.DATA_DNA)
     sk = g.Sketcher(params, device=local)
     elem = sk.elem_size
     B, S = a.batch, a.sketch
 
     # ---- synthetic batch of this rank, generated straight into pinned host memory
-    cap1 = g.synth.max_bytes(a.genome_len, 1)
+    cap1 = g.synth.max_bytes(a.nprot * (333 + 333 // 2 + 2), a.nprot) if a.aa else g.synth.max_bytes(a.genome_len, 1)
     h_bytes = torch.empty(cap1 * B, dtype=torch.uint8, pin_memory=True)
     offs = np.zeros(B + 1, dtype=np.uint64)
     pos = 0
     for i in range(B):
-        n = g.synth.dna_genome_into(rank * B + i, a.genome_len, 1, h_bytes.data_ptr() + pos, cap1)
+        if a.aa:
+            n = g.synth.aa_proteome_into(rank * B + i, a.nprot, 333, h_bytes.data_ptr() + pos, cap1)
+        else:
+            n = g.synth.dna_genome_into(rank * B + i, a.genome_len, 1, h_bytes.data_ptr() + pos, cap1)
         assert n > 0
         pos += n
         offs[i + 1] = pos
@@ -248,7 +266,10 @@ def run_own(a):
 
     # sanity, outside the timed region: every signature is filled and encoded lengths are right
     nb = d_nb.cpu().numpy()
-    assert (nb > 0.99 * a.genome_len - 100).all() and (nb <= a.genome_len).all(), nb[:4]
+    if a.aa:
+        assert (nb > 0.5 * a.nprot * 333).all() and (nb < 2 * a.nprot * 333).all(), nb[:4]
+    else:
+        assert (nb > 0.99 * a.genome_len - 100).all() and (nb <= a.genome_len).all(), nb[:4]
     sig0 = d_sig.cpu().numpy().view(sk.dtype).reshape(B, S)
     assert (sig0 != 0).mean() > 0.999
 
@@ -326,13 +347,14 @@ def cpu_baseline(a):
     import _oracle as O
     cores = host_threads()
     sample = max(1, min(a.batch, a.cpu_sample))
-    buf, offs = gen_batch_numpy(0, sample, a.genome_len)
-    algo = 0 if a.algo == "prob" else 2
+    buf, offs = gen_batch_aa_numpy(0, sample, a.nprot) if a.aa else gen_batch_numpy(0, sample, a.genome_len)
+    algo = ALGO_ID[a.algo]
     t0 = time.perf_counter()
-    O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 0, False, 0, nthreads=cores)
+    O.sketch_buffer(buf, offs, a.kmer, a.sketch, algo, 1 if a.aa else 0, False, 0, nthreads=cores)
     dt = time.perf_counter() - t0
+    what = f"{a.nprot}-protein proteomes" if a.aa else f"{a.genome_len} bp genomes"
     return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample} x {a.genome_len} bp genomes, one genome per thread (oracle/, C restatement)"}
+            "sample": f"{sample} x {what}, one per thread (oracle/, C restatement)"}
 
 
 # --------------------------------------------------------------------------- request workload
