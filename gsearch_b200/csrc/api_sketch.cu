@@ -468,7 +468,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     size_t max_len = 0;
     for (uint32_t f : todo) max_len = std::max<size_t>(max_len, h_offsets[f + 1] - h_offsets[f]);
     if (max_len > kMaxProbSym) {
-        set_error("file of %zu bytes exceeds the %u-symbol limit of the prob path's 24-bit position "
+        set_error("file of %zu bytes exceeds the %u-symbol limit of the prob path's 30-bit position "
                   "field", max_len, kMaxProbSym);
         return GSB_ERR_CAPACITY;
     }
@@ -517,6 +517,10 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 ProbSlot &sl = h->slot[(g & 1) * kSlots + s];
                 ProbJob &j = hj[i];
                 j.file = f;
+                // position field just wide enough for this file (at least 24 bits, so that ordinary
+                // genomes keep an 8-bit fingerprint); the rest of the 32-bit entry is fingerprint
+                j.posbits = 24;
+                while (j.posbits < 30 && ((size_t)1 << j.posbits) < len + 2) j.posbits++;
                 j.nslot1 = (uint32_t)(((size_t)(prob_load() * (double)len) + 64) & ~(size_t)15);
                 j.bitmap = sl.bitmap.as<uint32_t>();
                 j.n_coll = sl.misc.as<uint32_t>() + 3;

@@ -31,7 +31,7 @@ namespace gsb {
 constexpr int kK2Threads = 256;
 constexpr int kRun = 32;                        // consecutive k-mer positions per thread
 constexpr int kChunk = kK2Threads * kRun;       // positions per CTA
-constexpr uint32_t kMaxProbSym = (1u << 24) - 2;  // 24-bit position field of a set entry
+constexpr uint32_t kMaxProbSym = (1u << 30) - 2;  // widest position field of an exact-set entry (30 bits)
 constexpr int kG = 8;                             // k-mers hashed and probed together per thread
 constexpr int kProbeRounds = 4;                   // probes before an insertion is deferred
 constexpr uint32_t kStageCap = 3072;              // per-CTA candidate stage (entries, 48 KiB)
@@ -46,6 +46,7 @@ struct ListEntry {
 // per-genome device-side job state for the prob path
 struct ProbJob {
     uint32_t file;       // index into FileDesc / FileResult
+    uint32_t posbits;    // exact-set entry = fingerprint (32 - posbits bits) | position + 1 (posbits bits)
     uint32_t nslot1;     // filter size in 2-bit units (16 per 32-bit word)
     uint32_t *bitmap;    // blocked filter: per word 24 "seen" bits + 8 "repeated" flags
     uint32_t *n_coll;    // occurrences that found their seen bits already set (statistics)
@@ -262,8 +263,8 @@ __device__ __forceinline__ void set_probe_result(const SeqView &sv, uint32_t k, 
         return;
     }
     bool same = false;
-    if ((old >> 24) == (entry >> 24)) {
-        const uint32_t pos2 = (old & 0xFFFFFFu) - 1;
+    if ((old >> job.posbits) == (entry >> job.posbits)) {
+        const uint32_t pos2 = (old & ((1u << job.posbits) - 1u)) - 1;
         same = Src::kmer_at(sv, pos2, k) == kmer;  // verified against the sequence: exact
     }
     if (same) {
@@ -591,7 +592,7 @@ k2_prob_overflow(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileDes
             kmer = (KT)oe.kmer;
             cand = oe.cand != 0;
             const uint64_t s0 = sm64_mix(nohash_seed<KT>(kmer, sc.spec_flags) + kGolden);
-            entry = ((uint32_t)s0 << 24) | oe.pos1;
+            entry = ((uint32_t)s0 << job.posbits) | oe.pos1;
             slot = __umulhi((uint32_t)(s0 >> 32), cap2);
         }
         while (act) {

@@ -129,3 +129,10 @@ def test_super_fast_path_and_aa(oracle):
     want, wnb = oracle.sketch_files(files, 21, 2048, g.ALGO_SUPER, nthreads=3)
     assert_same(got, nb, want, wnb)
     assert_same(*run_both(oracle, adversarial_aa_files(2), 7, 500, g.ALGO_SUPER, g.DATA_AA))
+
+
+def test_prob_genome_longer_than_2_pow_24(oracle):
+    # exact-set entries hold fingerprint | position: the position field widens with the file
+    # (24 bits up to 16.7 M symbols, 30 bits at most); 20 Mbp needs 25 bits
+    files = [g.synth.dna_genome(3, 20_000_000, ncontigs=2)]
+    assert_same(*run_both(oracle, files, 21, 4000))
