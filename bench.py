@@ -172,6 +172,14 @@ class ClockSampler:
         return out
 
 
+def measured_traffic(key):
+    """DRAM bytes from the committed ncu capture (profiles/r1_traffic.json), or None"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[key]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -304,6 +312,7 @@ def run_own(a):
         # span timed here (CUDA events on the launching stream, first group start -> last group
         # end) covers the whole K1 || K2 || K3 pipeline of a call, K2 being ~75 % of its stream time.
         k2_ms, k2_n = ktimes["k2_scan"]
+        traffic = measured_traffic("sketch_prob_k21_s18000") if (algo == 0 and not a.aa) else None
         genomes_timed = B * a.steps
         achieved = (alg_bytes_per_genome * genomes_timed / 1e9) / (k2_ms / 1e3) if k2_ms > 0 else None
         line = {
@@ -324,8 +333,12 @@ def run_own(a):
                 "kernel": "prob sketch pipeline: k2_prob_mark/classify/exact (dominant) overlapped with K1 pack and K3"
                           if algo == 0 else "k2_optdens",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_genome": alg_bytes_per_genome,
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": (traffic["dram_bytes_per_genome"] * B if traffic else None),
+                "traffic_source": "profiles/r1_traffic.json: ncu dram bytes of all sketch kernels per genome x "
+                                  "genomes per step" if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_genome": alg_bytes_per_genome,
+                "algorithmic_bytes_per_launch": alg_bytes_per_genome * B,
                 "avg_launch_ms": (k2_ms / k2_n) if k2_n else None, "launches_timed": k2_n,
                 "note": "L2-atomic / integer-ALU bound, not HBM bound (DESIGN.md); fraction reported as required; "
                         "kernel_ms holds the per-kernel stream times (they overlap across streams)",
