@@ -391,7 +391,11 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
         return GSB_ERR_UNSUPPORTED;
     }
     const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
-    const size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
+    size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
+    // visited bitmap in shared memory when it fits beside the row and the result heap
+    const size_t bm_bytes = ((idx->n + 31) / 32) * 4;
+    const uint32_t bm_words = smem + bm_bytes <= kSmemMax ? (uint32_t)(bm_bytes / 4) : 0u;
+    smem += (size_t)bm_words * 4;
     GSB_CUDA_TRY(cudaFuncSetAttribute(k7_hnsw_search<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemMax));
     const uint32_t nctas = std::min<uint32_t>(nq, (uint32_t)idx->nsm);
@@ -404,8 +408,8 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
     so.counts = idx->d_counts.as<uint32_t>();
     so.nb_eval = idx->d_neval.as<unsigned long long>();
     k7_hnsw_search<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(
-        graph_view(idx), idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, idx->d_ws.as<uint8_t>(), idx->wl,
-        so, idx->d_counter.as<uint32_t>());
+        graph_view(idx), idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, bm_words,
+        idx->d_ws.as<uint8_t>(), idx->wl, so, idx->d_counter.as<uint32_t>());
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;
 }
@@ -483,7 +487,10 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
         return GSB_ERR_UNSUPPORTED;
     }
     const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
-    const size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
+    size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
+    const size_t bm_bytes = (((size_t)first + W + 31) / 32) * 4;
+    const uint32_t bm_words = smem + bm_bytes <= kSmemMax ? (uint32_t)(bm_bytes / 4) : 0u;
+    smem += (size_t)bm_words * 4;
     static bool attr = false;
     if (!attr) {
         GSB_CUDA_TRY(cudaFuncSetAttribute(k8_hnsw_insert_select<ELEM, F32>,
@@ -506,7 +513,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
     GraphView g = graph_view(idx);
     g.n = first + W;
-    k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem,
+    k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem, bm_words,
                                                                          idx->d_ws.as<uint8_t>(), idx->wl);
     k9_write_own_lists<<<W, 256, 0, st>>>(g, wv);
     k9_reverse_updates<<<W, 256, 0, st>>>(g, wv);

@@ -132,14 +132,36 @@ struct GraphView {
     uint32_t M, n, entry, S;
 };
 
+// Neighbour lists are only written by the phase-B kernels, never while a search or phase-A
+// kernel runs, so they are read through L1 (and prefetched there one expansion ahead).
 __device__ __forceinline__ const uint32_t *list_of(const GraphView &g, uint32_t p, uint32_t layer, uint32_t &len) {
     if (layer == 0) {
-        len = __ldcg(&g.cnt0[p]);
+        len = __ldg(&g.cnt0[p]);
         return g.nbr0 + (size_t)p * 2 * g.M;
     }
     const uint32_t li = g.upper_off[p] + layer - 1;
-    len = __ldcg(&g.cntU[li]);
+    len = __ldg(&g.cntU[li]);
     return g.nbrU + (size_t)li * g.M;
+}
+
+// warp 0: pull the list of the candidate that will most likely be popped next into L1
+__device__ __forceinline__ void prefetch_list(const GraphView &g, uint32_t p, uint32_t layer) {
+    const uint32_t *base;
+    const uint32_t *cnt;
+    uint32_t bytes;
+    if (layer == 0) {
+        base = g.nbr0 + (size_t)p * 2 * g.M;
+        cnt = g.cnt0 + p;
+        bytes = 8 * g.M;
+    } else {
+        const uint32_t li = __ldg(&g.upper_off[p]) + layer - 1;
+        base = g.nbrU + (size_t)li * g.M;
+        cnt = g.cntU + li;
+        bytes = 4 * g.M;
+    }
+    const uint32_t off = threadIdx.x * 128u;
+    if (off < bytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(base) + off));
+    if (threadIdx.x == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(cnt));
 }
 
 struct SearchOut {
@@ -154,7 +176,7 @@ struct HnswShared {
     float D[kMaxList];
     uint32_t acc[kMaxList];  // eval_list scratch
     uint32_t wcnt[32];
-    uint32_t done, node, flag, work;
+    uint32_t done, node, flag, work, next;
     float fval;
     DHeap cand, ret;  // owned by thread 0
 };
@@ -163,6 +185,32 @@ struct HnswShared {
 // enough rows; a short list is split so that every warp streams a segment of a row (the serial
 // chain of a graph search is made of short expansions, and a warp alone is latency bound).
 // All threads of the CTA must call it (it synchronises when it splits rows).
+// visited set of one search_layer call: a bitmap in shared memory when the index fits (the
+// gather step of every expansion tests up to 2M neighbours; from global memory that is one more
+// dependent L2 round trip per expansion), visit stamps in the CTA's global workspace otherwise
+struct Visit {
+    uint32_t *bits;    // shared-memory bitmap, or nullptr
+    uint32_t nwords;
+    uint32_t *stamps;  // global: stamps[p] == stamp marks p visited
+    uint32_t stamp;
+    __device__ __forceinline__ void begin() {  // all threads of the CTA
+        if (bits) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) bits[i] = 0;
+            __syncthreads();
+        } else {
+            stamp++;
+        }
+    }
+    __device__ __forceinline__ bool seen(uint32_t x) const {
+        return bits ? ((bits[x >> 5] >> (x & 31u)) & 1u) != 0u : stamps[x] == stamp;
+    }
+    __device__ __forceinline__ void mark(uint32_t x) {
+        if (bits) atomicOr(&bits[x >> 5], 1u << (x & 31u));
+        else stamps[x] = stamp;
+    }
+};
+
 template <int ELEM, bool F32>
 __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView &g, const uint32_t *E,
                                           uint32_t nE, float *D, uint32_t *acc /* [kMaxList] shared scratch */) {
@@ -230,16 +278,17 @@ __device__ __forceinline__ void stage_row(uint8_t *smem, const uint8_t *grow, si
 }
 
 // hnsw_rs search_layer: best-first search on one layer from `ep` (distance d_ep known), result in
-// sh.ret (max-heap of at most ef), candidates in sh.cand.  `stamps[p] == stamp` marks visited.
+// sh.ret (max-heap of at most ef), candidates in sh.cand; `vis` is reset here.
 template <int ELEM, bool F32>
 __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint32_t ep, float d_ep,
-                                 uint32_t ef, uint32_t layer, HnswShared &sh, uint32_t *stamps,
-                                 uint32_t stamp, unsigned long long &neval) {
+                                 uint32_t ef, uint32_t layer, HnswShared &sh, Visit &vis,
+                                 unsigned long long &neval) {
+    vis.begin();
     __syncthreads();
     if (threadIdx.x == 0) {
         sh.cand.n = 0;
         sh.ret.n = 0;
-        stamps[ep] = stamp;
+        vis.mark(ep);
         sh.cand.push(-d_ep, ep);
         sh.ret.push(d_ep, ep);
         neval += 1;  // the reference evaluates the distance to the layer's entry point again
@@ -254,18 +303,20 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
                 const HItem c = sh.cand.pop();
                 if (-c.d > sh.ret.a[0].d) sh.done = 1;
                 sh.node = c.p;
+                sh.next = sh.cand.n ? sh.cand.a[0].p : 0xFFFFFFFFu;  // the likely next pop
             }
         }
         __syncthreads();
         if (sh.done) break;
+        if (threadIdx.x < 32 && sh.next != 0xFFFFFFFFu) prefetch_list(g, sh.next, layer);
         // gather the unvisited neighbours of the popped node in list order
         uint32_t len;
         const uint32_t *lst = list_of(g, sh.node, layer, len);
         uint32_t nb = 0xFFFFFFFFu;
         bool unv = false;
         if (threadIdx.x < len) {
-            nb = __ldcg(&lst[threadIdx.x]);
-            unv = stamps[nb] != stamp;
+            nb = __ldg(&lst[threadIdx.x]);
+            unv = !vis.seen(nb);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, unv);
         if (lane_id() == 0) sh.wcnt[threadIdx.x >> 5] = __popc(bal);
@@ -277,7 +328,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
         }
         if (unv) {
             sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = nb;
-            stamps[nb] = stamp;
+            vis.mark(nb);
         }
         __syncthreads();
         eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
@@ -311,7 +362,7 @@ struct WsLayout {
 template <int ELEM, bool F32>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, uint32_t knbn, uint32_t ef,
-               int ret_in_smem, uint8_t *__restrict__ ws, WsLayout wl, SearchOut so,
+               int ret_in_smem, uint32_t bm_words, uint8_t *__restrict__ ws, WsLayout wl, SearchOut so,
                uint32_t *__restrict__ qcounter) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -329,7 +380,12 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
     }
     __syncthreads();
     uint32_t phase = 0;
-    uint32_t stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
+    Visit vis;
+    vis.nwords = bm_words;
+    vis.bits = bm_words ? reinterpret_cast<uint32_t *>(smem + row128 + (ret_in_smem ? ((size_t)ef + 2) * sizeof(HItem) : 0))
+                        : nullptr;
+    vis.stamps = stamps;
+    vis.stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
     for (;;) {
         if (threadIdx.x == 0) s_q = atomicAdd(qcounter, 1u);
         __syncthreads();
@@ -350,7 +406,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             uint32_t len;
             const uint32_t *lst = list_of(g, pivot, (uint32_t)layer, len);
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldcg(&lst[i]);
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldg(&lst[i]);
             __syncthreads();
             eval_list<ELEM, F32>(smem, g, sh.E, len, sh.D, sh.acc);
             __syncthreads();
@@ -366,8 +422,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             pivot = newp;
         }
         // ---- search_layer(q, pivot, ef, 0)
-        stamp++;
-        search_layer_dev<ELEM, F32>(g, smem, pivot, dist_to_entry, ef, 0, sh, stamps, stamp, neval);
+        search_layer_dev<ELEM, F32>(g, smem, pivot, dist_to_entry, ef, 0, sh, vis, neval);
         if (threadIdx.x == 0) {
             sh.ret.into_sorted();
             uint32_t last = knbn < ef ? knbn : ef;
@@ -387,7 +442,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = stamp;
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = vis.stamp;
 }
 
 // =========================================================================== construction
@@ -409,7 +464,8 @@ __device__ __forceinline__ size_t sel_off(uint32_t M, uint32_t t, uint32_t l) {
 // of the wave merged in, select_neighbours (Malkov heuristic, extension on layer 0), sort.
 template <int ELEM, bool F32>
 __global__ void __launch_bounds__(kInsertThreads, 1)
-k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__restrict__ ws, WsLayout wl) {
+k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_words, uint8_t *__restrict__ ws,
+                      WsLayout wl) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ HnswShared sh;
@@ -431,7 +487,13 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
     }
     __syncthreads();
     uint32_t phase = 0;
-    uint32_t stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
+    Visit vis;
+    vis.nwords = bm_words;
+    vis.bits = bm_words ? reinterpret_cast<uint32_t *>(smem + row128 +
+                                                       (ret_in_smem ? ((size_t)wv.ef_c + 2) * sizeof(HItem) : 0))
+                        : nullptr;
+    vis.stamps = stamps;
+    vis.stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
     unsigned long long neval = 0;
     const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (;;) {
@@ -454,8 +516,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
         float d_ep = sh.D[0];
         // ---- greedy descent through the layers above the point's level: search_layer(ef = 1)
         for (int l = (int)lmax; l >= (int)level + 1; l--) {
-            stamp++;
-            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, 1, (uint32_t)l, sh, stamps, stamp, neval);
+            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, 1, (uint32_t)l, sh, vis, neval);
             if (threadIdx.x == 0) {
                 s_ep = ep;
                 s_dep = d_ep;
@@ -473,8 +534,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
         }
         const int top = (int)(level < lmax ? level : lmax);
         for (int l = top; l >= 0; l--) {
-            stamp++;
-            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, wv.ef_c, (uint32_t)l, sh, stamps, stamp, neval);
+            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval);
             // ---- earlier points of this wave, in order, as if search_layer had met them last
             {
                 const uint32_t m = wv.first + threadIdx.x;
@@ -520,27 +580,28 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
                         s_nout++;
                     }
                 }
-                if (s_mode == 2) {  // extension: the neighbours of the candidates join them
-                    stamp++;        // (thread 0's copy; re-broadcast below)
+            }
+            __syncthreads();
+            if (s_mode == 2) {  // extension: the neighbours of the candidates join them
+                vis.begin();
+                if (threadIdx.x == 0) {
                     const uint32_t n0 = sh.cand.n;
-                    for (uint32_t i = 0; i < n0; i++) stamps[sh.cand.a[i].p] = stamp;
+                    for (uint32_t i = 0; i < n0; i++) vis.mark(sh.cand.a[i].p);
                     uint32_t nnew = 0;
                     for (uint32_t i = 0; i < n0; i++) {
                         uint32_t len;
                         const uint32_t *lst = list_of(g, sh.cand.a[i].p, (uint32_t)l, len);
                         for (uint32_t j = 0; j < len; j++) {
-                            const uint32_t e = __ldcg(&lst[j]);
-                            if (stamps[e] == stamp) continue;
-                            stamps[e] = stamp;
+                            const uint32_t e = __ldg(&lst[j]);
+                            if (vis.seen(e)) continue;
+                            vis.mark(e);
                             newc[nnew++] = e;
                         }
                     }
                     s_nnew = nnew;
                 }
-                sh.work = stamp;
+                __syncthreads();
             }
-            __syncthreads();
-            stamp = sh.work;
             if (s_mode == 2) {
                 const uint32_t nnew = s_nnew;
                 for (uint32_t c0 = 0; c0 < nnew; c0 += kMaxList) {
@@ -643,7 +704,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint8_t *__rest
             if (l > 0 && s_mode != 0) stage_row(smem, qrow, row, &bar, phase);  // the heuristic replaced q
         }
     }
-    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = stamp;
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = vis.stamp;
 }
 
 // Phase B, step 1: the selections become the lists of the new points
