@@ -12,7 +12,7 @@
 
 namespace gsb {
 
-constexpr int kHamThreads = 256;
+constexpr int kHamThreads = 512;
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
