@@ -38,83 +38,103 @@ struct HItem {
     uint32_t p;
 };
 
-struct DHeap {
-    HItem *a;
+// Binary heap of thread 0, Rust std::collections::BinaryHeap order of operations.  HYB: the
+// first `cs` entries live in shared memory and the rest in the CTA's global workspace -- a sift
+// walks log2(n) DEPENDENT entries, and a global store invalidates the L1 line, so a heap kept in
+// global memory runs at L2 latency (the candidate heap is popped once per expansion).
+template <bool HYB>
+struct HeapT {
+    HItem *a;     // shared-memory part (HYB) or the whole heap
+    HItem *g;     // HYB: entry i >= cs is g[i - cs]
+    uint32_t cs;
     uint32_t n;
+    __device__ __forceinline__ HItem &at(uint32_t i) {
+        if (HYB) return i < cs ? a[i] : g[i - cs];
+        return a[i];
+    }
     __device__ __forceinline__ void sift_up(uint32_t start, uint32_t pos) {
-        const HItem e = a[pos];
+        const HItem e = at(pos);
         while (pos > start) {
             const uint32_t parent = (pos - 1) >> 1;
-            if (e.d <= a[parent].d) break;
-            a[pos] = a[parent];
+            const HItem pe = at(parent);
+            if (e.d <= pe.d) break;
+            at(pos) = pe;
             pos = parent;
         }
-        a[pos] = e;
+        at(pos) = e;
     }
     __device__ __forceinline__ void push(float d, uint32_t p) {
-        a[n].d = d;
-        a[n].p = p;
+        HItem e;
+        e.d = d;
+        e.p = p;
+        at(n) = e;
         n++;
         sift_up(0, n - 1);
     }
     __device__ __forceinline__ void sift_down_to_bottom(uint32_t pos) {
         const uint32_t end = n, start = pos;
-        const HItem e = a[pos];
+        const HItem e = at(pos);
         uint32_t child = 2 * pos + 1;
         while (end >= 2 && child <= end - 2) {
-            child += (a[child].d <= a[child + 1].d) ? 1u : 0u;
-            a[pos] = a[child];
+            const HItem c0 = at(child), c1 = at(child + 1);
+            const bool right = c0.d <= c1.d;
+            child += right ? 1u : 0u;
+            at(pos) = right ? c1 : c0;
             pos = child;
             child = 2 * pos + 1;
         }
         if (end >= 1 && child == end - 1) {
-            a[pos] = a[child];
+            at(pos) = at(child);
             pos = child;
         }
-        a[pos] = e;
+        at(pos) = e;
         sift_up(start, pos);
     }
     __device__ __forceinline__ HItem pop() {
-        HItem item = a[n - 1];
+        HItem item = at(n - 1);
         n--;
         if (n > 0) {
-            const HItem t = a[0];
-            a[0] = item;
+            const HItem t = at(0);
+            at(0) = item;
             item = t;
             sift_down_to_bottom(0);
         }
         return item;
     }
     __device__ __forceinline__ void sift_down_range(uint32_t pos, uint32_t end) {
-        const HItem e = a[pos];
+        const HItem e = at(pos);
         uint32_t child = 2 * pos + 1;
         while (end >= 2 && child <= end - 2) {
-            child += (a[child].d <= a[child + 1].d) ? 1u : 0u;
-            if (e.d >= a[child].d) {
-                a[pos] = e;
+            const HItem c0 = at(child), c1 = at(child + 1);
+            const bool right = c0.d <= c1.d;
+            child += right ? 1u : 0u;
+            const HItem c = right ? c1 : c0;
+            if (e.d >= c.d) {
+                at(pos) = e;
                 return;
             }
-            a[pos] = a[child];
+            at(pos) = c;
             pos = child;
             child = 2 * pos + 1;
         }
-        if (end >= 1 && child == end - 1 && e.d < a[child].d) {
-            a[pos] = a[child];
+        if (end >= 1 && child == end - 1 && e.d < at(child).d) {
+            at(pos) = at(child);
             pos = child;
         }
-        a[pos] = e;
+        at(pos) = e;
     }
     __device__ __forceinline__ void into_sorted() {
         uint32_t end = n;
         while (end > 1) {
             end--;
-            const HItem t = a[0];
-            a[0] = a[end];
-            a[end] = t;
+            const HItem t = at(0);
+            at(0) = at(end);
+            at(end) = t;
             sift_down_range(0, end);
         }
     }
 };
+constexpr uint32_t kCandSmem = 2048;  // entries of the candidate heap kept in shared memory
 
 struct GraphView {
     const uint8_t *sigs;        // n x S x elem
@@ -178,7 +198,8 @@ struct HnswShared {
     uint32_t wcnt[32];
     uint32_t done, node, flag, work, next;
     float fval;
-    DHeap cand, ret;  // owned by thread 0
+    HeapT<true> cand;   // owned by thread 0
+    HeapT<false> ret;
 };
 
 // distances of the staged row to the nE rows E[i] -> D[i].  One warp per row when there are
@@ -303,7 +324,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
                 const HItem c = sh.cand.pop();
                 if (-c.d > sh.ret.a[0].d) sh.done = 1;
                 sh.node = c.p;
-                sh.next = sh.cand.n ? sh.cand.a[0].p : 0xFFFFFFFFu;  // the likely next pop
+                sh.next = sh.cand.n ? sh.cand.at(0).p : 0xFFFFFFFFu;  // the likely next pop
             }
         }
         __syncthreads();
@@ -367,6 +388,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ HnswShared sh;
+    __shared__ __align__(8) HItem cand_sm[kCandSmem];
     __shared__ uint32_t s_q;
     const size_t row = (size_t)g.S * ELEM;
     const size_t row128 = (row + 127) & ~(size_t)127;
@@ -375,7 +397,9 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
-        sh.cand.a = reinterpret_cast<HItem *>(my + wl.off_cand);
+        sh.cand.a = cand_sm;
+        sh.cand.g = reinterpret_cast<HItem *>(my + wl.off_cand);
+        sh.cand.cs = kCandSmem;
         sh.ret.a = ret_in_smem ? reinterpret_cast<HItem *>(smem + row128) : reinterpret_cast<HItem *>(my + wl.off_ret);
     }
     __syncthreads();
@@ -469,6 +493,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ HnswShared sh;
+    __shared__ __align__(8) HItem cand_sm[kCandSmem];
     __shared__ uint32_t s_t, s_ep, s_nout, s_mode, s_nnew;
     __shared__ float s_dep;
     __shared__ uint32_t outP[kMaxList];
@@ -482,7 +507,9 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
-        sh.cand.a = reinterpret_cast<HItem *>(my + wl.off_cand);
+        sh.cand.a = cand_sm;
+        sh.cand.g = reinterpret_cast<HItem *>(my + wl.off_cand);
+        sh.cand.cs = kCandSmem;
         sh.ret.a = ret_in_smem ? reinterpret_cast<HItem *>(smem + row128) : reinterpret_cast<HItem *>(my + wl.off_ret);
     }
     __syncthreads();
@@ -586,11 +613,11 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                 vis.begin();
                 if (threadIdx.x == 0) {
                     const uint32_t n0 = sh.cand.n;
-                    for (uint32_t i = 0; i < n0; i++) vis.mark(sh.cand.a[i].p);
+                    for (uint32_t i = 0; i < n0; i++) vis.mark(sh.cand.at(i).p);
                     uint32_t nnew = 0;
                     for (uint32_t i = 0; i < n0; i++) {
                         uint32_t len;
-                        const uint32_t *lst = list_of(g, sh.cand.a[i].p, (uint32_t)l, len);
+                        const uint32_t *lst = list_of(g, sh.cand.at(i).p, (uint32_t)l, len);
                         for (uint32_t j = 0; j < len; j++) {
                             const uint32_t e = __ldg(&lst[j]);
                             if (vis.seen(e)) continue;
