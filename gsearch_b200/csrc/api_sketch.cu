@@ -79,7 +79,8 @@ __global__ void k_fill_u32(uint32_t *p, size_t n, uint32_t v) {
 // per group: clear the hash sets, reset cursors and slot state, compute the bounds
 __global__ void __launch_bounds__(256)
 k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult *__restrict__ res,
-             SketchConsts sc, ProbBound *__restrict__ bound, uint32_t *__restrict__ overflow) {
+             SketchConsts sc, ProbBound *__restrict__ bound, uint32_t *__restrict__ overflow,
+             uint32_t *__restrict__ retry) {
     const uint32_t j = blockIdx.y;
     if (j >= njobs) return;
     const ProbJob job = jobs[j];
@@ -105,6 +106,7 @@ k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult 
         *job.ovf_n = 0;
         *job.n_coll = 0;
         overflow[j] = 0;
+        retry[job.file] = 0;  // k3_prob_finalize accumulates into it
         const uint32_t N = res[job.file].nsym;
         const uint32_t nk = N >= sc.k ? N - sc.k + 1 : 0;
         ProbBound b;
@@ -394,7 +396,7 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     const FileResult *res = h->d_res.as<FileResult>();
     {
         Timed t_(h, CAT_RESET, st);
-        k_prob_reset<<<dim3(296, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf);
+        k_prob_reset<<<dim3(296, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf, h->d_retry.as<uint32_t>());
     }
     if (nchunks) {
         {
@@ -431,10 +433,10 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
     k3_prob_points<KT, 1><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
     if (h->elem == 8)
-        k3_prob_finalize<uint64_t><<<njobs, 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint64_t *)d_sig,
+        k3_prob_finalize<uint64_t><<<dim3(kFinParts, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint64_t *)d_sig,
                                                           d_nb, h->d_retry.as<uint32_t>());
     else
-        k3_prob_finalize<uint32_t><<<njobs, 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig,
+        k3_prob_finalize<uint32_t><<<dim3(kFinParts, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig,
                                                           d_nb, h->d_retry.as<uint32_t>());
     h->launches += nchunks ? 8 : 4;
 }

@@ -661,44 +661,36 @@ k3_prob_points(const ProbJob *__restrict__ jobs, uint32_t njobs,
     }
 }
 
-// per genome: check the bound, convert to the output element type, reset touched counters
+// per genome: check the bound, convert to the output element type, reset touched counters.
+// grid = (kFinParts, njobs): the slots of a genome are split over several CTAs (one CTA per
+// genome walked 18 000 slots in 70 dependent rounds); `retry` is zeroed before the pass.
+constexpr uint32_t kFinParts = 8;
 template <typename SigT>
 __global__ void __launch_bounds__(256)
 k3_prob_finalize(const ProbJob *__restrict__ jobs, uint32_t njobs,
                  const ProbBound *__restrict__ bound, const FileResult *__restrict__ res,
                  SketchConsts sc, SigT *__restrict__ sig_out, uint64_t *__restrict__ nb_bases_out,
                  uint32_t *__restrict__ retry) {
-    const uint32_t j = blockIdx.x;
+    const uint32_t j = blockIdx.y;
     if (j >= njobs) return;
     const ProbJob job = jobs[j];
-    __shared__ unsigned long long smax[256];
     const unsigned long long Tb = (unsigned long long)__double_as_longlong(bound[j].T);
-    unsigned long long mx = 0;
-    for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
-        const unsigned long long hb = job.hmin[k];
-        mx = hb > mx ? hb : mx;
+    const uint32_t N = res[job.file].nsym;
+    const bool has_kmers = N >= sc.k && res[job.file].status == 0;
+    bool over = false;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < sc.m; k += gridDim.x * blockDim.x) {
+        // exact iff every slot's minimum is strictly below the bound (no skipped point can win
+        // or tie); an empty genome is trivially exact
+        over |= !(job.hmin[k] < Tb);
         const unsigned long long s = job.sigw[k];
         sig_out[(size_t)job.file * sc.m + k] = (s == ~0ull) ? (SigT)0 : (SigT)s;
     }
-    smax[threadIdx.x] = mx;
-    __syncthreads();
-    for (int d = 128; d >= 1; d >>= 1) {
-        if (threadIdx.x < d && smax[threadIdx.x + d] > smax[threadIdx.x])
-            smax[threadIdx.x] = smax[threadIdx.x + d];
-        __syncthreads();
-    }
-    const uint32_t N = res[job.file].nsym;
-    const bool has_kmers = N >= sc.k && res[job.file].status == 0;
-    if (threadIdx.x == 0) {
-        // exact iff every slot's minimum is strictly below the bound (no skipped point can
-        // win or tie); an empty genome is trivially exact
-        uint32_t r = (has_kmers && !(smax[0] < Tb)) ? 1u : 0u;
-        retry[job.file] = r | (res[job.file].status << 8);
+    if (__syncthreads_or(over && has_kmers) && threadIdx.x == 0) atomicOr(&retry[job.file], 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (res[job.file].status) atomicOr(&retry[job.file], res[job.file].status << 8);
         if (nb_bases_out) nb_bases_out[job.file] = res[job.file].nbases;
-    }
-    // the extra-occurrence counters touched by this genome are cleared by the slot's next
-    // k_prob_reset (full grid) from the list left here
-    if (threadIdx.x == 0) {
+        // the extra-occurrence counters touched by this genome are cleared by the slot's next
+        // k_prob_reset (full grid) from the list left here
         const uint32_t n = *job.list_n;
         *job.prev_n = n > job.list_cap ? job.list_cap : n;
     }
