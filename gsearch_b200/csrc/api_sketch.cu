@@ -442,15 +442,15 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
 }
 
 template <class Src, typename KT>
-void launch_dens(gsb_sketcher *h, uint32_t njobs, uint32_t nchunks, bool dna, bool want_bounds, void *d_sig,
-                 uint64_t *d_nb, cudaStream_t st) {
-    const DensJob *jobs = h->d_jobs.as<DensJob>();
+void launch_dens(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunks, uint32_t cpoff, bool dna,
+                 bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    const DensJob *jobs = h->d_jobs.as<DensJob>() + joff;
     const FileResult *res = h->d_res.as<FileResult>();
     if (nchunks) {
-        Timed t_(h, CAT_K2, st);
-        const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * 8));
+        Timed t_(h, CAT_K2_MARK, st);
+        const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * 4));
         k2_optdens<Src, KT><<<grid, kK2Threads, 0, st>>>(
-            jobs, h->d_chunk_prefix.as<uint32_t>(), njobs, h->d_files.as<FileDesc>(), res,
+            jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
             dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
             want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
     }
@@ -630,44 +630,86 @@ int run_super_sequential(gsb_sketcher *h, const std::vector<uint32_t> &list, voi
 }
 
 int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vector<double> &tmult,
-             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st, K1Plan &kp) {
     const bool dna = h->p.data_t == GSB_DATA_DNA;
     const bool want_bounds = dna && !h->p.block_flag;
     const uint32_t n = (uint32_t)todo.size();
+    // files per group: groups alternate between the two group streams (GSB_DENS_GROUP overrides)
+    const uint32_t kG = (uint32_t)env_int("GSB_DENS_GROUP", 16, 1, 256);
+    const uint32_t ngroups = (n + kG - 1) / kG;
     int rc;
     if ((rc = h->h_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
     if ((rc = h->d_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
-    if ((rc = h->h_chunk_prefix.ensure((size_t)(n + 1) * 4))) return rc;
-    if ((rc = h->d_chunk_prefix.ensure((size_t)(n + 1) * 4))) return rc;
+    if ((rc = h->h_chunk_prefix.ensure((size_t)ngroups * (kG + 1) * 4))) return rc;
+    if ((rc = h->d_chunk_prefix.ensure((size_t)ngroups * (kG + 1) * 4))) return rc;
     if ((rc = h->d_bins.ensure((size_t)n * h->sc.m * 4))) return rc;
     DensJob *hj = h->h_jobs.as<DensJob>();
     uint32_t *hcp = h->h_chunk_prefix.as<uint32_t>();
-    uint64_t acc = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t f = todo[i];
-        const size_t len = h_offsets[f + 1] - h_offsets[f];
-        hj[i].file = f;
-        hj[i].bins = h->d_bins.as<uint32_t>() + (size_t)i * h->sc.m;
-        hj[i].tmult = tmult[i];
-        hcp[i] = (uint32_t)acc;
-        acc += (len + kChunk - 1) / kChunk;
-    }
-    hcp[n] = (uint32_t)acc;
-    if (acc > 0x7FFFFFFFull) {
-        set_error("batch too large: %llu k-mer chunks", (unsigned long long)acc);
-        return GSB_ERR_CAPACITY;
+    std::vector<uint32_t> group_chunks(ngroups);
+    for (uint32_t g = 0; g < ngroups; g++) {
+        uint64_t acc = 0;
+        for (uint32_t s = 0; s <= kG; s++) {
+            hcp[g * (kG + 1) + s] = (uint32_t)acc;
+            const uint32_t i = g * kG + s;
+            if (s < kG && i < n) {
+                const uint32_t f = todo[i];
+                const size_t len = h_offsets[f + 1] - h_offsets[f];
+                hj[i].file = f;
+                hj[i].bins = h->d_bins.as<uint32_t>() + (size_t)i * h->sc.m;
+                hj[i].tmult = tmult[i];
+                acc += (len + kChunk - 1) / kChunk;
+            }
+        }
+        if (acc > 0x7FFFFFFFull) {
+            set_error("batch too large: %llu k-mer chunks", (unsigned long long)acc);
+            return GSB_ERR_CAPACITY;
+        }
+        group_chunks[g] = (uint32_t)acc;
     }
     GSB_CUDA_TRY(pull_small(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), st));
-    GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)(n + 1) * 4, st));
+    GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (kG + 1) * 4, st));
     k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
     h->launches += 1;
-    const uint32_t nchunks = (uint32_t)acc;
-    if (dna) {
-        if (h->kt32) launch_dens<SrcDNA<uint32_t>, uint32_t>(h, n, nchunks, true, want_bounds, d_sig, d_nb, st);
-        else launch_dens<SrcDNA<uint64_t>, uint64_t>(h, n, nchunks, true, want_bounds, d_sig, d_nb, st);
-    } else {
-        if (h->kt32) launch_dens<SrcAA<uint32_t>, uint32_t>(h, n, nchunks, false, false, d_sig, d_nb, st);
-        else launch_dens<SrcAA<uint64_t>, uint64_t>(h, n, nchunks, false, false, d_sig, d_nb, st);
+    GSB_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    for (auto gs : h->gstream) GSB_CUDA_TRY(cudaStreamWaitEvent(gs, h->ev_fork, 0));
+    {
+        Timed tp_(h, CAT_K2, st);
+        for (uint32_t g = 0; g < ngroups; g++) {
+            const uint32_t joff = g * kG, nj = std::min<uint32_t>(kG, n - joff);
+            const uint32_t cpoff = g * (kG + 1);
+            cudaStream_t gs = h->gstream[g & 1];
+            if (kp.pending) {  // first pass: group g = files [joff, joff + nj); K1 runs ahead on `st`
+                GSB_CUDA_TRY(wait_files_ready(h, st, joff + nj - 1));
+                launch_k1_range(h, kp, joff, nj, st);
+                if (h->ev_k1.size() <= g) {
+                    cudaEvent_t e = nullptr;
+                    GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->ev_k1.push_back(e);
+                }
+                GSB_CUDA_TRY(cudaEventRecord(h->ev_k1[g], st));
+                GSB_CUDA_TRY(cudaStreamWaitEvent(gs, h->ev_k1[g], 0));
+            }
+            if (dna) {
+                if (h->kt32)
+                    launch_dens<SrcDNA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, true, want_bounds,
+                                                            d_sig, d_nb, gs);
+                else
+                    launch_dens<SrcDNA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, true, want_bounds,
+                                                            d_sig, d_nb, gs);
+            } else {
+                if (h->kt32)
+                    launch_dens<SrcAA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, false, false, d_sig,
+                                                           d_nb, gs);
+                else
+                    launch_dens<SrcAA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, false, false, d_sig,
+                                                           d_nb, gs);
+            }
+        }
+        kp.pending = false;
+        for (int i = 0; i < 2; i++) {
+            GSB_CUDA_TRY(cudaEventRecord(h->ev_join[i], h->gstream[i]));
+            GSB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[i], 0));
+        }
     }
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;
@@ -753,22 +795,7 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     const bool prob = h->p.algo == GSB_ALGO_PROB3A;
     // files of a group without any tile are not visited by K1: their result is "empty"
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_res.p, 0, (size_t)n * sizeof(FileResult), st));
-    if (!ntiles) {
-        kp.pending = false;
-    } else if (!prob) {
-        if (h->h2d_active) {  // pack chunk by chunk as the bytes arrive
-            uint32_t f0 = 0;
-            for (size_t c = 0; c < h->h2d_end.size(); c++) {
-                GSB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[c], 0));
-                launch_k1_range(h, kp, f0, h->h2d_end[c] - f0, st);
-                f0 = h->h2d_end[c];
-            }
-        } else {
-            launch_k1_range(h, kp, 0, n, st);
-        }
-        kp.pending = false;
-        GSB_CUDA_TRY(cudaGetLastError());
-    }
+    if (!ntiles) kp.pending = false;  // otherwise K1 runs group by group inside the first pass
 
     // ---- K2/K3 with bound retries
     std::vector<uint32_t> todo(n);
@@ -777,7 +804,7 @@ extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_byte
     std::vector<uint32_t> seq_files;  // SuperMinHash: files for the sequential cold path
     for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++) {
         rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp)
-                  : run_dens(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st);
+                  : run_dens(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp);
         if (rc) return rc;
         GSB_CUDA_TRY(cudaMemcpyAsync(h->h_retry.p, h->d_retry.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         GSB_CUDA_TRY(cudaStreamSynchronize(st));

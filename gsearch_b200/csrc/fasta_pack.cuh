@@ -65,6 +65,15 @@ __device__ __forceinline__ uint32_t fn_zero_lanes(uint32_t f) {
     return (z & 1u) | ((z >> 2) & 1u) << 8 | ((z >> 4) & 1u) << 16 | ((z >> 6) & 1u) << 24;
 }
 
+// residues "ACDEFGHIKLMNPQRSTVWY" -> 1..20 without a table: bit (c - 'A') of the mask says valid,
+// the rank of that bit is the code (the alphabet string is in alphabetical order)
+constexpr uint32_t kAAMask = 0x16fbdfdu;
+__device__ __forceinline__ uint32_t aa_code(uint32_t c) {  // 0 = not a residue
+    const uint32_t d = c - 'A';
+    if (d > 25u || !((kAAMask >> d) & 1u)) return 0u;
+    return (uint32_t)__popc(kAAMask & ((1u << d) - 1u)) + 1u;
+}
+
 template <int DATA_T>
 __device__ __forceinline__ int sym_code(uint32_t c, const uint8_t *aa_lut) {
     if (DATA_T == 0) {
@@ -74,7 +83,8 @@ __device__ __forceinline__ int sym_code(uint32_t c, const uint8_t *aa_lut) {
         const uint32_t x = (c >> 1) & 3u;  // A0 C1 T2 G3
         return (int)(x ^ (x >> 1));        // A0 C1 G2 T3
     } else {
-        const int v = aa_lut[c];
+        (void)aa_lut;
+        const int v = (int)aa_code(c);
         return v ? v : -1;
     }
 }
@@ -164,7 +174,10 @@ __device__ __forceinline__ bool chunk16_scan(const uint8_t *p, const uint8_t *aa
     }
     if (DATA_T == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) c.sym |= (aa_lut[p[i]] ? 1u : 0u) << i;
+        for (int i = 0; i < 16; i++) {
+            const uint32_t d = ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 'A';
+            c.sym |= ((d <= 25u) ? ((kAAMask >> d) & 1u) : 0u) << i;
+        }
     }
     return true;
 }
@@ -472,7 +485,7 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if ((emit >> i) & 1u) stage[o++] = aa_lut[p[i]];
+                if ((emit >> i) & 1u) stage[o++] = (uint8_t)aa_code(p[i]);
         }
     } else {
 #pragma unroll 1
