@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -93,6 +94,7 @@ struct GrowBuf {
 }  // namespace
 
 struct gsb_index {
+    std::recursive_mutex mu;  // a handle serialises its calls
     gsb_index_params p;
     int device = 0;
     int nsm = 148;
@@ -292,6 +294,8 @@ int ensure_workspace(gsb_index *idx, uint32_t nctas, uint64_t npts, uint32_t ef)
 extern "C" int gsb_index_load_graph(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n,
                                     const uint8_t *levels, const uint32_t *ranks, const uint64_t *nbr_offsets,
                                     const uint32_t *nbr_index, const float *nbr_dist, uint64_t entry_point) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || (n && (!sigs || !ids || !levels || !ranks || !nbr_offsets || !nbr_index))) {
         set_error("gsb_index_load_graph: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -417,6 +421,8 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
 extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t nq, uint32_t knbn,
                                       uint32_t ef, gsb_neighbour *out, uint32_t *counts_out,
                                       uint64_t *nb_eval_out) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || (nq && (!queries || !out || !counts_out))) {
         set_error("gsb_index_search_batch: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -524,6 +530,8 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
 }  // namespace
 
 extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || (n && (!sigs || !ids))) {
         set_error("gsb_index_insert_batch: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -651,6 +659,8 @@ int fetch_graph(const gsb_index *idx, HostGraph &hg) {
 }  // namespace
 
 extern "C" int gsb_index_graph_sizes(const gsb_index *idx, uint64_t *total_lists, uint64_t *total_nbrs) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || !total_lists || !total_nbrs) {
         set_error("gsb_index_graph_sizes: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -672,6 +682,8 @@ extern "C" int gsb_index_graph_sizes(const gsb_index *idx, uint64_t *total_lists
 extern "C" int gsb_index_export_graph(const gsb_index *idx, uint8_t *levels, uint32_t *ranks, uint64_t *ids,
                                       uint64_t *nbr_offsets, uint32_t *nbr_index, float *nbr_dist,
                                       uint64_t *entry_point) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || !nbr_offsets || !entry_point) {
         set_error("gsb_index_export_graph: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -719,6 +731,8 @@ bool rd(FILE *f, T *p, size_t n) {
 }  // namespace
 
 extern "C" int gsb_index_dump(const gsb_index *idx, const char *dir, const char *basename) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || !dir || !basename) {
         set_error("gsb_index_dump: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -770,6 +784,8 @@ extern "C" int gsb_index_dump(const gsb_index *idx, const char *dir, const char 
 }
 
 extern "C" int gsb_index_load(gsb_index *idx, const char *dir, const char *basename) {
+    std::unique_lock<std::recursive_mutex> lock_;
+    if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || !dir || !basename) {
         set_error("gsb_index_load: NULL argument");
         return GSB_ERR_INVALID_ARG;

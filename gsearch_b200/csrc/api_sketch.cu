@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -71,11 +72,6 @@ static cudaError_t pull_small(void *dst, const void *src_pinned, size_t bytes, c
     return cudaGetLastError();
 }
 
-__global__ void k_fill_u32(uint32_t *p, size_t n, uint32_t v) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        p[i] = v;
-}
-
 // per group: clear the hash sets, reset cursors and slot state, compute the bounds
 __global__ void __launch_bounds__(256)
 k_prob_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult *__restrict__ res,
@@ -129,6 +125,7 @@ __global__ void k_dens_reset(uint32_t *bins, size_t n) {
 }  // namespace
 
 struct gsb_sketcher {
+    std::mutex mu;  // a handle serialises its calls (the reference clones its sketcher per worker)
     gsb_sketch_params p;
     int device = 0;
     int sig_type = 0;
@@ -635,23 +632,23 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     const bool want_bounds = dna && !h->p.block_flag;
     const uint32_t n = (uint32_t)todo.size();
     // files per group: groups alternate between the two group streams (GSB_DENS_GROUP overrides)
-    const uint32_t kG = (uint32_t)env_int("GSB_DENS_GROUP", 16, 1, 256);
-    const uint32_t ngroups = (n + kG - 1) / kG;
+    const uint32_t grp = (uint32_t)env_int("GSB_DENS_GROUP", 16, 1, 256);
+    const uint32_t ngroups = (n + grp - 1) / grp;
     int rc;
     if ((rc = h->h_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
     if ((rc = h->d_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
-    if ((rc = h->h_chunk_prefix.ensure((size_t)ngroups * (kG + 1) * 4))) return rc;
-    if ((rc = h->d_chunk_prefix.ensure((size_t)ngroups * (kG + 1) * 4))) return rc;
+    if ((rc = h->h_chunk_prefix.ensure((size_t)ngroups * (grp + 1) * 4))) return rc;
+    if ((rc = h->d_chunk_prefix.ensure((size_t)ngroups * (grp + 1) * 4))) return rc;
     if ((rc = h->d_bins.ensure((size_t)n * h->sc.m * 4))) return rc;
     DensJob *hj = h->h_jobs.as<DensJob>();
     uint32_t *hcp = h->h_chunk_prefix.as<uint32_t>();
     std::vector<uint32_t> group_chunks(ngroups);
     for (uint32_t g = 0; g < ngroups; g++) {
         uint64_t acc = 0;
-        for (uint32_t s = 0; s <= kG; s++) {
-            hcp[g * (kG + 1) + s] = (uint32_t)acc;
-            const uint32_t i = g * kG + s;
-            if (s < kG && i < n) {
+        for (uint32_t s = 0; s <= grp; s++) {
+            hcp[g * (grp + 1) + s] = (uint32_t)acc;
+            const uint32_t i = g * grp + s;
+            if (s < grp && i < n) {
                 const uint32_t f = todo[i];
                 const size_t len = h_offsets[f + 1] - h_offsets[f];
                 hj[i].file = f;
@@ -667,7 +664,7 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
         group_chunks[g] = (uint32_t)acc;
     }
     GSB_CUDA_TRY(pull_small(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), st));
-    GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (kG + 1) * 4, st));
+    GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (grp + 1) * 4, st));
     k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
     h->launches += 1;
     GSB_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
@@ -675,8 +672,8 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     {
         Timed tp_(h, CAT_K2, st);
         for (uint32_t g = 0; g < ngroups; g++) {
-            const uint32_t joff = g * kG, nj = std::min<uint32_t>(kG, n - joff);
-            const uint32_t cpoff = g * (kG + 1);
+            const uint32_t joff = g * grp, nj = std::min<uint32_t>(grp, n - joff);
+            const uint32_t cpoff = g * (grp + 1);
             cudaStream_t gs = h->gstream[g & 1];
             if (kp.pending) {  // first pass: group g = files [joff, joff + nj); K1 runs ahead on `st`
                 GSB_CUDA_TRY(wait_files_ready(h, st, joff + nj - 1));
@@ -717,9 +714,22 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
 
 }  // namespace
 
+static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, const uint64_t *h_offsets, uint32_t n,
+                                   void *d_sig_out, uint64_t *d_nb_bases_out, void *stream);
+
 extern "C" int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_bytes, const uint64_t *h_offsets,
                                           uint32_t n, void *d_sig_out, uint64_t *d_nb_bases_out,
                                           void *stream) {
+    if (!h) {
+        set_error("gsb_sketch_fasta_batch_dev: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    std::lock_guard<std::mutex> lock(h->mu);
+    return sketch_batch_dev_locked(h, d_bytes, h_offsets, n, d_sig_out, d_nb_bases_out, stream);
+}
+
+static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, const uint64_t *h_offsets, uint32_t n,
+                                   void *d_sig_out, uint64_t *d_nb_bases_out, void *stream) {
     if (!h || !h_offsets || (n && (!d_bytes && h_offsets[n] > 0)) || (n && !d_sig_out)) {
         set_error("gsb_sketch_fasta_batch_dev: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -862,6 +872,7 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
         return GSB_ERR_INVALID_ARG;
     }
     if (n == 0) return GSB_OK;
+    std::lock_guard<std::mutex> lock(h->mu);
     GSB_CUDA_TRY(cudaSetDevice(h->device));
     const uint64_t lo = offsets[0], hi = offsets[n];
     if (hi < lo || (hi > lo && !bytes)) {
@@ -912,8 +923,8 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
     std::vector<uint64_t> rel(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
     h->h2d_active = true;
-    rc = gsb_sketch_fasta_batch_dev(h, h->d_bytes.as<uint8_t>(), rel.data(), n, h->d_sig.p, h->d_nb.as<uint64_t>(),
-                                    (void *)st);
+    rc = sketch_batch_dev_locked(h, h->d_bytes.as<uint8_t>(), rel.data(), n, h->d_sig.p, h->d_nb.as<uint64_t>(),
+                                 (void *)st);
     h->h2d_active = false;
     if (rc) {
         cudaStreamSynchronize(h->copy_stream);

@@ -98,15 +98,4 @@ __device__ __forceinline__ double exp01_sample_from(const Exp01 &e, double u0, X
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
-// warp-aggregated append: returns this lane's index in a global list, or ~0u if !pred
-__device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t *cursor) {
-    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-    if (mask == 0) return 0xffffffffu;
-    const uint32_t leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane_id() == leader) base = atomicAdd(cursor, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return pred ? base + __popc(mask & ((1u << lane_id()) - 1)) : 0xffffffffu;
-}
-
 }  // namespace gsb

@@ -14,11 +14,12 @@
 //   where (x_1,k_1,x_2,k_2,...) is the draw sequence of xoshiro256++ seeded by d.  The result
 //   does not depend on processing order, and a point with h >= T can be skipped whenever
 //   T >= max_k min-h[k] at the end (verified per genome; widened and re-run otherwise).
-//   * K2 streams k-mers, keeps an EXACT set of the genome's distinct canonical k-mers in a
-//     hash set of 32-bit entries (8-bit fingerprint | 24-bit position of first occurrence;
-//     equality is verified against the packed sequence, so the set is exact), counts extra
-//     occurrences, and emits only k-mers that can matter: first draw below T ("light"), or
-//     repeated (weight > 1).
+//   * K2 streams k-mers twice.  `k2_prob_mark`: every occurrence marks a blocked filter with one
+//     atomicOr; a k-mer that occurs more than once always ends with its flag raised.
+//     `k2_prob_classify`: a k-mer whose flag is down has weight 1 exactly and is kept only if
+//     its first draw can be below T ("light"); flagged occurrences go through an EXACT set
+//     (`k2_prob_overflow`: 32-bit entries = fingerprint | position of the first occurrence,
+//     equality verified against the packed sequence), which counts them.
 //   * K3a/K3b replay the exact f64 arithmetic for those few k-mers: atomicMin on the ordered
 //     bit pattern of h, then the owner of the minimum writes the k-mer (ties: smaller k-mer).
 #pragma once
@@ -33,7 +34,6 @@ constexpr int kRun = 32;                        // consecutive k-mer positions p
 constexpr int kChunk = kK2Threads * kRun;       // positions per CTA
 constexpr uint32_t kMaxProbSym = (1u << 30) - 2;  // widest position field of an exact-set entry (30 bits)
 constexpr int kG = 8;                             // k-mers hashed and probed together per thread
-constexpr int kProbeRounds = 4;                   // probes before an insertion is deferred
 constexpr uint32_t kStageCap = 3072;              // per-CTA candidate stage (entries, 48 KiB)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;         // list entry of a k-mer that never entered the exact set
 
@@ -58,7 +58,7 @@ struct ProbJob {
     uint32_t list_cap;
     uint32_t *list_n;    // cursor (device)
     uint32_t *prev_n;    // entries of the slot's previous genome whose counters are still set
-    struct OvfEntry *ovf;  // deferred insertions (probe sequence longer than kProbeRounds)
+    struct OvfEntry *ovf;  // flagged occurrences on their way to the exact set
     uint32_t ovf_cap;
     uint32_t *ovf_n;
     unsigned long long *hmin;  // [m] ordered bits of min h per slot
@@ -66,7 +66,7 @@ struct ProbJob {
     double tmult;        // early-stop bound multiplier (1 = default, grown on retry)
 };
 
-struct ProbBound {  // written by k_prob_setup
+struct ProbBound {  // written by k_prob_reset
     double T;       // points with h >= T are skipped
     uint64_t uT;    // 52-bit first draws below this are "light" (conservative superset)
 };
@@ -221,31 +221,7 @@ __device__ __forceinline__ uint64_t nohash_seed(KT v, uint32_t spec_flags) {
            (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
 }
 
-// ------------------------------------------------------------------ prob: setup
-__global__ void k_prob_setup(const ProbJob *__restrict__ jobs, uint32_t njobs,
-                             const FileResult *__restrict__ res, SketchConsts sc,
-                             ProbBound *__restrict__ bound) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
-    const uint32_t N = res[jobs[j].file].nsym;
-    const uint32_t nk = N >= sc.k ? N - sc.k + 1 : 0;
-    ProbBound b;
-    if (nk == 0) {
-        b.T = 0.0;
-        b.uT = 0;
-    } else {
-        b.T = jobs[j].tmult * ((double)sc.m / (double)nk) * sc.lnm8;
-        // x1 = c1*u >= u, so u < T is necessary for x1 < T (K3 re-tests exactly)
-        b.uT = b.T >= 1.0 ? (1ull << 52) : (uint64_t)(b.T * 4503599627370496.0) + 2;
-    }
-    bound[j] = b;
-}
-
 // ------------------------------------------------------------------ prob: K2
-// Deferred insertion: a k-mer whose first kProbeRounds slots are all taken by other k-mers
-// is finished by k2_prob_overflow.  Linear probing keeps this exact: every occurrence of that
-// k-mer sees the same occupied prefix, so all of them are deferred together and continue from
-// the same slot.
 struct OvfEntry {   // a k-mer occurrence that must go through the exact set
     uint64_t kmer;
     uint32_t pos1;  // position + 1 of this occurrence (the set entry is fingerprint | pos1)

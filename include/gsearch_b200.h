@@ -14,10 +14,12 @@
  *     nothing ever unwinds or aborts across the ABI (reference: panic!/exit(1),
  *     src/dna/dnasketch.rs:228,285,380,463);
  *   - the caller owns all in/out buffers; the library owns opaque handles;
- *   - `*_dev` variants take DEVICE pointers and a CUDA stream (passed as void*,
- *     0 = default stream) and do not synchronise; the plain variants take HOST
- *     pointers, stage through pinned memory, and return when results are in host
- *     memory;
+ *   - `*_dev` variants take DEVICE pointers (and, where stated, a CUDA stream passed
+ *     as void*, 0 = default stream); the plain variants take HOST pointers and return
+ *     when the results are in host memory;
+ *   - a handle serialises the calls made on it (internal lock); use one handle per
+ *     host thread for concurrency, as the reference clones its sketcher per worker
+ *     (src/dna/dnasketch.rs:305);
  *   - there is NO CPU fallback: if no CUDA device is usable every compute call
  *     returns GSB_ERR_NO_DEVICE.
  */
@@ -134,9 +136,10 @@ GSB_API uint32_t gsb_sketcher_elem_size(const gsb_sketcher *h);
 GSB_API int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets,
                                    uint32_t n, void *sig_out, uint64_t *nb_bases_out);
 
-/* Same, all pointers are device pointers; work is enqueued on `stream` and not
- * synchronised.  d_offsets may be NULL if h_offsets (host copy, n+1 values) is
- * supplied; h_offsets is required (grid sizing is done on the host).            */
+/* Same with the bytes and the outputs in device memory.  Work is enqueued on `stream`
+ * (and on internal streams ordered after it); the call returns after `stream` has been
+ * synchronised, because the rare early-stop-bound retries are decided on the host.
+ * h_offsets is a HOST array of n+1 values (grid sizing is done on the host).        */
 GSB_API int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_bytes,
                                        const uint64_t *h_offsets, uint32_t n, void *d_sig_out,
                                        uint64_t *d_nb_bases_out, void *stream);
