@@ -97,3 +97,23 @@ def test_tohnsw_request_add_end_to_end(tmp_path, monkeypatch):
     cli.main("request -b {} -r {} -n 5".format(work, qd).split())
     txt = open(work / "gsearch.neighbors.txt").read()
     assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(new / "g025.fa") in txt
+
+
+@pytest.mark.gpu
+def test_tohnsw_request_aa_optdens(tmp_path, monkeypatch):
+    db, qd, work = tmp_path / "db", tmp_path / "q", tmp_path / "work"
+    for d in (db, qd, work):
+        d.mkdir()
+    for i in range(12):
+        (db / f"p{i:03d}.faa").write_bytes(g.synth.aa_proteome(i, 60, 200))
+    (qd / "q.faa.gz").write_bytes(gzip.compress(g.synth.aa_proteome(7, 60, 200)))
+    (qd / "ignored.fna").write_bytes(g.synth.dna_genome(1, 5000))      # not an AA suffix
+    monkeypatch.chdir(work)
+    cli.main("tohnsw -d {} -k 7 -s 400 -n 8 --ef 40 --algo optdens --aa --scale_modify_f 0.25".format(db).split())
+    doc = json.load(open(work / "parameters.json"))
+    assert doc["sketch"] == {"kmer_size": 7, "sketch_size": 400, "algo": "OPTDENS", "data_t": "AA"}
+    assert doc["hnsw"]["scale_modification"] == 0.25
+    cli.main("request -b {} -r {} -n 3".format(work, qd).split())
+    txt = open(work / "gsearch.neighbors.txt").read()
+    assert txt.count("query_id:") >= 1 and "ignored" not in txt
+    assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(db / "p007.faa") in txt

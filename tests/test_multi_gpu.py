@@ -1,6 +1,7 @@
 """Two-GPU check of the sharded path (skipped on a one-GPU box): two NCCL ranks sketch their
-genomes with the CUDA sketcher, all-gather the signatures over NVLink, and every rank must hold
-exactly the single-GPU result in global order."""
+genomes with the CUDA sketcher, all-gather the signatures over NVLink, build the same index
+replica, search their share of the queries and gather the answers; everything must equal the
+single-GPU result in global order."""
 import os
 import socket
 import sys
@@ -34,7 +35,13 @@ def _worker(rank, world, port, nfiles, q):
         files = [g.synth.dna_genome(i, 150_000 + 1000 * i) for i in range(nfiles)]
         sk = g.Sketcher(g.SeqSketcherParams(21, 2048), device=rank)
         sig, nb = sharding.sketch_sharded(sk.sketch_files, files, rank, world, device=f"cuda:{rank}")
-        q.put((rank, sig, nb))
+        # tohnsw: insertion does not shard -- every rank builds the same (deterministic) replica
+        idx = g.Hnsw(g.HnswParams(max_nb_conn=8, ef=32), 2048, sig.dtype, device=rank)
+        idx.parallel_insert(sig, np.arange(nfiles, dtype=np.uint64))
+        # request: queries sharded over the ranks, answers gathered
+        out, cnt = sharding.search_sharded(lambda qs: idx.search_raw(qs, 4, 32)[:2], sig, 4, rank, world,
+                                           device=f"cuda:{rank}")
+        q.put((rank, sig, nb, out["d_id"].copy(), out["distance"].copy(), cnt))
     finally:
         dist.destroy_process_group()
 
@@ -59,6 +66,11 @@ def test_two_gpu_sketch_equals_one_gpu():
         assert p.exitcode == 0
     files = [g.synth.dna_genome(i, 150_000 + 1000 * i) for i in range(nfiles)]
     want, wnb = g.Sketcher(g.SeqSketcherParams(21, 2048)).sketch_files(files)
-    for rank, sig, nb in got:
+    idx = g.Hnsw(g.HnswParams(max_nb_conn=8, ef=32), 2048, want.dtype)
+    idx.parallel_insert(want, np.arange(nfiles, dtype=np.uint64))
+    wout, wcnt, _ = idx.search_raw(want, 4, 32)
+    for rank, sig, nb, ids, dd, cnt in got:
         assert sig.tobytes() == want.tobytes(), f"rank {rank}"
         assert nb.tolist() == wnb.tolist()
+        assert cnt.tolist() == wcnt.tolist() and ids.tolist() == wout["d_id"].tolist()
+        assert dd.tobytes() == wout["distance"].tobytes()
