@@ -71,3 +71,25 @@ def test_hnsw_at_reference_parameters_agrees_with_brute_force():
         # with ef >= n the search visits everything reachable: exact top-50 up to ties
         assert out["distance"][i, -1] == np.sort(d[i])[49]
     assert (neval <= n + 300).all()
+
+
+def test_baseline_config0_whole_pipeline_against_the_oracle(oracle):
+    """BASELINE configs[0]: tohnsw on 32 synthetic 1 Mbp FASTA, k=16 s=2048 --algo prob (-n 128
+    --ef 1600 as in the README): signatures, graph and answers all equal the CPU restatement."""
+    files = [g.synth.dna_genome(i, 1_000_000) for i in range(32)]
+    sig, nb = g.Sketcher(g.SeqSketcherParams(16, 2048)).sketch_files(files)
+    want, wnb = oracle.sketch_files(files, 16, 2048, nthreads=8)
+    assert sig.dtype == np.uint32 and sig.tobytes() == want.tobytes() and nb.tolist() == wnb.tolist()
+    ids = np.arange(32, dtype=np.uint64)
+    idx = g.Hnsw(g.HnswParams(max_nb_conn=128, ef=1600), 2048, np.uint32)
+    idx.parallel_insert(sig, ids)
+    h = oracle.Hnsw(128, 1600, 2048, np.uint32)
+    h.insert_waves(want, ids, 148)                       # the library's default wave = one point per SM
+    ga, gb = idx.export_graph(), h.export()
+    assert ga["entry_point"] == gb["entry_point"]
+    for k in ("levels", "ranks", "nbr_offsets", "nbr_index"):
+        assert np.array_equal(ga[k], gb[k]), k
+    got, gc, _ = idx.search_raw(sig, 10, 5000)           # ef_search = 5000, src/bin/gsearch.rs:893
+    ref, rc, _ = h.search(want, 10, 5000, nthreads=4)
+    assert gc.tolist() == rc.tolist() and got["d_id"].tolist() == ref["d_id"].tolist()
+    assert got["distance"].tobytes() == ref["distance"].tobytes()
