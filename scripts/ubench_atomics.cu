@@ -7,7 +7,7 @@ __device__ __forceinline__ uint32_t mix(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x;
 }
 // MODE 0: dependent CAS chain (next address waits for the result)   1: B independent CAS per step
-// MODE 2: RED (atomicMin, no return)   3: independent loads
+// MODE 2: RED (atomicMin, no return)   3: independent loads   4: one atomicOr + one load per step (2 ops)
 template <int MODE, int B>
 __global__ void k(uint32_t *t, uint32_t cap, int iters, uint32_t *sink) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, acc = 0;
@@ -19,7 +19,11 @@ __global__ void k(uint32_t *t, uint32_t cap, int iters, uint32_t *sink) {
             uint32_t idx = __umulhi(h, cap);
             if (MODE <= 1) old[b] = atomicCAS(&t[idx], 0u, h | 1u);
             else if (MODE == 2) { atomicMin(&t[idx], h); old[b] = 0; }
-            else old[b] = __ldcg(&t[idx]);
+            else if (MODE == 3) old[b] = __ldcg(&t[idx]);
+            else {
+                old[b] = atomicOr(&t[idx], h | 1u);
+                old[b] += __ldcg(&t[__umulhi(mix(h + 77u), cap)]);
+            }
         }
 #pragma unroll
         for (int b = 0; b < B; b++) acc += old[b];
@@ -37,7 +41,7 @@ void run(const char *name, uint32_t *t, size_t cap, uint32_t *sink) {
     k<MODE, B><<<blocks, threads>>>(t, (uint32_t)cap, iters, sink);
     cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
-    double ops = (double)blocks * threads * iters;
+    double ops = (double)blocks * threads * iters * (MODE == 4 ? 2 : 1);
     printf("%-28s table %7.1f MB : %8.2f Gops/s  (%.3f ms)\n", name, cap * 4 / 1e6, ops / ms / 1e6, ms);
 }
 int main() {
@@ -51,6 +55,7 @@ int main() {
         run<2, 4>("RED min B=4", t, cap, sink);
         run<3, 4>("LDG.cg B=4", t, cap, sink);
         run<3, 8>("LDG.cg B=8", t, cap, sink);
+        run<4, 8>("atomicOr + LDG.cg B=8", t, cap, sink);
     }
     return 0;
 }
