@@ -119,7 +119,17 @@ def format_answers(rank, qitem, neighbours, seqdict, threshold=ANSWER_THRESHOLD)
 
 
 # ---------------------------------------------------------------- GPU pipeline
-def sketch_directory(g, directory, p, pio, device=0):
+def read_all(paths, nbthreads):
+    """inflate a batch of files on a thread pool (zlib / bz2 / lzma release the GIL); the reference
+    does the same with rayon in process_dir_parallel (src/utils/files.rs:258-341)"""
+    if nbthreads <= 1 or len(paths) <= 1:
+        return [read_inflated(f) for f in paths]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=nbthreads) as ex:
+        return list(ex.map(read_inflated, paths))
+
+
+def sketch_directory(g, directory, p, pio, device=0, nbthreads=0):
     files = walk_fasta(directory, p["aa"])
     if not files:
         raise SystemExit(f"no fasta file found in {directory}")
@@ -131,7 +141,7 @@ def sketch_directory(g, directory, p, pio, device=0):
     batch = max(1, min(pio, 256))
     for b in range(0, len(files), batch):
         chunk = files[b:b + batch]
-        sig, nb = sk.sketch_files([read_inflated(f) for f in chunk])
+        sig, nb = sk.sketch_files(read_all(chunk, nbthreads or (os.cpu_count() or 1)))
         sigs.append(sig)
         items += [(f, "", int(n)) for f, n in zip(chunk, nb)]
     return np.concatenate(sigs), items, sk.dtype
@@ -155,7 +165,7 @@ def cmd_tohnsw(a):
     p = {"capacity": 1_500_000, "ef": a.ef, "nbng": a.nbng & 0xFF, "scale": a.scale_modify_f, "kmer": a.kmer,
          "sketch": a.sketch, "algo": a.algo, "aa": a.aa, "block": a.block}   # `nbng as u8`, gsearch.rs:268
     t0 = time.time()
-    sig, items, dtype = sketch_directory(g, a.dir, p, a.pio)
+    sig, items, dtype = sketch_directory(g, a.dir, p, a.pio, nbthreads=a.nbthreads)
     t1 = time.time()
     idx = open_index(g, p, dtype)
     idx.parallel_insert(sig, np.arange(len(items), dtype=np.uint64))
@@ -169,7 +179,7 @@ def cmd_add(a):
     p = reload_parameters(a.hnsw)
     seqdict = reload_seqdict(a.hnsw)
     t0 = time.time()
-    sig, items, dtype = sketch_directory(g, a.new, p, a.pio)
+    sig, items, dtype = sketch_directory(g, a.new, p, a.pio, nbthreads=a.nbthreads)
     idx = open_index(g, p, dtype)
     idx.load(a.hnsw, "hnswdump")
     assert idx.get_nb_point() == len(seqdict)                       # src/dna/dnasketch.rs:438
@@ -183,7 +193,7 @@ def cmd_request(a):
     import gsearch_b200 as g
     p = reload_parameters(a.hnsw)
     seqdict = reload_seqdict(a.hnsw)
-    sig, items, dtype = sketch_directory(g, a.query, p, a.pio)
+    sig, items, dtype = sketch_directory(g, a.query, p, a.pio, nbthreads=a.nbthreads)
     idx = open_index(g, p, dtype)
     idx.load(a.hnsw, "hnswdump")
     out, counts, _ = idx.search_raw(sig, a.nbanswers, EF_SEARCH)
@@ -197,7 +207,7 @@ def cmd_request(a):
 def build_parser():
     ap = argparse.ArgumentParser(prog="gsearch", description="GSearch sketch-and-search path on B200")
     ap.add_argument("--pio", type=int, default=64, help="files read and sketched together")
-    ap.add_argument("--nbthreads", type=int, default=0, help="accepted for compatibility; the GPU path ignores it")
+    ap.add_argument("--nbthreads", type=int, default=0, help="host threads that read and inflate files (0 = all cores)")
     sub = ap.add_subparsers(dest="cmd", required=True)
     t = sub.add_parser("tohnsw")
     t.add_argument("-d", "--dir", required=True)
