@@ -306,6 +306,18 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
                                  unsigned long long &neval) {
     vis.begin();
     __syncthreads();
+    // thread 0 owns the heaps: pop the next candidate (or decide to stop) and publish it
+    auto pop_next = [&]() {
+        sh.done = 0;
+        if (sh.cand.n == 0) {
+            sh.done = 1;
+        } else {
+            const HItem c = sh.cand.pop();
+            if (-c.d > sh.ret.a[0].d) sh.done = 1;
+            sh.node = c.p;
+            sh.next = sh.cand.n ? sh.cand.at(0).p : 0xFFFFFFFFu;  // the likely next pop
+        }
+    };
     if (threadIdx.x == 0) {
         sh.cand.n = 0;
         sh.ret.n = 0;
@@ -313,42 +325,32 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
         sh.cand.push(-d_ep, ep);
         sh.ret.push(d_ep, ep);
         neval += 1;  // the reference evaluates the distance to the layer's entry point again
+        pop_next();
     }
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t cap = layer == 0 ? 2 * g.M : g.M;           // list capacity: entries beyond the
+    const uint32_t scan_warps = (cap + 31) >> 5;               // count are stale but readable
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            sh.done = 0;
-            if (sh.cand.n == 0) {
-                sh.done = 1;
-            } else {
-                const HItem c = sh.cand.pop();
-                if (-c.d > sh.ret.a[0].d) sh.done = 1;
-                sh.node = c.p;
-                sh.next = sh.cand.n ? sh.cand.at(0).p : 0xFFFFFFFFu;  // the likely next pop
-            }
-        }
         __syncthreads();
         if (sh.done) break;
         if (threadIdx.x < 32 && sh.next != 0xFFFFFFFFu) prefetch_list(g, sh.next, layer);
-        // gather the unvisited neighbours of the popped node in list order
+        // gather the unvisited neighbours of the popped node in list order; the count and the
+        // entries are loaded together (one L2 round trip instead of two dependent ones)
         uint32_t len;
         const uint32_t *lst = list_of(g, sh.node, layer, len);
-        uint32_t nb = 0xFFFFFFFFu;
-        bool unv = false;
-        if (threadIdx.x < len) {
-            nb = __ldg(&lst[threadIdx.x]);
-            unv = !vis.seen(nb);
-        }
+        uint32_t nb = threadIdx.x < cap ? __ldg(&lst[threadIdx.x]) : 0u;
+        const bool unv = threadIdx.x < len && !vis.seen(nb);
         const uint32_t bal = __ballot_sync(0xffffffffu, unv);
-        if (lane_id() == 0) sh.wcnt[threadIdx.x >> 5] = __popc(bal);
+        if (lane == 0) sh.wcnt[warp] = __popc(bal);
         __syncthreads();
         uint32_t pre = 0, tot = 0;
-        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
-            if (w < (threadIdx.x >> 5)) pre += sh.wcnt[w];
-            tot += sh.wcnt[w];
+        for (uint32_t w = 0; w < scan_warps; w++) {
+            const uint32_t c = sh.wcnt[w];
+            if (w < warp) pre += c;
+            tot += c;
         }
         if (unv) {
-            sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = nb;
+            sh.E[pre + __popc(bal & ((1u << lane) - 1))] = nb;
             vis.mark(nb);
         }
         __syncthreads();
@@ -364,6 +366,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
                     if (sh.ret.n > ef) (void)sh.ret.pop();
                 }
             }
+            pop_next();
         }
     }
     __syncthreads();
