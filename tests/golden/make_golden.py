@@ -23,10 +23,41 @@ CASES = {
     "optdens_aa_k7_s512": (lambda: [g.synth.aa_proteome(i, 40, 150) for i in range(3)], 7, 512, 2, 1, False),
     "optdens_dna_k21_s256": (lambda: [g.synth.dna_genome(i, 20000) for i in range(2)], 21, 256, 2, 0, False),
     "prob_aa_k6_s128": (lambda: [g.synth.aa_proteome(i, 30, 120) for i in range(2)], 6, 128, 0, 1, False),
+    # SuperMinHash: the first file is small (sequential cold path on the device), the second reaches
+    # every slot at the first level (bin-min fast path)
+    "super_dna_k21_s256": (lambda: [g.synth.dna_genome(7, 1500), g.synth.dna_genome(8, 40000)], 21, 256, 1, 0, False),
 }
 
 
-def main():
+def wave_graph_fixture():
+    """graph built by the oracle's wave insertion (wave_max = 24): pins the construction semantics
+    the device builder follows"""
+    rng = np.random.default_rng(321)
+    base = rng.integers(1, 2**31, (260, 192)).astype(np.uint32)
+    for i in range(1, 260):
+        redraw = rng.random(192) >= 0.8
+        base[i] = np.where(redraw, base[i], base[(i - 1) // 3])
+    base = base[rng.permutation(260)]
+    h = O.Hnsw(12, 40, 192, np.uint32, scale=0.5)
+    h.insert_waves(base, np.arange(260, dtype=np.uint64) * 2 + 1, 24)
+    gr = h.export()
+    np.savez_compressed(os.path.join(HERE, "hnsw_wave_u32_s192.npz"), base=base, levels=gr["levels"],
+                        ranks=gr["ranks"], ids=gr["ids"], nbr_offsets=gr["nbr_offsets"], nbr_index=gr["nbr_index"],
+                        nbr_dist=gr["nbr_dist"], entry=np.array([gr["entry_point"]], dtype=np.uint64))
+    print("wave graph fixture", len(gr["nbr_index"]), "links, entry", gr["entry_point"])
+
+
+def main(only=None):
+    if only == "new":   # fixtures added after the first set: leaves the committed ones untouched
+        name = "super_dna_k21_s256"
+        mk, k, S, algo, data_t, block = CASES[name]
+        files = mk()
+        sig, nb = O.sketch_files(files, k, S, algo, data_t, block)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), sig=sig, nb=nb,
+                            meta=np.array([k, S, algo, data_t, int(block), len(files)]),
+                            sha=np.array([hash_bytes(f) for f in files], dtype=np.uint64))
+        wave_graph_fixture()
+        return
     for name, (mk, k, S, algo, data_t, block) in CASES.items():
         files = mk()
         sig, nb = O.sketch_files(files, k, S, algo, data_t, block)
@@ -52,6 +83,7 @@ def main():
                         entry=np.array([gr["entry_point"]], dtype=np.uint64),
                         dist_q_base=O.hamming_matrix(q, base))
     print("hnsw fixture", counts.tolist(), neval.tolist())
+    wave_graph_fixture()
 
 
 def hash_bytes(b):
@@ -63,4 +95,4 @@ def hash_bytes(b):
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -60,3 +60,30 @@ def test_gpu_hnsw_and_hamming_reproduce_golden():
     assert out["distance"].tobytes() == z["distance"].tobytes()
     assert out["layer"].tolist() == z["layer"].tolist() and out["rank"].tolist() == z["rank"].tolist()
     assert counts.tolist() == z["counts"].tolist() and neval.tolist() == z["neval"].tolist()
+
+
+def _wave_fixture():
+    return np.load(os.path.join(GOLD, "hnsw_wave_u32_s192.npz"))
+
+
+def _same_graph(gr, z):
+    assert gr["entry_point"] == int(z["entry"][0])
+    for k in ("levels", "ranks", "ids", "nbr_offsets", "nbr_index"):
+        assert np.array_equal(gr[k], z[k]), k
+    assert gr["nbr_dist"].tobytes() == z["nbr_dist"].tobytes()
+
+
+def test_oracle_wave_insertion_reproduces_golden(oracle):
+    z = _wave_fixture()
+    h = oracle.Hnsw(12, 40, 192, np.uint32, scale=0.5)
+    h.insert_waves(z["base"], np.arange(260, dtype=np.uint64) * 2 + 1, 24)
+    _same_graph(h.export(), z)
+
+
+@pytest.mark.gpu
+def test_gpu_wave_insertion_reproduces_golden():
+    z = _wave_fixture()
+    idx = g.Hnsw(g.HnswParams(max_nb_conn=12, ef=40, scale_modification=0.5), 192, np.uint32)
+    idx.set_wave_max(24)
+    idx.parallel_insert(z["base"], np.arange(260, dtype=np.uint64) * 2 + 1)
+    _same_graph(idx.export_graph(), z)
