@@ -103,7 +103,7 @@ __device__ __forceinline__ void load_tile(const uint8_t *__restrict__ bytes, uin
         const int64_t off = (int64_t)tbase - 16 + (int64_t)blk * 16;
         uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
         if (off >= 0 && (uint64_t)off + 16 <= total) {
-            v = __ldg(reinterpret_cast<const uint4 *>(bytes + off));
+            v = __ldcs(reinterpret_cast<const uint4 *>(bytes + off));  // streaming: do not displace the filters in L2
         } else if (off + 16 > 0 && (uint64_t)(off < 0 ? 0 : off) < total) {
             uint8_t tmp[16];
 #pragma unroll
