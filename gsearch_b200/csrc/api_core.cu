@@ -58,11 +58,9 @@ template <int ELEM, bool F32>
 static int launch_hamming(const uint8_t *q, uint32_t nq, const uint8_t *c, uint32_t n, uint32_t S, float *out,
                           cudaStream_t st) {
     const size_t row = (size_t)S * ELEM;
-    const size_t smem = (row + 127) & ~(size_t)127;
-    if (smem > 200 * 1024) {
-        set_error("signature row of %zu bytes does not fit the shared-memory staging buffer", row);
-        return GSB_ERR_UNSUPPORTED;
-    }
+    size_t smem = (row + 127) & ~(size_t)127;
+    const int staged = smem <= 200 * 1024 ? 1 : 0;  // larger rows are read from global memory
+    if (!staged) smem = 0;
     static bool attr_set = false;
     if (!attr_set) {
         GSB_CUDA_TRY(cudaFuncSetAttribute(k6_hamming_matrix<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -73,7 +71,7 @@ static int launch_hamming(const uint8_t *q, uint32_t nq, const uint8_t *c, uint3
     uint32_t per = 8;
     while ((uint64_t)nq * ((n + per - 1) / per) > 148ull * 16 && per < 4096) per *= 2;
     dim3 grid((n + per - 1) / per, nq);
-    k6_hamming_matrix<ELEM, F32><<<grid, kHamThreads, smem, st>>>(q, nq, c, n, S, per, out);
+    k6_hamming_matrix<ELEM, F32><<<grid, kHamThreads, smem, st>>>(q, nq, c, n, S, per, out, staged);
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;
 }

@@ -388,12 +388,10 @@ extern "C" int gsb_index_load_graph(gsb_index *idx, const void *sigs, const uint
 template <int ELEM, bool F32>
 static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef, cudaStream_t st) {
     const size_t row = (size_t)idx->p.sketch_size * ELEM;
-    const size_t row128 = (row + 127) & ~(size_t)127;
     const size_t ret_bytes = ((size_t)ef + 2) * sizeof(HItem);
-    if (row128 > kSmemMax) {
-        set_error("signature row of %zu bytes does not fit in shared memory", row);
-        return GSB_ERR_UNSUPPORTED;
-    }
+    // a row that does not fit in shared memory stays in global memory (S up to 65535 is legal)
+    const int staged = ((row + 127) & ~(size_t)127) <= kSmemMax ? 1 : 0;
+    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
     const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
     size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
     // visited bitmap in shared memory when it fits beside the row and the result heap
@@ -412,7 +410,7 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
     so.counts = idx->d_counts.as<uint32_t>();
     so.nb_eval = idx->d_neval.as<unsigned long long>();
     k7_hnsw_search<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(
-        graph_view(idx), idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, bm_words,
+        graph_view(idx), idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, bm_words, staged,
         idx->d_ws.as<uint8_t>(), idx->wl, so, idx->d_counter.as<uint32_t>());
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;
@@ -486,12 +484,9 @@ template <int ELEM, bool F32>
 int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     const uint32_t ef_c = idx->p.ef_construction;
     const size_t row = (size_t)idx->p.sketch_size * ELEM;
-    const size_t row128 = (row + 127) & ~(size_t)127;
     const size_t ret_bytes = ((size_t)ef_c + 2) * sizeof(HItem);
-    if (row128 > kSmemMax) {
-        set_error("signature row of %zu bytes does not fit in shared memory", row);
-        return GSB_ERR_UNSUPPORTED;
-    }
+    const int staged = ((row + 127) & ~(size_t)127) <= kSmemMax ? 1 : 0;
+    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
     const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
     size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
     const size_t bm_bytes = (((size_t)first + W + 31) / 32) * 4;
@@ -519,7 +514,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
     GraphView g = graph_view(idx);
     g.n = first + W;
-    k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem, bm_words,
+    k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem, bm_words, staged,
                                                                          idx->d_ws.as<uint8_t>(), idx->wl);
     k9_write_own_lists<<<W, 256, 0, st>>>(g, wv);
     k9_reverse_updates<<<W, 256, 0, st>>>(g, wv);

@@ -180,7 +180,7 @@ __device__ __forceinline__ uint32_t warp_row_count(const uint8_t *smem_q, const 
 template <int ELEM, bool IS_F32>
 __global__ void __launch_bounds__(kHamThreads)
 k6_hamming_matrix(const uint8_t *__restrict__ queries, uint32_t nq, const uint8_t *__restrict__ cands,
-                  uint32_t n, uint32_t S, uint32_t cands_per_cta, float *__restrict__ out) {
+                  uint32_t n, uint32_t S, uint32_t cands_per_cta, float *__restrict__ out, int staged) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const uint32_t qi = blockIdx.y;
@@ -192,7 +192,10 @@ k6_hamming_matrix(const uint8_t *__restrict__ queries, uint32_t nq, const uint8_
     }
     __syncthreads();
     const uint8_t *gq = queries + (size_t)qi * row;
-    if ((row & 15) == 0 && (((uintptr_t)gq) & 15) == 0) {
+    const uint8_t *qrow = smem;  // where the query row is read from
+    if (!staged) {
+        qrow = gq;  // the row does not fit in shared memory (S up to 65535 is legal): read it through L1/L2
+    } else if ((row & 15) == 0 && (((uintptr_t)gq) & 15) == 0) {
         stage_query(smem, gq, (uint32_t)row, &bar, 0);
     } else {
         for (uint32_t i = threadIdx.x; i < row; i += blockDim.x) smem[i] = gq[i];
@@ -206,16 +209,16 @@ k6_hamming_matrix(const uint8_t *__restrict__ queries, uint32_t nq, const uint8_
     for (uint32_t c = c0 + warp; c < c1; c += nwarps) {
         const uint8_t *cr = cands + (size_t)c * row;
         uint32_t cnt;
-        if ((((uintptr_t)cr) & 15) == 0) {
-            cnt = warp_row_count<ELEM, IS_F32>(smem, cr, S);
+        if (((((uintptr_t)cr) | ((uintptr_t)qrow)) & 15) == 0) {
+            cnt = warp_row_count<ELEM, IS_F32>(qrow, cr, S);
         } else {  // unaligned rows (row size not a multiple of 16): element-wise
             cnt = 0;
             for (uint32_t e = lane_id(); e < S; e += 32) {
-                if (ELEM == 8) cnt += ((const uint64_t *)smem)[e] != ((const uint64_t *)cr)[e];
+                if (ELEM == 8) cnt += ((const uint64_t *)qrow)[e] != ((const uint64_t *)cr)[e];
                 else if (ELEM == 4) {
-                    if (IS_F32) cnt += ((const float *)smem)[e] != ((const float *)cr)[e];
-                    else cnt += ((const uint32_t *)smem)[e] != ((const uint32_t *)cr)[e];
-                } else cnt += ((const uint16_t *)smem)[e] != ((const uint16_t *)cr)[e];
+                    if (IS_F32) cnt += ((const float *)qrow)[e] != ((const float *)cr)[e];
+                    else cnt += ((const uint32_t *)qrow)[e] != ((const uint32_t *)cr)[e];
+                } else cnt += ((const uint16_t *)qrow)[e] != ((const uint16_t *)cr)[e];
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);

@@ -284,10 +284,16 @@ __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView
     if (threadIdx.x < nE) D[threadIdx.x] = __fdiv_rn((float)acc[threadIdx.x], fS);
 }
 
-// stage one signature row in shared memory (TMA bulk copy when alignment allows); all threads
-// must have finished reading the previous content (caller synchronises before)
-__device__ __forceinline__ void stage_row(uint8_t *smem, const uint8_t *grow, size_t row, uint64_t *bar,
-                                          uint32_t &phase) {
+// stage one signature row in shared memory (TMA bulk copy when alignment allows) and return where
+// the row now is; all threads must have finished reading the previous content (caller
+// synchronises before).  A row that does not fit in shared memory (S up to 65535 is legal) stays
+// in global memory: the compare loop reads it through L1/L2 instead.
+__device__ __forceinline__ const uint8_t *stage_row(uint8_t *smem, const uint8_t *grow, size_t row, uint64_t *bar,
+                                                    uint32_t &phase, int staged) {
+    if (!staged) {
+        __syncthreads();
+        return grow;
+    }
     if ((row & 15) == 0 && (((uintptr_t)grow) & 15) == 0) {
         fence_proxy_async();
         stage_query(smem, grow, (uint32_t)row, bar, phase);
@@ -296,6 +302,7 @@ __device__ __forceinline__ void stage_row(uint8_t *smem, const uint8_t *grow, si
         for (uint32_t i = threadIdx.x; i < row; i += blockDim.x) smem[i] = grow[i];
     }
     __syncthreads();
+    return smem;
 }
 
 // hnsw_rs search_layer: best-first search on one layer from `ep` (distance d_ep known), result in
@@ -386,15 +393,15 @@ struct WsLayout {
 template <int ELEM, bool F32>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, uint32_t knbn, uint32_t ef,
-               int ret_in_smem, uint32_t bm_words, uint8_t *__restrict__ ws, WsLayout wl, SearchOut so,
-               uint32_t *__restrict__ qcounter) {
+               int ret_in_smem, uint32_t bm_words, int staged, uint8_t *__restrict__ ws, WsLayout wl,
+               SearchOut so, uint32_t *__restrict__ qcounter) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ HnswShared sh;
     __shared__ __align__(8) HItem cand_sm[kCandSmem];
     __shared__ uint32_t s_q;
     const size_t row = (size_t)g.S * ELEM;
-    const size_t row128 = (row + 127) & ~(size_t)127;
+    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
     uint8_t *my = ws + (size_t)blockIdx.x * wl.stride;
     uint32_t *stamps = reinterpret_cast<uint32_t *>(my + wl.off_stamp);
     if (threadIdx.x == 0) {
@@ -418,12 +425,12 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
         __syncthreads();
         const uint32_t q = s_q;
         if (q >= nq) break;
-        stage_row(smem, queries + (size_t)q * row, row, &bar, phase);
+        const uint8_t *cur = stage_row(smem, queries + (size_t)q * row, row, &bar, phase, staged);
         unsigned long long neval = 0;
         uint32_t pivot = g.entry;
         if (threadIdx.x == 0) sh.E[0] = pivot;
         __syncthreads();
-        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D, sh.acc);
+        eval_list<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc);
         __syncthreads();
         float dist_to_entry = sh.D[0];
         neval += 1;
@@ -435,7 +442,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldg(&lst[i]);
             __syncthreads();
-            eval_list<ELEM, F32>(smem, g, sh.E, len, sh.D, sh.acc);
+            eval_list<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc);
             __syncthreads();
             neval += len;
             // every thread scans the same shared arrays: uniform result, no broadcast needed
@@ -449,7 +456,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             pivot = newp;
         }
         // ---- search_layer(q, pivot, ef, 0)
-        search_layer_dev<ELEM, F32>(g, smem, pivot, dist_to_entry, ef, 0, sh, vis, neval);
+        search_layer_dev<ELEM, F32>(g, cur, pivot, dist_to_entry, ef, 0, sh, vis, neval);
         if (threadIdx.x == 0) {
             sh.ret.into_sorted();
             uint32_t last = knbn < ef ? knbn : ef;
@@ -491,8 +498,8 @@ __device__ __forceinline__ size_t sel_off(uint32_t M, uint32_t t, uint32_t l) {
 // of the wave merged in, select_neighbours (Malkov heuristic, extension on layer 0), sort.
 template <int ELEM, bool F32>
 __global__ void __launch_bounds__(kInsertThreads, 1)
-k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_words, uint8_t *__restrict__ ws,
-                      WsLayout wl) {
+k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_words, int staged,
+                      uint8_t *__restrict__ ws, WsLayout wl) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ HnswShared sh;
@@ -502,7 +509,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
     __shared__ uint32_t outP[kMaxList];
     __shared__ float outD[kMaxList];
     const size_t row = (size_t)g.S * ELEM;
-    const size_t row128 = (row + 127) & ~(size_t)127;
+    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
     const float fS = (float)g.S;
     uint8_t *my = ws + (size_t)blockIdx.x * wl.stride;
     uint32_t *stamps = reinterpret_cast<uint32_t *>(my + wl.off_stamp);
@@ -536,17 +543,17 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
         const uint32_t level = g.levels[np];
         const uint8_t *qrow = g.sigs + (size_t)np * row;
         if (threadIdx.x < kMaxLayers) wv.sel_n[(size_t)t * kMaxLayers + threadIdx.x] = 0;
-        stage_row(smem, qrow, row, &bar, phase);
+        const uint8_t *cur = stage_row(smem, qrow, row, &bar, phase, staged);
         uint32_t ep = wv.entry;
         const uint32_t lmax = g.levels[wv.entry];
         if (threadIdx.x == 0) sh.E[0] = ep;
         __syncthreads();
-        eval_list<ELEM, F32>(smem, g, sh.E, 1, sh.D, sh.acc);
+        eval_list<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc);
         __syncthreads();
         float d_ep = sh.D[0];
         // ---- greedy descent through the layers above the point's level: search_layer(ef = 1)
         for (int l = (int)lmax; l >= (int)level + 1; l--) {
-            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, 1, (uint32_t)l, sh, vis, neval);
+            search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, 1, (uint32_t)l, sh, vis, neval);
             if (threadIdx.x == 0) {
                 s_ep = ep;
                 s_dep = d_ep;
@@ -564,7 +571,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
         }
         const int top = (int)(level < lmax ? level : lmax);
         for (int l = top; l >= 0; l--) {
-            search_layer_dev<ELEM, F32>(g, smem, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval);
+            search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval);
             // ---- earlier points of this wave, in order, as if search_layer had met them last
             {
                 const uint32_t m = wv.first + threadIdx.x;
@@ -579,7 +586,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                 }
                 if (on) sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = m;
                 __syncthreads();
-                eval_list<ELEM, F32>(smem, g, sh.E, tot, sh.D, sh.acc);
+                eval_list<ELEM, F32>(cur, g, sh.E, tot, sh.D, sh.acc);
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     for (uint32_t i = 0; i < tot; i++) {
@@ -639,7 +646,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                     __syncthreads();
                     for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) sh.E[i] = newc[c0 + i];
                     __syncthreads();
-                    eval_list<ELEM, F32>(smem, g, sh.E, nc, sh.D, sh.acc);
+                    eval_list<ELEM, F32>(cur, g, sh.E, nc, sh.D, sh.acc);
                     __syncthreads();
                     if (threadIdx.x == 0)
                         for (uint32_t i = 0; i < nc; i++) sh.cand.push(-sh.D[i], sh.E[i]);
@@ -666,12 +673,12 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                     if (sh.done) break;
                     const uint32_t nout = s_nout;
                     if (nout > 0) {
-                        stage_row(smem, g.sigs + (size_t)sh.node * row, row, &bar, phase);
+                        cur = stage_row(smem, g.sigs + (size_t)sh.node * row, row, &bar, phase, staged);
                         const float ed = sh.fval;
                         // nearest selected points first (they reject most often), 64 rows at a time
                         for (uint32_t c0 = 0; c0 < nout; c0 += 64) {
                             const uint32_t nc = nout - c0 < 64u ? nout - c0 : 64u;
-                            eval_list<ELEM, F32>(smem, g, outP + c0, nc, sh.D, sh.acc);
+                            eval_list<ELEM, F32>(cur, g, outP + c0, nc, sh.D, sh.acc);
                             __syncthreads();
                             const int hit = threadIdx.x < nc && sh.D[threadIdx.x] <= ed;
                             if (__syncthreads_or(hit)) {
@@ -731,7 +738,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
             __syncthreads();
             ep = s_ep;
             d_ep = s_dep;
-            if (l > 0 && s_mode != 0) stage_row(smem, qrow, row, &bar, phase);  // the heuristic replaced q
+            if (l > 0 && s_mode != 0) cur = stage_row(smem, qrow, row, &bar, phase, staged);  // the heuristic replaced q
         }
     }
     if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = vis.stamp;

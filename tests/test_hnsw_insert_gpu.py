@@ -106,3 +106,20 @@ def test_dump_and_reload_round_trip(oracle, tmp_path):
     assert idx2.get_nb_point() == 405
     with pytest.raises(g.GsbError):
         g.Hnsw(g.HnswParams(max_nb_conn=9, ef=32), 256, np.uint32).load(tmp_path, "hnswdump")
+
+
+def test_rows_larger_than_shared_memory(oracle):
+    """S = 65535 is legal (README.md:676); a u64 row is then 524 KB and cannot be staged in shared
+    memory: distance, construction and search must still equal the oracle"""
+    rng = np.random.default_rng(13)
+    S, n = 65535, 80
+    sigs = tree_sigs(rng, n, S, np.uint64, keep=0.9)
+    d = g.DistHamming().matrix(sigs[:5], sigs)
+    assert d.tobytes() == oracle.hamming_matrix(sigs[:5], sigs).tobytes()
+    h, idx = both(oracle, sigs, 6, 24, 16)
+    assert_same_graph(idx.export_graph(), h.export())
+    got, gc, ge = idx.search_raw(sigs[::9], 4, 30)
+    want, wc, we = h.search(sigs[::9], 4, 30)
+    assert gc.tolist() == wc.tolist() and ge.tolist() == we.tolist()
+    assert got["d_id"].tolist() == want["d_id"].tolist()
+    assert got["distance"].tobytes() == want["distance"].tobytes()
