@@ -674,11 +674,14 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                     const uint32_t nout = s_nout;
                     if (nout > 0) {
                         cur = stage_row(smem, g.sigs + (size_t)sh.node * row, row, &bar, phase, staged);
+                        const uint8_t *erow = cur;
                         const float ed = sh.fval;
-                        // nearest selected points first (they reject most often), 64 rows at a time
-                        for (uint32_t c0 = 0; c0 < nout; c0 += 64) {
-                            const uint32_t nc = nout - c0 < 64u ? nout - c0 : 64u;
-                            eval_list<ELEM, F32>(cur, g, outP + c0, nc, sh.D, sh.acc);
+                        // nearest selected points first (they reject most often), in growing chunks
+                        // so that an early rejection costs a few rows, not sixty-four
+                        uint32_t step = 4;
+                        for (uint32_t c0 = 0; c0 < nout; c0 += step, step = step < 64u ? step * 2 : 64u) {
+                            const uint32_t nc = nout - c0 < step ? nout - c0 : step;
+                            eval_list<ELEM, F32>(erow, g, outP + c0, nc, sh.D, sh.acc);
                             __syncthreads();
                             const int hit = threadIdx.x < nc && sh.D[threadIdx.x] <= ed;
                             if (__syncthreads_or(hit)) {
@@ -696,6 +699,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                 }
             }
             __syncthreads();
+            if (l > 0 && s_mode != 0) cur = stage_row(smem, qrow, row, &bar, phase, staged);  // the heuristic replaced q
             // ---- sort by (distance, index) and publish; next entry = nearest selected point
             // that is not of this wave
             const uint32_t nout = s_nout;
@@ -738,7 +742,6 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
             __syncthreads();
             ep = s_ep;
             d_ep = s_dep;
-            if (l > 0 && s_mode != 0) cur = stage_row(smem, qrow, row, &bar, phase, staged);  // the heuristic replaced q
         }
     }
     if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = vis.stamp;
