@@ -3,6 +3,7 @@
 // draws the levels (hnsw_rs LayerGenerator, restated in oracle/hnsw.c) and launches kernels.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -396,7 +397,7 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
     size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
     // visited bitmap in shared memory when it fits beside the row and the result heap
     const size_t bm_bytes = ((idx->n + 31) / 32) * 4;
-    const uint32_t bm_words = smem + bm_bytes <= kSmemMax ? (uint32_t)(bm_bytes / 4) : 0u;
+    const uint32_t bm_words = (smem + bm_bytes <= kSmemMax && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
     smem += (size_t)bm_words * 4;
     GSB_CUDA_TRY(cudaFuncSetAttribute(k7_hnsw_search<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemMax));
@@ -490,7 +491,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
     size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
     const size_t bm_bytes = (((size_t)first + W + 31) / 32) * 4;
-    const uint32_t bm_words = smem + bm_bytes <= kSmemMax ? (uint32_t)(bm_bytes / 4) : 0u;
+    const uint32_t bm_words = (smem + bm_bytes <= kSmemMax && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
     smem += (size_t)bm_words * 4;
     static bool attr = false;
     if (!attr) {

@@ -123,3 +123,17 @@ def test_rows_larger_than_shared_memory(oracle):
     assert gc.tolist() == wc.tolist() and ge.tolist() == we.tolist()
     assert got["d_id"].tolist() == want["d_id"].tolist()
     assert got["distance"].tobytes() == want["distance"].tobytes()
+
+
+def test_visit_stamps_fallback(oracle, monkeypatch):
+    """indexes too large for the shared-memory visited bitmap use visit stamps in global memory;
+    GSB_NO_BITMAP forces that path at test size"""
+    monkeypatch.setenv("GSB_NO_BITMAP", "1")
+    rng = np.random.default_rng(17)
+    sigs = tree_sigs(rng, 500, 320, np.uint64)
+    h, idx = both(oracle, sigs, 10, 40, 64)
+    assert_same_graph(idx.export_graph(), h.export())
+    got, gc, ge = idx.search_raw(sigs[::23], 5, 60)
+    want, wc, we = h.search(sigs[::23], 5, 60)
+    assert gc.tolist() == wc.tolist() and ge.tolist() == we.tolist()
+    assert got["d_id"].tolist() == want["d_id"].tolist()
