@@ -143,7 +143,10 @@ def sketch_directory(g, directory, p, pio, device=0, nbthreads=0):
         chunk = files[b:b + batch]
         sig, nb = sk.sketch_files(read_all(chunk, nbthreads or (os.cpu_count() or 1)))
         sigs.append(sig)
-        items += [(f, "", int(n)) for f, n in zip(chunk, nb)]
+        # ItemDict ids: seq mode keeps an empty fasta_id (src/dna/dnafiles.rs:86-93), block mode the
+        # literal "-total-sequence" (src/dna/dnafiles.rs:268-272)
+        fid = "-total-sequence" if p["block"] else ""
+        items += [(f, fid, int(n)) for f, n in zip(chunk, nb)]
     return np.concatenate(sigs), items, sk.dtype
 
 
