@@ -896,7 +896,8 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
     h->h2d_end.clear();
     {
         const uint64_t kChunkBytes = 48ull << 20;
-        const uint32_t kChunkFiles = 8;
+        // one chunk per genome group on the prob path: a group starts as soon as its own files are in
+        const uint32_t kChunkFiles = h->p.algo == GSB_ALGO_PROB3A ? (uint32_t)prob_slots() : 8u;
         uint32_t b = 0;
         for (uint32_t i = 1; i <= n; i++)
             if (i == n || i - b >= kChunkFiles || offsets[i + 1] - offsets[b] > kChunkBytes) {
