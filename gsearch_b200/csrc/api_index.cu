@@ -250,7 +250,7 @@ GraphView graph_view(const gsb_index *idx) {
     return g;
 }
 
-constexpr size_t kSmemMax = 194 * 1024;  // dynamic; the kernels add up to 31 KB of static shared memory
+constexpr size_t kSmemMax = 192 * 1024;  // dynamic; the kernels add up to 33 KB of static shared memory
 
 // per-CTA workspace for `nctas` CTAs over `npts` points with a result heap of `ef`; grown
 // geometrically (and zeroed: the visit stamps live there) so that a growing index does not

@@ -164,6 +164,12 @@ __device__ __forceinline__ const uint32_t *list_of(const GraphView &g, uint32_t 
     return g.nbrU + (size_t)li * g.M;
 }
 
+// the distances stored beside a neighbour list (same indexing as list_of)
+__device__ __forceinline__ const float *dist_of(const GraphView &g, uint32_t p, uint32_t layer) {
+    if (layer == 0) return g.dist0 + (size_t)p * 2 * g.M;
+    return g.distU + (size_t)(g.upper_off[p] + layer - 1) * g.M;
+}
+
 // warp 0: pull the list of the candidate that will most likely be popped next into L1
 __device__ __forceinline__ void prefetch_list(const GraphView &g, uint32_t p, uint32_t layer) {
     const uint32_t *base;
@@ -508,6 +514,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
     __shared__ float s_dep;
     __shared__ uint32_t outP[kMaxList];
     __shared__ float outD[kMaxList];
+    __shared__ float aD[kMaxList];  // selection: own distances of the candidates of the current chunk
     const size_t row = (size_t)g.S * ELEM;
     const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
     const float fS = (float)g.S;
@@ -654,47 +661,83 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                 __syncthreads();
             }
             if (s_mode != 0) {
-                // Malkov heuristic: a candidate is kept unless an already selected point is
-                // at least as close to it as the new point is
+                // Malkov heuristic: candidates leave the heap nearest first; one is kept unless an
+                // already selected point is at least as close to it as the new point is.  The pop
+                // order does not depend on the decisions, so candidates are taken in chunks: the
+                // chunk is tested against each selected point in turn (that point's row staged in
+                // shared memory, the surviving candidates streamed against it like a search
+                // expansion), then scanned in order -- the first survivor is selected and the
+                // survivors after it are tested against it.  Same decisions as the one-by-one
+                // loop of the reference, but whole batches of rows per staged row.
                 for (;;) {
                     __syncthreads();
                     if (threadIdx.x == 0) {
-                        sh.done = 0;
-                        if (sh.cand.n == 0 || s_nout >= nb_asked) {
-                            sh.done = 1;
-                        } else {
-                            const HItem e = sh.cand.pop();
-                            sh.node = e.p;
-                            sh.fval = -e.d;
-                        }
-                        sh.flag = 0;
+                        uint32_t nc = 0;
+                        if (s_nout < nb_asked)
+                            while (sh.cand.n > 0 && nc < (uint32_t)kMaxList) {
+                                const HItem e = sh.cand.pop();
+                                sh.E[nc] = e.p;
+                                aD[nc] = -e.d;
+                                nc++;
+                            }
+                        sh.work = nc;        // alive candidates, in pop order
+                        sh.next = s_nout;    // selected points this chunk has not been tested against yet: [0, next)
+                        sh.flag = 0;         // index of the first selected point still to test
                     }
                     __syncthreads();
-                    if (sh.done) break;
-                    const uint32_t nout = s_nout;
-                    if (nout > 0) {
-                        cur = stage_row(smem, g.sigs + (size_t)sh.node * row, row, &bar, phase, staged);
-                        const uint8_t *erow = cur;
-                        const float ed = sh.fval;
-                        // nearest selected points first (they reject most often), in growing chunks
-                        // so that an early rejection costs a few rows, not sixty-four
-                        uint32_t step = 4;
-                        for (uint32_t c0 = 0; c0 < nout; c0 += step, step = step < 64u ? step * 2 : 64u) {
-                            const uint32_t nc = nout - c0 < step ? nout - c0 : step;
-                            eval_list<ELEM, F32>(erow, g, outP + c0, nc, sh.D, sh.acc);
-                            __syncthreads();
-                            const int hit = threadIdx.x < nc && sh.D[threadIdx.x] <= ed;
-                            if (__syncthreads_or(hit)) {
-                                if (threadIdx.x == 0) sh.flag = 1;
-                                break;
+                    if (sh.work == 0) break;
+                    for (;;) {  // rounds: one staged selected row each
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            sh.done = 0;
+                            if (sh.work == 0) {
+                                sh.done = 1;
+                            } else if (sh.flag >= s_nout) {
+                                // tested against everything selected so far: the first survivor is selected
+                                if (sh.work == 0 || s_nout >= nb_asked) {
+                                    sh.done = 1;
+                                } else {
+                                    outP[s_nout] = sh.E[0];
+                                    outD[s_nout] = aD[0];
+                                    s_nout++;
+                                    sh.done = (sh.work == 1 || s_nout >= nb_asked) ? 1u : 2u;  // 2: drop entry 0, test the rest
+                                }
                             }
                         }
                         __syncthreads();
-                    }
-                    if (threadIdx.x == 0 && !sh.flag) {
-                        outP[s_nout] = sh.node;
-                        outD[s_nout] = sh.fval;
-                        s_nout++;
+                        if (sh.done == 1) break;
+                        const uint32_t drop = sh.done == 2 ? 1u : 0u;     // entry 0 was just selected
+                        const uint32_t nal = sh.work - drop;
+                        const uint32_t si = sh.flag;                      // selected point to test against
+                        cur = stage_row(smem, g.sigs + (size_t)outP[si] * row, row, &bar, phase, staged);
+                        eval_list<ELEM, F32>(cur, g, sh.E + drop, nal, sh.D, sh.acc);
+                        __syncthreads();
+                        // ordered compaction of the survivors (distance to the selected point > own distance)
+                        uint32_t e = 0;
+                        float ed = 0.f;
+                        bool keep = false;
+                        if (threadIdx.x < nal) {
+                            e = sh.E[drop + threadIdx.x];
+                            ed = aD[drop + threadIdx.x];
+                            keep = !(sh.D[threadIdx.x] <= ed);
+                        }
+                        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                        if (lane_id() == 0) sh.wcnt[warp] = __popc(bal);
+                        __syncthreads();
+                        uint32_t pre = 0, tot = 0;
+                        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
+                            if (w < warp) pre += sh.wcnt[w];
+                            tot += sh.wcnt[w];
+                        }
+                        if (keep) {
+                            const uint32_t at = pre + __popc(bal & ((1u << lane_id()) - 1));
+                            sh.E[at] = e;
+                            aD[at] = ed;
+                        }
+                        if (threadIdx.x == 0) {
+                            sh.work = tot;
+                            sh.flag = si + 1;
+                        }
                     }
                 }
             }
