@@ -28,7 +28,7 @@
 
 namespace gsb {
 
-constexpr int kSearchThreads = 512;   // K7: 16 warps (768 measured 6 % slower: the chain of expansions, not occupancy, limits it)
+constexpr int kSearchThreads = 256;   // K7: 8 warps per CTA, three CTAs per SM (three independent search chains)
 constexpr int kInsertThreads = 512;   // K8: 16 warps (the selection code needs more registers)
 constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255) and >= wave size
 constexpr int kMaxLayers = 17;   // levels 0..16
@@ -341,8 +341,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
         pop_next();
     }
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t cap = layer == 0 ? 2 * g.M : g.M;           // list capacity: entries beyond the
-    const uint32_t scan_warps = (cap + 31) >> 5;               // count are stale but readable
+    const uint32_t cap = layer == 0 ? 2 * g.M : g.M;  // list capacity: entries beyond the count are stale but readable
     for (;;) {
         __syncthreads();
         if (sh.done) break;
@@ -351,20 +350,26 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
         // entries are loaded together (one L2 round trip instead of two dependent ones)
         uint32_t len;
         const uint32_t *lst = list_of(g, sh.node, layer, len);
-        uint32_t nb = threadIdx.x < cap ? __ldg(&lst[threadIdx.x]) : 0u;
-        const bool unv = threadIdx.x < len && !vis.seen(nb);
-        const uint32_t bal = __ballot_sync(0xffffffffu, unv);
-        if (lane == 0) sh.wcnt[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t pre = 0, tot = 0;
-        for (uint32_t w = 0; w < scan_warps; w++) {
-            const uint32_t c = sh.wcnt[w];
-            if (w < warp) pre += c;
-            tot += c;
-        }
-        if (unv) {
-            sh.E[pre + __popc(bal & ((1u << lane) - 1))] = nb;
-            vis.mark(nb);
+        uint32_t tot = 0;
+        for (uint32_t base = 0; base < cap; base += blockDim.x) {  // one pass unless the CTA is narrower than the list
+            const uint32_t i = base + threadIdx.x;
+            const uint32_t nb = i < cap ? __ldg(&lst[i]) : 0u;
+            const bool unv = i < len && !vis.seen(nb);
+            const uint32_t bal = __ballot_sync(0xffffffffu, unv);
+            if (lane == 0) sh.wcnt[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t pre = tot;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
+                const uint32_t c = sh.wcnt[w];
+                if (w < warp) pre += c;
+                tot += c;
+            }
+            if (unv) {
+                sh.E[pre + __popc(bal & ((1u << lane) - 1))] = nb;
+                vis.mark(nb);
+            }
+            __syncthreads();
+            if (base + blockDim.x >= len) break;  // nothing valid beyond the count
         }
         __syncthreads();
         eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
@@ -397,7 +402,7 @@ struct WsLayout {
 
 // smem: [row: row bytes rounded to 128][ret heap: (ef+2) items if ret_in_smem]
 template <int ELEM, bool F32>
-__global__ void __launch_bounds__(kSearchThreads, 1)
+__global__ void __launch_bounds__(kSearchThreads, 3)
 k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, uint32_t knbn, uint32_t ef,
                int ret_in_smem, uint32_t bm_words, int staged, uint8_t *__restrict__ ws, WsLayout wl,
                SearchOut so, uint32_t *__restrict__ qcounter) {
