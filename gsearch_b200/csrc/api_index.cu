@@ -162,7 +162,7 @@ extern "C" int gsb_index_create(const gsb_index_params *params, int device, gsb_
                        log((double)params->max_nb_connection);
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&idx->nsm, cudaDevAttrMultiProcessorCount, device);
-    idx->wave_max = (uint32_t)idx->nsm;
+    idx->wave_max = (uint32_t)idx->nsm * 2;  // one wave = one point per resident insertion CTA
     if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete idx;
@@ -490,7 +490,8 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     const uint32_t ef_c = idx->p.ef_construction;
     const size_t row = (size_t)idx->p.sketch_size * ELEM;
     const size_t ret_bytes = ((size_t)ef_c + 2) * sizeof(HItem);
-    const int staged = ((row + 127) & ~(size_t)127) <= kSmemMax ? 1 : 0;
+    // as for the search: rows are read through L1/L2, two CTAs (two insertion chains) per SM
+    const int staged = (((row + 127) & ~(size_t)127) <= kSmemMax && getenv("GSB_K8_STAGED")) ? 1 : 0;
     const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
     const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
     size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
@@ -503,7 +504,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         attr = true;
     }
-    const uint32_t nctas = std::min<uint32_t>(W, (uint32_t)idx->nsm);
+    const uint32_t nctas = std::min<uint32_t>(W, (uint32_t)idx->nsm * (staged ? 1u : 2u));
     int rc;
     if ((rc = ensure_workspace(idx, nctas, (uint64_t)first + W, ef_c))) return rc;
     WaveView wv;

@@ -29,7 +29,7 @@
 namespace gsb {
 
 constexpr int kSearchThreads = 256;   // K7: 8 warps per CTA, three CTAs per SM (three independent search chains)
-constexpr int kInsertThreads = 512;   // K8: 16 warps (the selection code needs more registers)
+constexpr int kInsertThreads = 256;   // K8: 8 warps per CTA, two CTAs per SM (128 registers per thread)
 constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255) and >= wave size
 constexpr int kMaxLayers = 17;   // levels 0..16
 
@@ -508,7 +508,7 @@ __device__ __forceinline__ size_t sel_off(uint32_t M, uint32_t t, uint32_t l) {
 // Phase A.  One CTA per new point: greedy descent, search_layer(ef_c) per layer, earlier points
 // of the wave merged in, select_neighbours (Malkov heuristic, extension on layer 0), sort.
 template <int ELEM, bool F32>
-__global__ void __launch_bounds__(kInsertThreads, 1)
+__global__ void __launch_bounds__(kInsertThreads, 2)
 k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_words, int staged,
                       uint8_t *__restrict__ ws, WsLayout wl) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -586,18 +586,22 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
             search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval);
             // ---- earlier points of this wave, in order, as if search_layer had met them last
             {
-                const uint32_t m = wv.first + threadIdx.x;
-                const bool on = m < np && g.levels[m] >= (uint32_t)l;
-                const uint32_t bal = __ballot_sync(0xffffffffu, on);
-                if (lane_id() == 0) sh.wcnt[warp] = __popc(bal);
-                __syncthreads();
-                uint32_t pre = 0, tot = 0;
-                for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
-                    if (w < warp) pre += sh.wcnt[w];
-                    tot += sh.wcnt[w];
+                uint32_t tot = 0;
+                for (uint32_t base = 0; wv.first + base < np; base += blockDim.x) {
+                    const uint32_t m = wv.first + base + threadIdx.x;
+                    const bool on = m < np && g.levels[m] >= (uint32_t)l;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                    if (lane_id() == 0) sh.wcnt[warp] = __popc(bal);
+                    __syncthreads();
+                    uint32_t pre = tot;
+                    for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
+                        const uint32_t c = sh.wcnt[w];
+                        if (w < warp) pre += c;
+                        tot += c;
+                    }
+                    if (on) sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = m;
+                    __syncthreads();
                 }
-                if (on) sh.E[pre + __popc(bal & ((1u << lane_id()) - 1))] = m;
-                __syncthreads();
                 eval_list<ELEM, F32>(cur, g, sh.E, tot, sh.D, sh.acc);
                 __syncthreads();
                 if (threadIdx.x == 0) {
@@ -679,7 +683,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                     if (threadIdx.x == 0) {
                         uint32_t nc = 0;
                         if (s_nout < nb_asked)
-                            while (sh.cand.n > 0 && nc < (uint32_t)kMaxList) {
+                            while (sh.cand.n > 0 && nc < blockDim.x && nc < (uint32_t)kMaxList) {
                                 const HItem e = sh.cand.pop();
                                 sh.E[nc] = e.p;
                                 aD[nc] = -e.d;
@@ -758,9 +762,9 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
             }
             __syncthreads();
             const size_t so = sel_off(g.M, t, (uint32_t)l);
-            if (threadIdx.x < nout) {
-                const float d = outD[threadIdx.x];
-                const uint32_t p = outP[threadIdx.x];
+            for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+                const float d = outD[i];
+                const uint32_t p = outP[i];
                 uint32_t rank = 0;
                 for (uint32_t j = 0; j < nout; j++) {
                     const float dj = outD[j];
@@ -772,9 +776,9 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                 if (p < wv.first) atomicMin(&sh.work, rank);
             }
             __syncthreads();
-            if (threadIdx.x < nout) {
-                const float d = outD[threadIdx.x];
-                const uint32_t p = outP[threadIdx.x];
+            for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+                const float d = outD[i];
+                const uint32_t p = outP[i];
                 uint32_t rank = 0;
                 for (uint32_t j = 0; j < nout; j++) {
                     const float dj = outD[j];

@@ -242,7 +242,7 @@ GSB_API int gsb_index_export_graph(const gsb_index *idx, uint8_t *levels, uint32
                                    float *nbr_dist, uint64_t *entry_point);
 /* Points inserted together by gsb_index_insert_batch (the reference inserts with one rayon
  * task per point, src/dna/dnasketch.rs:435; here a wave of at most wave_max points searches
- * the graph as it was before the wave).  Default = number of SMs; 1 = sequential insertion. */
+ * the graph as it was before the wave).  Default = two per SM; 1 = sequential insertion. */
 GSB_API int gsb_index_set_wave_max(gsb_index *idx, uint32_t wave_max);
 /* file_dump(dir, basename) / HnswIo::load_hnsw: <basename>.hnsw.graph + <basename>.hnsw.data in
  * this library's own layout; hnswio byte compatibility is not claimed         */

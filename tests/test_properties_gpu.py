@@ -82,9 +82,10 @@ def test_baseline_config0_whole_pipeline_against_the_oracle(oracle):
     assert sig.dtype == np.uint32 and sig.tobytes() == want.tobytes() and nb.tolist() == wnb.tolist()
     ids = np.arange(32, dtype=np.uint64)
     idx = g.Hnsw(g.HnswParams(max_nb_conn=128, ef=1600), 2048, np.uint32)
+    idx.set_wave_max(296)                                # the library's default on a B200: two points per SM
     idx.parallel_insert(sig, ids)
     h = oracle.Hnsw(128, 1600, 2048, np.uint32)
-    h.insert_waves(want, ids, 148)                       # the library's default wave = one point per SM
+    h.insert_waves(want, ids, 296)
     ga, gb = idx.export_graph(), h.export()
     assert ga["entry_point"] == gb["entry_point"]
     for k in ("levels", "ranks", "nbr_offsets", "nbr_index"):
