@@ -7,9 +7,14 @@ one batch of `--batch` distinct genomes per GPU; the batch (~0.5 GB of FASTA) is
 L2, so nothing is served from cache between steps.  `value` is measured with the batch
 resident in HBM (CUDA events, max over ranks); `e2e` goes through the public host-pointer C-ABI
 call with the FASTA in pinned host memory (H2D + kernels + D2H of the signatures inside the
-timed region).  With N > 1 every rank sketches its own genomes (weak scaling) and the finished
-signatures are all-gathered over NCCL inside the timed region, as `tohnsw` needs them on every
-GPU before HNSW insertion.
+timed region; the H2D copy of later genome groups runs under the kernels of earlier ones).
+With N > 1 every rank sketches its own genomes (weak scaling) and the finished signatures are
+all-gathered over NCCL inside the timed region, as `tohnsw` needs them on every GPU before HNSW
+insertion.
+
+Other workloads: `--aa --algo optdens --kmer 7 --sketch 12000` (configs[3]); `--workload request`
+(configs[2]: a 50 000-signature HNSW index built on device, 1 000 queries, K7 roofline from the
+distance evaluations the kernel reports, CPU arm = oracle search on the same graph).
 
 `--impl reference` times the reference's CPU implementation of the same path: the C
 restatement under oracle/ (the Rust reference cannot be built in this image -- no cargo, crates
