@@ -6,11 +6,15 @@
 // = true, keep_pruned = false, :159-160).
 //
 // One CTA owns one query (search) or one new point (insert) at a time; persistent CTAs pull work
-// from a counter (the reference's rayon par_iter).  The query signature stays in shared memory
-// (TMA bulk copy), the result heap too, and every neighbour expansion evaluates its <= 2M
-// unvisited candidates with all warps streaming candidate signatures from HBM (K6's inner loop).
-// Heap order, visit order and tie behaviour reproduce Rust's std BinaryHeap exactly (see
-// oracle/hnsw.c), so that on the same graph the returned ids are identical to the CPU
+// from a counter (the reference's rayon par_iter).  A search is a chain of ~ef expansions with one
+// or two new rows each, i.e. serial phases (heap updates by thread 0, neighbour gathering) between
+// short streaming phases, so SEVERAL CTAs share an SM (three for search, two for insertion): their
+// chains hide each other's serial phases.  To make them fit, the query signature is NOT staged in
+// shared memory (it is read through L1/L2 beside every candidate row); the result heap, the head
+// of the candidate heap and the visited bitmap are.  Every neighbour expansion evaluates its <= 2M
+// unvisited candidates with all warps of the CTA streaming candidate signatures from HBM (K6's
+// inner loop).  Heap order, visit order and tie behaviour reproduce Rust's std BinaryHeap exactly
+// (see oracle/hnsw.c), so that on the same graph the returned ids are identical to the CPU
 // restatement.
 //
 // The graph is mutable and device resident: fixed-capacity adjacency (2M entries per point on
