@@ -213,3 +213,240 @@ def hamming(a, b):
     a = np.asarray(a)
     b = np.asarray(b)
     return np.float32(np.float32((a != b).sum()) / np.float32(len(a)))
+
+
+# --------------------------------------------------------------------------- HNSW (small cases)
+# Written from the published algorithm (Malkov & Yashunin) and the documented behaviour of Rust's
+# std::collections::BinaryHeap, not from oracle/hnsw.c: Python lists, (key, point) tuples, the wave
+# semantics of DESIGN.md section 2.  Agreement with the C oracle pins its heap operations, tie
+# handling, neighbour selection and wave bookkeeping.
+import numpy as _np
+
+
+class RustHeap:
+    """max-heap on key with std BinaryHeap's exact element movements"""
+
+    def __init__(self):
+        self.d = []
+
+    def __len__(self):
+        return len(self.d)
+
+    def _sift_up(self, start, pos):
+        e = self.d[pos]
+        while pos > start:
+            parent = (pos - 1) // 2
+            if e[0] <= self.d[parent][0]:
+                break
+            self.d[pos] = self.d[parent]
+            pos = parent
+        self.d[pos] = e
+
+    def push(self, key, p):
+        self.d.append((key, p))
+        self._sift_up(0, len(self.d) - 1)
+
+    def pop(self):
+        item = self.d.pop()
+        if self.d:
+            item, self.d[0] = self.d[0], item
+            end, pos, e = len(self.d), 0, self.d[0]
+            child = 1
+            while child <= max(end - 2, 0) and end >= 2:
+                if self.d[child][0] <= self.d[child + 1][0]:
+                    child += 1
+                self.d[pos] = self.d[child]
+                pos = child
+                child = 2 * pos + 1
+            if child == end - 1:
+                self.d[pos] = self.d[child]
+                pos = child
+            self.d[pos] = e
+            self._sift_up(0, pos)
+        return item
+
+    def peek(self):
+        return self.d[0]
+
+    def into_sorted(self):
+        d = self.d
+        end = len(d)
+        while end > 1:
+            end -= 1
+            d[0], d[end] = d[end], d[0]
+            pos, e, child = 0, d[0], 1
+            while end >= 2 and child <= end - 2:
+                if d[child][0] <= d[child + 1][0]:
+                    child += 1
+                if e[0] >= d[child][0]:
+                    break
+                d[pos] = d[child]
+                pos = child
+                child = 2 * pos + 1
+            else:
+                if child == end - 1 and e[0] < d[child][0]:
+                    d[pos] = d[child]
+                    pos = child
+            d[pos] = e
+        return d
+
+
+class PyHnsw:
+    def __init__(self, M, ef_c, max_layer=16, scale=1.0, extend=True, seed=0x5EED):
+        self.M, self.ef_c, self.max_layer, self.extend = M, ef_c, max_layer, extend
+        self.scale = scale / math.log(M)
+        self.rng = Xoshiro(seed)
+        self.pts, self.ids, self.level, self.rank, self.nbrs = [], [], [], [], []
+        self.layer_count = [0] * 32
+        self.entry = -1
+
+    def dist(self, a, b):
+        return _np.float32(int((_np.asarray(a) != _np.asarray(b)).sum())) / _np.float32(len(a))
+
+    def gen_level(self):
+        lv = -math.log(self.rng.f64()) * self.scale
+        if not lv < self.max_layer:
+            return self.rng.usize(self.max_layer)
+        return int(math.floor(lv))
+
+    def search_layer(self, q, ep, ef, layer):
+        visited = {ep}
+        d0 = self.dist(q, self.pts[ep])
+        cand, ret = RustHeap(), RustHeap()
+        cand.push(-d0, ep)
+        ret.push(d0, ep)
+        while len(cand):
+            c = cand.pop()
+            if -c[0] > ret.peek()[0]:
+                break
+            for e, _ in self.nbrs[c[1]][layer]:
+                if e in visited:
+                    continue
+                visited.add(e)
+                ed = self.dist(q, self.pts[e])
+                if ed < ret.peek()[0] or len(ret) < ef:
+                    cand.push(-ed, e)
+                    ret.push(ed, e)
+                    if len(ret) > ef:
+                        ret.pop()
+        return ret
+
+    def select(self, q, cand, nb_asked, extend_asked, layer):
+        out = []
+        extend = False
+        if len(cand) <= nb_asked:
+            if not extend_asked:
+                while len(cand):
+                    k, p = cand.pop()
+                    out.append((p, -k))
+                return out
+            extend = True
+        if extend:
+            seen = {p for _, p in cand.d}
+            new = []
+            for _, p in list(cand.d):
+                for e, _ in self.nbrs[p][layer]:
+                    if e not in seen:
+                        seen.add(e)
+                        new.append(e)
+            for e in new:
+                cand.push(-self.dist(q, self.pts[e]), e)
+        while len(cand) and len(out) < nb_asked:
+            k, p = cand.pop()
+            ed = -k
+            if all(not (self.dist(self.pts[p], self.pts[s]) <= ed) for s, _ in out):
+                out.append((p, ed))
+        return out
+
+    def insert_waves(self, sigs, ids, wave_max):
+        i, n = 0, len(sigs)
+        while i < n:
+            if self.entry < 0:
+                self._add(sigs[i], ids[i])
+                self.entry = 0
+                i += 1
+                continue
+            W = min(max(len(self.pts) // 4, 1), wave_max, n - i)
+            first = len(self.pts)
+            for t in range(W):
+                self._add(sigs[i + t], ids[i + t])
+            entry = self.entry
+            sels = [self._phase_a(first + t, first, entry) for t in range(W)]
+            for t in range(W):
+                for l, sel in sels[t].items():
+                    self.nbrs[first + t][l] = list(sel)
+            for t in range(W):
+                np_ = first + t
+                for l in sorted(sels[t], reverse=True):
+                    for qp, d in sels[t][l]:
+                        if qp == np_ or l > self.level[qp]:
+                            continue
+                        lst = self.nbrs[qp][l]
+                        if any(x == np_ for x, _ in lst):
+                            continue
+                        lst.append((np_, d))
+                        lst.sort(key=lambda x: (x[1], x[0]))
+                        if len(lst) > (self.M if l > 0 else 2 * self.M):
+                            lst.pop()
+                if self.level[np_] > self.level[self.entry]:
+                    self.entry = np_
+            i += W
+
+    def _add(self, sig, pid):
+        lv = self.gen_level()
+        self.pts.append(_np.array(sig))
+        self.ids.append(int(pid))
+        self.level.append(lv)
+        self.rank.append(self.layer_count[lv])
+        self.layer_count[lv] += 1
+        self.nbrs.append([[] for _ in range(lv + 1)])
+
+    def _phase_a(self, np_, first, entry):
+        q, level = self.pts[np_], self.level[np_]
+        ep, lmax = entry, self.level[entry]
+        d_ep = self.dist(q, self.pts[ep])
+        for l in range(lmax, level, -1):
+            ret = self.search_layer(q, ep, 1, l)
+            if len(ret):
+                d, p = ret.pop()
+                if d < d_ep:
+                    ep, d_ep = p, d
+        sel = {}
+        for l in range(min(level, lmax), -1, -1):
+            ret = self.search_layer(q, ep, self.ef_c, l)
+            for m in range(first, np_):
+                if self.level[m] < l:
+                    continue
+                ed = self.dist(q, self.pts[m])
+                if ed < ret.peek()[0] or len(ret) < self.ef_c:
+                    ret.push(ed, m)
+                    if len(ret) > self.ef_c:
+                        ret.pop()
+            cand = RustHeap()
+            for d, p in ret.d:
+                cand.push(-d, p)
+            out = self.select(q, cand, 2 * self.M if l == 0 else self.M, l == 0 and self.extend, l)
+            out.sort(key=lambda x: (x[1], x[0]))
+            sel[l] = out
+            for p, _ in out:
+                if p < first:
+                    ep = p
+                    break
+        return sel
+
+    def search(self, q, knbn, ef_arg):
+        if self.entry < 0:
+            return []
+        pivot = self.entry
+        dte = self.dist(q, self.pts[pivot])
+        for layer in range(self.level[pivot], 0, -1):
+            newp = pivot
+            for e, _ in self.nbrs[pivot][layer]:
+                d = self.dist(q, self.pts[e])
+                if d < dte:
+                    dte, newp = d, e
+            pivot = newp
+        ef = max(ef_arg, knbn)
+        ret = self.search_layer(q, pivot, ef, 0)
+        srt = ret.into_sorted()
+        return [(self.ids[p], float(d)) for d, p in srt[:min(knbn, ef)]]

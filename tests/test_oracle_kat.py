@@ -288,3 +288,35 @@ def test_hnsw_wave_insert_keeps_recall(oracle):
             hit += sum(1 for j in range(cnt[i]) if out["distance"][i][j] <= kth)
         recalls.append(hit / (64 * k))
     assert recalls[1] >= recalls[0] - 0.02 and recalls[1] > 0.97, recalls
+
+
+@pytest.mark.parametrize("wave", [1, 7])
+def test_hnsw_oracle_equals_independent_python_restatement(oracle, wave):
+    """tests/_pyref.py restates HNSW (Rust BinaryHeap movements, search_layer, Malkov selection
+    with extension, wave insertion) from the published definitions; the C oracle must build the
+    same graph and return the same neighbours, ties included."""
+    import _pyref as P
+    rng = np.random.default_rng(5 + wave)
+    n, S, M, ef_c = 90, 24, 4, 12
+    base = rng.integers(1, 6, (n, S)).astype(np.uint32)          # tiny alphabet: distances tie massively
+    for i in range(1, n):
+        keep = rng.random(S) < 0.7
+        base[i] = np.where(keep, base[int(rng.integers(0, i))], base[i])
+    ids = np.arange(n, dtype=np.uint64) + 100
+    h = oracle.Hnsw(M, ef_c, S, np.uint32, scale=1.0)
+    h.insert_waves(base, ids, wave)
+    p = P.PyHnsw(M, ef_c)
+    p.insert_waves(list(base), list(ids), wave)
+    gr = h.export()
+    assert gr["entry_point"] == p.entry and gr["levels"].tolist() == p.level and gr["ranks"].tolist() == p.rank
+    li = 0
+    for pt in range(n):
+        for l in range(p.level[pt] + 1):
+            a, b = int(gr["nbr_offsets"][li]), int(gr["nbr_offsets"][li + 1])
+            assert gr["nbr_index"][a:b].tolist() == [x for x, _ in p.nbrs[pt][l]], (pt, l)
+            li += 1
+    out, cnt, _ = h.search(base[:20], 5, 9)
+    for i in range(20):
+        want = p.search(base[i], 5, 9)
+        assert out["d_id"][i, :cnt[i]].tolist() == [w[0] for w in want], i
+        assert [float(x) for x in out["distance"][i, :cnt[i]]] == [w[1] for w in want]
