@@ -208,6 +208,25 @@ def optdens_definition(vals, m, f64_draw=False):
     return np.array(sk, dtype=np.float32)
 
 
+def superminhash_definition(vals, m):
+    """Ertl's SuperMinHash as a plain definition, without the a_upper early stop or the lazy
+    permutation bookkeeping: every distinct item runs its whole Fisher-Yates permutation
+    (j = 0..m-1: r_j, k_j = j + U(m-j), swap) and sig[slot] = min over items of r_j + j."""
+    import numpy as np
+    sig = [np.float32(4294967296.0)] * m
+    for v in set(vals):
+        rng = Xoshiro((v * 0x517CC1B727220A95) & M64)
+        perm = list(range(m))
+        for j in range(m):
+            r = np.float32(rng.f32())
+            k = j + rng.usize(m - j)
+            perm[j], perm[k] = perm[k], perm[j]
+            val = np.float32(r + np.float32(j))
+            if val < sig[perm[j]]:
+                sig[perm[j]] = val
+    return np.array(sig, dtype=np.float32)
+
+
 def hamming(a, b):
     import numpy as np
     a = np.asarray(a)

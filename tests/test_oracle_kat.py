@@ -320,3 +320,16 @@ def test_hnsw_oracle_equals_independent_python_restatement(oracle, wave):
         want = p.search(base[i], 5, 9)
         assert out["d_id"][i, :cnt[i]].tolist() == [w[0] for w in want], i
         assert [float(x) for x in out["distance"][i, :cnt[i]]] == [w[1] for w in want]
+
+
+def test_superminhash_early_stop_equals_definition(oracle):
+    """the oracle's a_upper early stop and lazy permutation arrays only skip work: same bits as the
+    full-permutation definition in tests/_pyref.py"""
+    import _pyref as P
+    rng = np.random.default_rng(2)
+    for n, m in [(1, 8), (5, 16), (60, 16), (400, 32)]:
+        vals = rng.integers(1, 2**40, n).astype(np.uint64)
+        vals = np.concatenate([vals, vals[: n // 2]])            # repeated items are idempotent
+        got = oracle.superminhash(vals, m)
+        want = P.superminhash_definition([int(v) for v in vals], m)
+        assert got.tobytes() == want.tobytes(), (n, m)
