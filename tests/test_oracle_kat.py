@@ -333,3 +333,25 @@ def test_superminhash_early_stop_equals_definition(oracle):
         got = oracle.superminhash(vals, m)
         want = P.superminhash_definition([int(v) for v in vals], m)
         assert got.tobytes() == want.tobytes(), (n, m)
+
+
+def test_fasta_parser_fuzz_against_python():
+    """random byte soup biased towards the parser's special bytes ('>', newlines, the letters of
+    "capsid", CR, lower case, non-alphabet): the C oracle and the line-based Python restatement
+    must produce the same records in every mode"""
+    from hypothesis import given, settings, strategies as st
+
+    soup = st.lists(st.sampled_from([b">", b"\n", b"\r\n", b"capsid", b"c", b"a", b"A", b"C", b"G", b"T", b"N",
+                                     b"acgt", b"MKV", b"*", b"X", b" ", b"ACGTACGTAC", b"p", b"s", b"i", b"d"]),
+                    min_size=0, max_size=60)
+
+    @settings(max_examples=300, deadline=None)
+    @given(soup)
+    def check(parts):
+        data = b">" + b"".join(parts)          # a FASTA file starts with '>' (anything else is an error)
+        for data_t in (0, 1):
+            for block in (False, True):
+                got = [list(map(int, s)) for s in O.parse_fasta(data, data_t, block)]
+                assert got == R.parse_fasta(data, data_t, block), (data, data_t, block)
+
+    check()

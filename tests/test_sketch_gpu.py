@@ -136,3 +136,20 @@ def test_prob_genome_longer_than_2_pow_24(oracle):
     # (24 bits up to 16.7 M symbols, 30 bits at most); 20 Mbp needs 25 bits
     files = [g.synth.dna_genome(3, 20_000_000, ncontigs=2)]
     assert_same(*run_both(oracle, files, 21, 4000))
+
+
+def test_byte_soup_files_match_oracle(oracle):
+    """400 random files made of the parser's special bytes ('>', newlines, CR, the letters of
+    "capsid", lower case, non-alphabet bytes, short and long runs of bases): K1's SIMD fast path
+    and its byte-serial path must agree with the oracle in every mode"""
+    rng = np.random.default_rng(2024)
+    atoms = [b">", b"\n", b"\r\n", b"capsid", b"c", b"a", b"A", b"C", b"G", b"T", b"N", b"acgt", b"MKV", b"*",
+             b"X", b" ", b"ACGTACGTAC", b"p", b"s", b"i", b"d", b"ACGTTGCATGCATGCAAGGCTTAACCGGTT" * 3,
+             b"MKVLAAGIVGLTERDQ" * 2]
+    files = []
+    for _ in range(400):
+        n = int(rng.integers(0, 120))
+        files.append(b">" + b"".join(atoms[int(i)] for i in rng.integers(0, len(atoms), n)))
+    for k, S, algo, data_t, block in [(5, 64, g.ALGO_PROB3A, g.DATA_DNA, False), (4, 32, g.ALGO_PROB3A, g.DATA_DNA, True),
+                                      (3, 48, g.ALGO_OPTDENS, g.DATA_AA, False), (2, 16, g.ALGO_SUPER, g.DATA_AA, True)]:
+        assert_same(*run_both(oracle, files, k, S, algo, data_t, block))
