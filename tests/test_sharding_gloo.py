@@ -52,14 +52,14 @@ def _worker(rank, world, port, nfiles, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nfiles", [7, 8])
-def test_two_rank_sketch_and_request_equal_single_process(oracle, nfiles):
+@pytest.mark.parametrize("world,nfiles", [(2, 7), (2, 8), (3, 10)])
+def test_sharded_sketch_and_request_equal_single_process(oracle, world, nfiles):
     import gsearch_b200 as g
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, nfiles, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nfiles, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
