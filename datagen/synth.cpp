@@ -1,4 +1,6 @@
-// datagen.cu -- seeded synthetic FASTA for the benchmark and the tests (host code, no CUDA).
+// synth.cpp -- seeded synthetic workloads for the benchmark and the tests.  Host code, no CUDA,
+// NOT part of the product: it builds into its own datagen/libgsb_synth.so so that the CPU
+// reference arm of bench.py maps no product code.
 //
 // The reference ships no sample data; the workloads of BASELINE.json are
 // synthesised as SURVEY.md 8(d) specifies: genomes come in families of 16 around a random root
@@ -14,7 +16,11 @@
 #include <cstdio>
 #include <vector>
 
-#include "../../include/gsearch_b200.h"
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+#define GSB_API __attribute__((visibility("default")))
 
 namespace {
 
@@ -165,4 +171,90 @@ extern "C" GSB_API uint64_t gsb_synth_aa_proteome(uint64_t index, uint32_t nprot
         }
     }
     return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic signature database for the `request` workload (BASELINE configs[2]; SURVEY 8d:
+// "sketches may be generated directly as synthetic signatures with planted family structure").
+// A random recursive tree: point 0 is random; point i > 0 keeps each slot of a random earlier
+// point par(i) with probability keep(i) in [0.50, 0.95] and draws the other slots fresh, so that
+// distances to ancestors and cousins are graded (1 - product of the keeps along the path).
+// Every value is a stateless hash of (seed, i, slot): the same database comes out for any
+// thread count, and the CPU reference arm and the GPU arm of bench.py see identical bytes.
+//   elem_bytes: 8 (u64 values below 2^40), 4 (u32) or 2 (u16)
+namespace {
+inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+inline uint64_t cell(uint64_t seed, uint64_t i, uint64_t s, uint64_t salt) {
+    return mix64(mix64(seed + 0x9e3779b97f4a7c15ULL * (i + 1)) ^ (0xD1B54A32D192ED03ULL * (s + 1)) ^ salt);
+}
+template <class T>
+void tree_rows(T *out, uint64_t n, uint32_t S, uint64_t seed, uint64_t vmask, uint64_t first) {
+    std::vector<uint64_t> par(n);
+    std::vector<uint64_t> keep(n);  // threshold on a 32-bit draw
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t g = first + i;
+        par[i] = g ? (uint64_t)(((__uint128_t)cell(seed, g, 0, 0x50415245ull) * g) >> 64) : 0;
+        const double k = 0.50 + 0.45 * ((double)(cell(seed, g, 0, 0x4B454550ull) >> 11) * (1.0 / 9007199254740992.0));
+        keep[i] = (uint64_t)(k * 4294967296.0);
+    }
+    // a block of columns is independent of the others: rows in order inside a block
+    const uint32_t kCols = 512;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c0 = 0; c0 < (int64_t)S; c0 += kCols) {
+        const uint32_t c1 = std::min<uint32_t>(S, (uint32_t)c0 + kCols);
+        for (uint64_t i = 0; i < n; i++) {
+            const uint64_t g = first + i;
+            T *row = out + i * (uint64_t)S;
+            const T *prow = (g && par[i] >= first) ? out + (par[i] - first) * (uint64_t)S : nullptr;
+            const uint64_t rowh = mix64(seed + 0x9e3779b97f4a7c15ULL * (g + 1));
+            for (uint32_t s = (uint32_t)c0; s < c1; s++) {
+                const uint64_t h = mix64(rowh ^ (0xD1B54A32D192ED03ULL * (s + 1)));  // == cell(seed, g, s, 0)
+                const bool kept = g != 0 && prow != nullptr && (h >> 32) < keep[i];
+                row[s] = kept ? prow[s] : (T)(1 + ((h * 0x9E3779B97F4A7C15ULL >> 20) & vmask));
+            }
+        }
+    }
+}
+}  // namespace
+
+// rows [first, first + n) of the database; with first > 0 a parent outside the range is treated
+// as absent (the row is fresh), so shards are self-contained.  Returns 0, or 1 on a bad argument.
+extern "C" GSB_API int gsb_synth_signatures(void *out, uint64_t n, uint32_t S, uint32_t elem_bytes, uint64_t seed,
+                                            uint64_t first) {
+    if (!out || !S) return 1;
+    switch (elem_bytes) {
+    case 8: tree_rows<uint64_t>((uint64_t *)out, n, S, seed, (1ull << 40) - 2, first); return 0;
+    case 4: tree_rows<uint32_t>((uint32_t *)out, n, S, seed, 0xFFFFFFFDull, first); return 0;
+    case 2: tree_rows<uint16_t>((uint16_t *)out, n, S, seed, 0xFFFDull, first); return 0;
+    default: return 1;
+    }
+}
+
+// queries: query j copies row pick(j) of `db` (n rows) and redraws each slot with probability
+// `noise` -- a mutated member of the database, as a `request` genome is of its family
+extern "C" GSB_API int gsb_synth_queries(void *out, uint32_t nq, const void *db, uint64_t n, uint32_t S,
+                                         uint32_t elem_bytes, uint64_t seed, double noise, uint64_t *picked) {
+    if (!out || !db || !n || !S || (elem_bytes != 8 && elem_bytes != 4 && elem_bytes != 2)) return 1;
+    const uint64_t thr = (uint64_t)(noise * 4294967296.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < (int64_t)nq; j++) {
+        const uint64_t p = (uint64_t)(((__uint128_t)cell(seed, (uint64_t)j, 0, 0x5049434Bull) * n) >> 64);
+        if (picked) picked[j] = p;
+        for (uint32_t s = 0; s < S; s++) {
+            const uint64_t h = cell(seed ^ 0x51554552ull, (uint64_t)j, s, 0);
+            const bool fresh = (h >> 32) < thr;
+            const uint64_t v = 1 + ((h * 0x9E3779B97F4A7C15ULL >> 20));
+            if (elem_bytes == 8)
+                ((uint64_t *)out)[(uint64_t)j * S + s] = fresh ? (v & ((1ull << 40) - 2)) + (1ull << 40) : ((const uint64_t *)db)[p * S + s];
+            else if (elem_bytes == 4)
+                ((uint32_t *)out)[(uint64_t)j * S + s] = fresh ? (uint32_t)(v | 1u) : ((const uint32_t *)db)[p * S + s];
+            else
+                ((uint16_t *)out)[(uint64_t)j * S + s] = fresh ? (uint16_t)(v | 1u) : ((const uint16_t *)db)[p * S + s];
+        }
+    }
+    return 0;
 }

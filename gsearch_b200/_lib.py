@@ -60,9 +60,6 @@ SYMBOLS = {
     "gsb_index_set_wave_max": (_int, [_vp, _u32]),
     "gsb_index_dump": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "gsb_index_load": (_int, [_vp, C.c_char_p, C.c_char_p]),
-    "gsb_synth_max_bytes": (_u64, [_u64, _u32]),
-    "gsb_synth_dna_genome": (_u64, [_u64, _u64, _u32, _vp, _u64]),
-    "gsb_synth_aa_proteome": (_u64, [_u64, _u32, _u32, _vp, _u64]),
 }
 
 _lib = None

@@ -61,12 +61,9 @@ static int launch_hamming(const uint8_t *q, uint32_t nq, const uint8_t *c, uint3
     size_t smem = (row + 127) & ~(size_t)127;
     const int staged = smem <= 200 * 1024 ? 1 : 0;  // larger rows are read from global memory
     if (!staged) smem = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GSB_CUDA_TRY(cudaFuncSetAttribute(k6_hamming_matrix<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
-        attr_set = true;
-    }
+    // the attribute is per device: set it on every launch (a process may use several GPUs)
+    GSB_CUDA_TRY(cudaFuncSetAttribute(k6_hamming_matrix<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
     // enough CTAs per query to fill the machine, but at least one candidate per warp
     uint32_t per = 8;
     while ((uint64_t)nq * ((n + per - 1) / per) > 148ull * 16 && per < 4096) per *= 2;

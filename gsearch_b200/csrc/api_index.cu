@@ -73,9 +73,16 @@ struct GrowBuf {
             set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
             return GSB_ERR_OOM;
         }
-        cudaStreamSynchronize(st);
-        if (cap) cudaMemcpy(q, p, cap, cudaMemcpyDeviceToDevice);
-        cudaMemset((uint8_t *)q + cap, 0, want - cap);
+        // everything on `st` (created non-blocking: the legacy default stream would not order
+        // with it), and finished before the old buffer goes
+        if (cap) cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st);
+        cudaMemsetAsync((uint8_t *)q + cap, 0, want - cap, st);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("GrowBuf: copy to the grown buffer failed: %s", cudaGetErrorString(e));
+            cudaFree(q);
+            return GSB_ERR_CUDA;
+        }
         if (p) cudaFree(p);
         p = q;
         cap = want;
@@ -498,12 +505,10 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     const size_t bm_bytes = (((size_t)first + W + 31) / 32) * 4;
     const uint32_t bm_words = (smem + bm_bytes <= kSmemMax && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
     smem += (size_t)bm_words * 4;
-    static bool attr = false;
-    if (!attr) {
-        GSB_CUDA_TRY(cudaFuncSetAttribute(k8_hnsw_insert_select<ELEM, F32>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-        attr = true;
-    }
+    // per device, not per process: set on every launch (cheap) so that an index on another GPU of
+    // the same process gets the opt-in too
+    GSB_CUDA_TRY(cudaFuncSetAttribute(k8_hnsw_insert_select<ELEM, F32>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     const uint32_t nctas = std::min<uint32_t>(W, (uint32_t)idx->nsm * (staged ? 1u : 2u));
     int rc;
     if ((rc = ensure_workspace(idx, nctas, (uint64_t)first + W, ef_c))) return rc;
@@ -814,18 +819,50 @@ extern "C" int gsb_index_load(gsb_index *idx, const char *dir, const char *basen
             rc = GSB_ERR_INVALID_ARG;
             break;
         }
-        std::vector<uint8_t> levels(n), sig((size_t)n * idx->p.sketch_size * idx->elem);
-        std::vector<uint32_t> ranks(n), nidx(tn);
-        std::vector<uint64_t> off(tl + 1), ids(n);
-        std::vector<float> ndist(tn);
-        if (!rd(fg, levels.data(), n) || !rd(fg, ranks.data(), n) || !rd(fg, off.data(), tl + 1) ||
-            !rd(fg, nidx.data(), tn) || !rd(fg, ndist.data(), tn) || !rd(fd, ids.data(), n) ||
-            !rd(fd, sig.data(), sig.size())) {
-            set_error("gsb_index_load: truncated dump %s", base.c_str());
+        // sizes come from an untrusted header: check them against the file lengths before allocating
+        const size_t row = (size_t)idx->p.sketch_size * idx->elem;
+        auto file_size = [](FILE *f) -> uint64_t {
+            const long at = ftell(f);
+            fseek(f, 0, SEEK_END);
+            const long sz = ftell(f);
+            fseek(f, at, SEEK_SET);
+            return sz < 0 ? 0 : (uint64_t)sz;
+        };
+        const uint64_t gsz = file_size(fg), dsz = file_size(fd);
+        const uint64_t lim = 1ull << 40;
+        if (n > lim || tl > lim || tn > lim || tl < n || tl > n * (uint64_t)kMaxLayers ||
+            gsz != 88 + n * 5 + (tl + 1) * 8 + tn * 8 || dsz != 32 + n * 8 + n * row) {
+            set_error("gsb_index_load: header of %s does not match the file sizes (corrupt or truncated dump)",
+                      base.c_str());
             break;
         }
-        rc = gsb_index_load_graph(idx, sig.data(), ids.data(), n, levels.data(), ranks.data(), off.data(),
-                                  nidx.data(), ndist.data(), hdr[7]);
+        try {
+            std::vector<uint8_t> levels(n), sig((size_t)n * row);
+            std::vector<uint32_t> ranks(n), nidx(tn);
+            std::vector<uint64_t> off(tl + 1), ids(n);
+            std::vector<float> ndist(tn);
+            if (!rd(fg, levels.data(), n) || !rd(fg, ranks.data(), n) || !rd(fg, off.data(), tl + 1) ||
+                !rd(fg, nidx.data(), tn) || !rd(fg, ndist.data(), tn) || !rd(fd, ids.data(), n) ||
+                !rd(fd, sig.data(), sig.size())) {
+                set_error("gsb_index_load: truncated dump %s", base.c_str());
+                break;
+            }
+            // offsets: monotone, starting at 0, ending at the neighbour count; one list per (point, layer)
+            uint64_t want_tl = 0;
+            for (uint64_t p = 0; p < n; p++) want_tl += (uint64_t)levels[p] + 1;
+            bool ok = want_tl == tl && off[0] == 0 && off[tl] == tn;
+            for (uint64_t i = 0; ok && i < tl; i++) ok = off[i] <= off[i + 1];
+            if (!ok) {
+                set_error("gsb_index_load: inconsistent neighbour offsets in %s", base.c_str());
+                rc = GSB_ERR_INVALID_ARG;
+                break;
+            }
+            rc = gsb_index_load_graph(idx, sig.data(), ids.data(), n, levels.data(), ranks.data(), off.data(),
+                                      nidx.data(), ndist.data(), hdr[7]);
+        } catch (const std::exception &) {
+            set_error("gsb_index_load: out of host memory reading %s", base.c_str());
+            rc = GSB_ERR_OOM;
+        }
     } while (0);
     if (fg) fclose(fg);
     if (fd) fclose(fd);

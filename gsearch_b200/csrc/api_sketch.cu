@@ -404,12 +404,8 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
                 dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
                 want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
         }
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k2_prob_classify<Src, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kStageCap * sizeof(ListEntry)));
-            attr_set = true;
-        }
+        cudaFuncSetAttribute(k2_prob_classify<Src, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kStageCap * sizeof(ListEntry)));  // per device: every launch
         {
             Timed tc_(h, CAT_K2_CLASSIFY, st);
             const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * env_int("GSB_CLS_R", 3, 1, 8)));

@@ -53,18 +53,28 @@ def gather_rows(local, n_total, rank=None, world=None, group=None, out=None):
     return full[:n_total]
 
 
-def sketch_sharded(sketch_fn, files, rank, world, device="cpu", group=None):
+def sketch_sharded(sketch_fn, files, rank, world, device="cpu", group=None, row_bytes=None, sig_dtype=None):
     """`tohnsw` sketch phase over G ranks.  sketch_fn(list of files) -> (sig [n, S] numpy, nb_bases [n]);
-    returns the full (signatures, nb_bases) in file order on every rank."""
+    returns the full (signatures, nb_bases) in file order on every rank.  A rank whose shard is
+    empty (fewer files than ranks) still takes part in the gather: it needs `row_bytes` (S *
+    sizeof(Sig)) and `sig_dtype`, which it cannot learn from an empty result."""
     import numpy as np
 
     mine = shard_indices(len(files), rank, world)
-    sig, nb = sketch_fn([files[i] for i in mine])
-    sig_t = torch.from_numpy(np.ascontiguousarray(sig).view(np.uint8).reshape(len(mine), -1)).to(device)
+    if mine:
+        sig, nb = sketch_fn([files[i] for i in mine])
+        sig = np.ascontiguousarray(sig)
+        row_bytes = sig.dtype.itemsize * sig.shape[1]
+        sig_dtype = sig.dtype
+    else:
+        if row_bytes is None or sig_dtype is None:
+            raise ValueError("sketch_sharded: this rank owns no file; pass row_bytes and sig_dtype")
+        sig, nb = np.zeros((0, row_bytes // np.dtype(sig_dtype).itemsize), dtype=sig_dtype), np.zeros(0, np.uint64)
+    sig_t = torch.from_numpy(sig.view(np.uint8).reshape(len(mine), row_bytes)).to(device)
     nb_t = torch.from_numpy(np.asarray(nb).astype(np.int64)).to(device)
     all_sig = gather_rows(sig_t, len(files), rank, world, group)
     all_nb = gather_rows(nb_t, len(files), rank, world, group)
-    sig_all = all_sig.cpu().numpy().view(sig.dtype).reshape(len(files), -1)
+    sig_all = all_sig.cpu().numpy().view(sig_dtype).reshape(len(files), -1)
     return sig_all, all_nb.cpu().numpy().astype(np.uint64)
 
 
@@ -73,8 +83,13 @@ def search_sharded(search_fn, queries, knbn, rank, world, device="cpu", group=No
     neighbour array [nq, knbn], counts [nq]); returns both for all queries on every rank."""
     import numpy as np
 
+    from .index import Neighbour
+
     mine = shard_indices(len(queries), rank, world)
-    out, counts = search_fn(queries[mine])
+    if mine:
+        out, counts = search_fn(queries[mine])
+    else:  # fewer queries than ranks: contribute an empty shard, do not call the index
+        out, counts = np.zeros((0, knbn), dtype=Neighbour), np.zeros(0, np.uint32)
     item = out.dtype.itemsize
     out_t = torch.from_numpy(np.ascontiguousarray(out).view(np.uint8).reshape(len(mine), knbn * item)).to(device)
     cnt_t = torch.from_numpy(np.asarray(counts).astype(np.int64)).to(device)

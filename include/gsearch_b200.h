@@ -249,15 +249,6 @@ GSB_API int gsb_index_set_wave_max(gsb_index *idx, uint32_t wave_max);
 GSB_API int gsb_index_dump(const gsb_index *idx, const char *dir, const char *basename);
 GSB_API int gsb_index_load(gsb_index *idx, const char *dir, const char *basename);
 
-/* ------------------------------------------------------------------------- */
-/* synthetic workloads (bench / tests; host code, seeded)       */
-/* ------------------------------------------------------------------------- */
-GSB_API uint64_t gsb_synth_max_bytes(uint64_t length, uint32_t nrecords);
-GSB_API uint64_t gsb_synth_dna_genome(uint64_t index, uint64_t length, uint32_t ncontigs,
-                                      uint8_t *out, uint64_t cap);
-GSB_API uint64_t gsb_synth_aa_proteome(uint64_t index, uint32_t nprot, uint32_t mean_len,
-                                       uint8_t *out, uint64_t cap);
-
 #ifdef __cplusplus
 }
 #endif
