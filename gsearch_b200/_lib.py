@@ -43,6 +43,8 @@ SYMBOLS = {
     "gsb_sketch_fasta_batch_dev": (_int, [_vp, _vp, _vp, _u32, _vp, _vp, _vp]),
     "gsb_sketcher_launch_count": (_u64, [_vp]),
     "gsb_sketcher_retry_count": (_u64, [_vp]),
+    "gsb_sketcher_fallback_count": (_u64, [_vp]),
+    "gsb_sketcher_set_prob_path": (_int, [_vp, _int]),
     "gsb_sketcher_enable_timing": (None, [_vp, _int]),
     "gsb_sketcher_kernel_times": (None, [_vp, _vp, _vp]),
     "gsb_hamming_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _int]),
@@ -53,6 +55,7 @@ SYMBOLS = {
     "gsb_index_insert_batch": (_int, [_vp, _vp, _vp, _u64]),
     "gsb_index_insert_batch_dev": (_int, [_vp, _vp, _vp, _u64]),
     "gsb_index_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "gsb_index_search_batch_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "gsb_index_nb_point": (_u64, [_vp]),
     "gsb_index_load_graph": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64]),
     "gsb_index_graph_sizes": (_int, [_vp, _vp, _vp]),

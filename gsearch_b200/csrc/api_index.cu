@@ -393,8 +393,16 @@ extern "C" int gsb_index_load_graph(gsb_index *idx, const void *sigs, const uint
     return GSB_OK;
 }
 
+struct SearchBufs {
+    const uint8_t *queries;
+    gsb_neighbour *out;
+    uint32_t *counts;
+    unsigned long long *nb_eval;
+};
+
 template <int ELEM, bool F32>
-static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef, cudaStream_t st) {
+static int launch_search(gsb_index *idx, const SearchBufs &sb, uint32_t nq, uint32_t knbn, uint32_t ef,
+                         cudaStream_t st) {
     const size_t row = (size_t)idx->p.sketch_size * ELEM;
     const size_t ret_bytes = ((size_t)ef + 2) * sizeof(HItem);
     // a row that does not fit in shared memory stays in global memory (S up to 65535 is legal)
@@ -418,19 +426,21 @@ static int launch_search(gsb_index *idx, uint32_t nq, uint32_t knbn, uint32_t ef
     if ((rc = idx->d_counter.ensure(256))) return rc;
     GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
     SearchOut so;
-    so.out = idx->d_out.as<gsb_neighbour>();
-    so.counts = idx->d_counts.as<uint32_t>();
-    so.nb_eval = idx->d_neval.as<unsigned long long>();
+    so.out = sb.out;
+    so.counts = sb.counts;
+    so.nb_eval = sb.nb_eval;
     k7_hnsw_search<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(
-        graph_view(idx), idx->d_queries.as<uint8_t>(), nq, knbn, ef, ret_in_smem, bm_words, staged,
+        graph_view(idx), sb.queries, nq, knbn, ef, ret_in_smem, bm_words, staged,
         idx->d_ws.as<uint8_t>(), idx->wl, so, idx->d_counter.as<uint32_t>());
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;
 }
 
-extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t nq, uint32_t knbn,
-                                      uint32_t ef, gsb_neighbour *out, uint32_t *counts_out,
-                                      uint64_t *nb_eval_out) {
+// queries / results in host memory (dev = false: copied in and out on the index stream, the call
+// returns when the results are in host memory) or in device memory (dev = true: the kernel reads
+// and writes the caller's buffers; the call returns after the stream has been synchronised)
+static int search_batch_impl(gsb_index *idx, const void *queries, uint32_t nq, uint32_t knbn, uint32_t ef,
+                             gsb_neighbour *out, uint32_t *counts_out, uint64_t *nb_eval_out, bool dev) {
     std::unique_lock<std::recursive_mutex> lock_;
     if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || (nq && (!queries || !out || !counts_out))) {
@@ -442,36 +452,64 @@ extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint3
         set_error("knbn must be > 0");
         return GSB_ERR_INVALID_ARG;
     }
+    GSB_CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
     if (idx->n == 0) {
-        for (uint32_t i = 0; i < nq; i++) counts_out[i] = 0;
-        if (nb_eval_out) memset(nb_eval_out, 0, (size_t)nq * 8);
+        if (dev) {
+            GSB_CUDA_TRY(cudaMemsetAsync(counts_out, 0, (size_t)nq * 4, st));
+            if (nb_eval_out) GSB_CUDA_TRY(cudaMemsetAsync(nb_eval_out, 0, (size_t)nq * 8, st));
+            GSB_CUDA_TRY(cudaStreamSynchronize(st));
+        } else {
+            for (uint32_t i = 0; i < nq; i++) counts_out[i] = 0;
+            if (nb_eval_out) memset(nb_eval_out, 0, (size_t)nq * 8);
+        }
         return GSB_OK;
     }
-    GSB_CUDA_TRY(cudaSetDevice(idx->device));
     const uint32_t efs = std::max(ef, knbn);  // hnsw_rs: ef = max(ef_arg, knbn)
     const size_t row = (size_t)idx->p.sketch_size * idx->elem;
     int rc;
-    if ((rc = idx->d_queries.ensure((size_t)nq * row + 64))) return rc;
-    if ((rc = idx->d_out.ensure((size_t)nq * knbn * sizeof(gsb_neighbour)))) return rc;
-    if ((rc = idx->d_counts.ensure((size_t)nq * 4))) return rc;
-    if ((rc = idx->d_neval.ensure((size_t)nq * 8))) return rc;
-    cudaStream_t st = idx->stream;
-    GSB_CUDA_TRY(cudaMemsetAsync(idx->d_out.p, 0, (size_t)nq * knbn * sizeof(gsb_neighbour), st));
-    GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_queries.p, queries, (size_t)nq * row, cudaMemcpyHostToDevice, st));
+    if (!dev) {
+        if ((rc = idx->d_queries.ensure((size_t)nq * row + 64))) return rc;
+        if ((rc = idx->d_out.ensure((size_t)nq * knbn * sizeof(gsb_neighbour)))) return rc;
+        if ((rc = idx->d_counts.ensure((size_t)nq * 4))) return rc;
+    }
+    if (!dev || !nb_eval_out)
+        if ((rc = idx->d_neval.ensure((size_t)nq * 8))) return rc;
+    SearchBufs sb;
+    sb.queries = dev ? (const uint8_t *)queries : idx->d_queries.as<uint8_t>();
+    sb.out = dev ? out : idx->d_out.as<gsb_neighbour>();
+    sb.counts = dev ? counts_out : idx->d_counts.as<uint32_t>();
+    sb.nb_eval = (dev && nb_eval_out) ? (unsigned long long *)nb_eval_out : idx->d_neval.as<unsigned long long>();
+    GSB_CUDA_TRY(cudaMemsetAsync(sb.out, 0, (size_t)nq * knbn * sizeof(gsb_neighbour), st));
+    if (!dev) GSB_CUDA_TRY(cudaMemcpyAsync(idx->d_queries.p, queries, (size_t)nq * row, cudaMemcpyHostToDevice, st));
     switch (idx->p.sig_type) {
-    case GSB_SIG_U64: rc = launch_search<8, false>(idx, nq, knbn, efs, st); break;
-    case GSB_SIG_U32: rc = launch_search<4, false>(idx, nq, knbn, efs, st); break;
-    case GSB_SIG_F32: rc = launch_search<4, true>(idx, nq, knbn, efs, st); break;
-    default: rc = launch_search<2, false>(idx, nq, knbn, efs, st); break;
+    case GSB_SIG_U64: rc = launch_search<8, false>(idx, sb, nq, knbn, efs, st); break;
+    case GSB_SIG_U32: rc = launch_search<4, false>(idx, sb, nq, knbn, efs, st); break;
+    case GSB_SIG_F32: rc = launch_search<4, true>(idx, sb, nq, knbn, efs, st); break;
+    default: rc = launch_search<2, false>(idx, sb, nq, knbn, efs, st); break;
     }
     if (rc) return rc;
-    GSB_CUDA_TRY(cudaMemcpyAsync(out, idx->d_out.p, (size_t)nq * knbn * sizeof(gsb_neighbour),
-                                 cudaMemcpyDeviceToHost, st));
-    GSB_CUDA_TRY(cudaMemcpyAsync(counts_out, idx->d_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    if (nb_eval_out)
-        GSB_CUDA_TRY(cudaMemcpyAsync(nb_eval_out, idx->d_neval.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+    if (!dev) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(out, idx->d_out.p, (size_t)nq * knbn * sizeof(gsb_neighbour),
+                                     cudaMemcpyDeviceToHost, st));
+        GSB_CUDA_TRY(cudaMemcpyAsync(counts_out, idx->d_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        if (nb_eval_out)
+            GSB_CUDA_TRY(cudaMemcpyAsync(nb_eval_out, idx->d_neval.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+    }
     GSB_CUDA_TRY(cudaStreamSynchronize(st));
     return GSB_OK;
+}
+
+extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t nq, uint32_t knbn,
+                                      uint32_t ef, gsb_neighbour *out, uint32_t *counts_out,
+                                      uint64_t *nb_eval_out) {
+    return search_batch_impl(idx, queries, nq, knbn, ef, out, counts_out, nb_eval_out, false);
+}
+
+extern "C" int gsb_index_search_batch_dev(gsb_index *idx, const void *d_queries, uint32_t nq, uint32_t knbn,
+                                          uint32_t ef, gsb_neighbour *d_out, uint32_t *d_counts_out,
+                                          uint64_t *d_nb_eval_out) {
+    return search_batch_impl(idx, d_queries, nq, knbn, ef, d_out, d_counts_out, d_nb_eval_out, true);
 }
 
 // ------------------------------------------------------------------------------ construction

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "api_common.h"
+#include "prob_partition.cuh"
 #include "sketch_kernels.cuh"
 
 using namespace gsb;
@@ -53,8 +54,17 @@ static int prob_slots() {
 
 struct ProbSlot {
     DevBuf bitmap, table, cnt, list, ovf, misc, hmin, sigw;
+    DevBuf buckets, cursor;  // partition path
     size_t cnt_dirty = 0;
 };
+
+// GSB_PROB_PATH=filter (or gsb_sketcher_set_prob_path(h, 1)) forces the round-1 filter path (mark /
+// classify / exact set) for every file; the default is the partition path with the filter path as
+// the fallback for the files it flags
+static int prob_path_from_env() {
+    const char *e = getenv("GSB_PROB_PATH");
+    return (e && !strcmp(e, "filter")) ? 1 : 0;
+}
 
 // Small host->device descriptor copies go through a kernel that reads the PINNED host buffer
 // directly (unified addressing) instead of cudaMemcpyAsync: a copy-engine transfer would queue
@@ -138,7 +148,10 @@ struct gsb_sketcher {
     PinBuf h_files, h_tile_prefix, h_jobs, h_chunk_prefix, h_retry, h_overflow;
     ProbSlot slot[kMaxSlots];
     DevBuf d_bytes, d_sig, d_nb;
-    uint64_t launches = 0, retries = 0;
+    uint64_t launches = 0, retries = 0, fallbacks = 0;
+    int prob_path = 0;  // 0 = partition path with filter fallback, 1 = filter path only
+    std::vector<uint32_t> pending_fallback;  // files flagged by the partition path, waiting for the filter path
+    std::vector<double> pending_fallback_t;
     // optional per-kernel-family timing (bench.py's roofline): CUDA events around launches
     bool timing = false;
     struct Span {
@@ -257,6 +270,7 @@ extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, 
     // c1*u >= 1 needs u >= 1/c1; anything from a little below that goes to the exact path
     sc.u_slow = (uint64_t)(4503599627370496.0 / sc.e01.c1) - 8;
     sc.spec_flags = p.spec_flags;
+    h->prob_path = prob_path_from_env();
     cudaSetDevice(device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -290,6 +304,8 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
         s.misc.release();
         s.hmin.release();
         s.sigw.release();
+        s.buckets.release();
+        s.cursor.release();
     }
     PinBuf *pb[] = {&h->h_files, &h->h_tile_prefix, &h->h_jobs, &h->h_chunk_prefix, &h->h_retry, &h->h_overflow};
     for (PinBuf *b : pb) b->release();
@@ -315,6 +331,16 @@ extern "C" int gsb_sketcher_sig_type(const gsb_sketcher *h) { return h ? h->sig_
 extern "C" uint32_t gsb_sketcher_elem_size(const gsb_sketcher *h) { return h ? h->elem : 0; }
 extern "C" uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h) { return h ? h->launches : 0; }
 extern "C" uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h) { return h ? h->retries : 0; }
+extern "C" uint64_t gsb_sketcher_fallback_count(const gsb_sketcher *h) { return h ? h->fallbacks : 0; }
+extern "C" int gsb_sketcher_set_prob_path(gsb_sketcher *h, int path) {
+    if (!h || path < 0 || path > 1) {
+        set_error("gsb_sketcher_set_prob_path: path must be 0 (partition, filter as fallback) or 1 (filter only)");
+        return GSB_ERR_INVALID_ARG;
+    }
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->prob_path = path;
+    return GSB_OK;
+}
 extern "C" void gsb_sketcher_enable_timing(gsb_sketcher *h, int on) {
     if (!h) return;
     h->timing = on != 0;
@@ -434,6 +460,86 @@ void launch_prob_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
     h->launches += nchunks ? 8 : 4;
 }
 
+static PartConsts part_consts(const gsb_sketcher *h) {
+    return make_part_consts(h->p.data_t == GSB_DATA_DNA ? 2 * h->sc.k : 5 * h->sc.k);
+}
+
+// partition path: reset, partition, count, then the same exact replay (K3) as the filter path
+template <class Src, typename KT, typename KEY, int KBITS = 0>
+void launch_part_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunks, uint32_t cpoff, bool dna,
+                       bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    const ProbJob *jobs = h->d_jobs.as<ProbJob>() + joff;
+    ProbBound *bound = h->d_bound.as<ProbBound>() + joff;
+    uint32_t *ovf = h->d_overflow.as<uint32_t>() + joff;
+    const FileResult *res = h->d_res.as<FileResult>();
+    const PartConsts pc = part_consts(h);
+    {
+        Timed t_(h, CAT_RESET, st);
+        k2p_reset<<<dim3(8, njobs), 256, 0, st>>>(jobs, njobs, res, h->sc, bound, ovf, h->d_retry.as<uint32_t>());
+    }
+    if (nchunks) {
+        const int psm = (int)part_smem_bytes<KEY>(), csm = (int)count_smem_bytes<KEY>();
+        cudaFuncSetAttribute(k2p_partition<Src, KT, KEY, KBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
+        cudaFuncSetAttribute(k2p_count<KT, KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm);
+        {
+            Timed tm_(h, CAT_K2_MARK, st);
+            const int per_sm = psm <= 73 * 1024 ? 3 : (psm <= 110 * 1024 ? 2 : 1);
+            const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * env_int("GSB_PART_R", per_sm, 1, 4)));
+            k2p_partition<Src, KT, KEY, KBITS><<<grid, kK2Threads, psm, st>>>(
+                jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+                dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, bound, h->sc, pc, ovf, nchunks);
+        }
+        {
+            Timed tc_(h, CAT_K2_CLASSIFY, st);
+            k2p_count<KT, KEY><<<dim3(kNB, njobs), kCThreads, csm, st>>>(jobs, njobs, res, h->sc, pc, ovf);
+        }
+    }
+    Timed t3_(h, CAT_K3, st);
+    k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
+    k3_prob_points<KT, 1><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
+    if (h->elem == 8)
+        k3_prob_finalize<uint64_t><<<dim3(kFinParts, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint64_t *)d_sig,
+                                                          d_nb, h->d_retry.as<uint32_t>());
+    else
+        k3_prob_finalize<uint32_t><<<dim3(kFinParts, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig,
+                                                          d_nb, h->d_retry.as<uint32_t>());
+    h->launches += nchunks ? 6 : 4;
+}
+
+template <class Src, typename KT>
+void launch_part_group_key(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunks, uint32_t cpoff, bool dna,
+                           bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    // a key (k-mer bits below the bucket bits) + the light flag must fit the key word
+    if constexpr (sizeof(KT) == 4) {
+        launch_part_group<Src, KT, uint32_t>(h, joff, njobs, nchunks, cpoff, dna, want_bounds, d_sig, d_nb, st);
+    } else {
+        if (part_consts(h).keybits <= 31)
+            launch_part_group<Src, KT, uint32_t>(h, joff, njobs, nchunks, cpoff, dna, want_bounds, d_sig, d_nb, st);
+        else
+            launch_part_group<Src, KT, uint64_t>(h, joff, njobs, nchunks, cpoff, dna, want_bounds, d_sig, d_nb, st);
+    }
+}
+
+// DNA: the k values of the BASELINE configurations get kernels with k fixed at compile time
+template <typename KT>
+void launch_part_group_dna(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunks, uint32_t cpoff,
+                           bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
+    if constexpr (sizeof(KT) == 4) {
+        if (h->sc.k == 16)
+            return launch_part_group<SrcDNA<uint32_t, 16>, uint32_t, uint32_t, 32>(h, joff, njobs, nchunks, cpoff, true,
+                                                                                   want_bounds, d_sig, d_nb, st);
+    } else {
+        if (h->sc.k == 21)
+            return launch_part_group<SrcDNA<uint64_t, 21>, uint64_t, uint32_t, 42>(h, joff, njobs, nchunks, cpoff, true,
+                                                                                   want_bounds, d_sig, d_nb, st);
+        if (h->sc.k == 31)
+            return launch_part_group<SrcDNA<uint64_t, 31>, uint64_t, uint64_t, 62>(h, joff, njobs, nchunks, cpoff, true,
+                                                                                   want_bounds, d_sig, d_nb, st);
+    }
+    launch_part_group_key<SrcDNA<KT>, KT>(h, joff, njobs, nchunks, cpoff, true, want_bounds, d_sig, d_nb, st);
+}
+
 template <class Src, typename KT>
 void launch_dens(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunks, uint32_t cpoff, bool dna,
                  bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
@@ -453,8 +559,11 @@ void launch_dens(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunk
     h->launches += nchunks ? 2 : 1;
 }
 
+// bucket-array capacity (keys) of the partition path for a file of `len` bytes
+static size_t part_cap_g(size_t len) { return ((len / kNB) * 5 / 4 + 256 + 3) & ~(size_t)3; }
+
 int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vector<double> &tmult,
-             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st, K1Plan &kp) {
+             const uint64_t *h_offsets, void *d_sig, uint64_t *d_nb, cudaStream_t st, K1Plan &kp, bool newpath) {
     const bool dna = h->p.data_t == GSB_DATA_DNA;
     const bool want_bounds = dna && !h->p.block_flag;
     const uint32_t n = (uint32_t)todo.size();
@@ -471,9 +580,21 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     const size_t filter_bytes_max = (((size_t)(prob_load() * (double)max_len) + 64) / 16 + 8) * 4;
     const size_t light_cap = (size_t)(3.0 * h->sc.m * h->sc.lnm8) + 65536;
     const size_t list_cap_max = std::min<size_t>(max_len + 64, light_cap + max_len / 2) + 64;
+    const size_t key_bytes = part_consts(h).keybits <= 31 ? 4 : 8;
     for (int s = 0; s < 2 * kSlots && s < (int)n; s++) {
         ProbSlot &sl = h->slot[s];
         int rc;
+        if (newpath) {
+            const void *old_misc = sl.misc.p;
+            if ((rc = sl.buckets.ensure((size_t)kNB * part_cap_g(max_len) * key_bytes + 64))) return rc;
+            if ((rc = sl.cursor.ensure((size_t)kNB * 4))) return rc;
+            if ((rc = sl.list.ensure(list_cap_max * sizeof(ListEntry)))) return rc;
+            if ((rc = sl.misc.ensure(256))) return rc;
+            if (sl.misc.p != old_misc) GSB_CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 256, st));
+            if ((rc = sl.hmin.ensure((size_t)h->sc.m * 8))) return rc;
+            if ((rc = sl.sigw.ensure((size_t)h->sc.m * 8))) return rc;
+            continue;
+        }
         const void *old_cnt = sl.cnt.p, *old_list = sl.list.p, *old_misc = sl.misc.p;
         if ((rc = sl.bitmap.ensure(filter_bytes_max + 64))) return rc;
         if ((rc = sl.table.ensure(cap_max * 4 + 64))) return rc;
@@ -533,6 +654,10 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 j.hmin = sl.hmin.as<unsigned long long>();
                 j.sigw = sl.sigw.as<unsigned long long>();
                 j.tmult = tmult[i];
+                j.buckets = sl.buckets.p;
+                j.cursor = sl.cursor.as<uint32_t>();
+                j.cap_g = (uint32_t)part_cap_g(len);
+                j.newpath = newpath ? 1u : 0u;
                 acc += (uint32_t)((len + kChunk - 1) / kChunk);
             }
         }
@@ -563,21 +688,23 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 GSB_CUDA_TRY(cudaEventRecord(h->ev_k1[g], st));
                 GSB_CUDA_TRY(cudaStreamWaitEvent(gs, h->ev_k1[g], 0));
             }
+#define GSB_PROB_LAUNCH(SRC, KT, DNA, WB)                                                                        \
+    do {                                                                                                         \
+        if (newpath && DNA)                                                                                      \
+            launch_part_group_dna<KT>(h, joff, nj, group_chunks[g], cpoff, WB, d_sig, d_nb, gs);                 \
+        else if (newpath)                                                                                        \
+            launch_part_group_key<SRC<KT>, KT>(h, joff, nj, group_chunks[g], cpoff, DNA, WB, d_sig, d_nb, gs);   \
+        else                                                                                                     \
+            launch_prob_group<SRC<KT>, KT>(h, joff, nj, group_chunks[g], cpoff, DNA, WB, d_sig, d_nb, gs);       \
+    } while (0)
             if (dna) {
-                if (h->kt32)
-                    launch_prob_group<SrcDNA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, true,
-                                                                  want_bounds, d_sig, d_nb, gs);
-                else
-                    launch_prob_group<SrcDNA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, true,
-                                                                  want_bounds, d_sig, d_nb, gs);
+                if (h->kt32) GSB_PROB_LAUNCH(SrcDNA, uint32_t, true, want_bounds);
+                else GSB_PROB_LAUNCH(SrcDNA, uint64_t, true, want_bounds);
             } else {
-                if (h->kt32)
-                    launch_prob_group<SrcAA<uint32_t>, uint32_t>(h, joff, nj, group_chunks[g], cpoff, false,
-                                                                 false, d_sig, d_nb, gs);
-                else
-                    launch_prob_group<SrcAA<uint64_t>, uint64_t>(h, joff, nj, group_chunks[g], cpoff, false,
-                                                                 false, d_sig, d_nb, gs);
+                if (h->kt32) GSB_PROB_LAUNCH(SrcAA, uint32_t, false, false);
+                else GSB_PROB_LAUNCH(SrcAA, uint64_t, false, false);
             }
+#undef GSB_PROB_LAUNCH
         }
         kp.pending = false;
         for (int i = 0; i < 2; i++) {
@@ -808,8 +935,16 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
     std::vector<double> tmult(n, 1.0);
     for (uint32_t i = 0; i < n; i++) todo[i] = i;
     std::vector<uint32_t> seq_files;  // SuperMinHash: files for the sequential cold path
-    for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++) {
-        rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp)
+    // prob: the partition path first; files it flags (a bucket array or a counting round overflowed:
+    // very large or very repetitive inputs) are re-run through the general filter path
+    bool newpath = prob && h->prob_path == 0;
+    if (newpath) {
+        size_t max_len = 0;
+        for (uint32_t i = 0; i < n; i++) max_len = std::max<size_t>(max_len, h_offsets[i + 1] - h_offsets[i]);
+        if (part_cap_g(max_len) > kCapGMax) newpath = false;  // 16-bit duplicate counters
+    }
+    for (int attempt = 0; attempt < 10 && !todo.empty(); attempt++) {
+        rc = prob ? run_prob(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp, newpath)
                   : run_dens(h, todo, tmult, h_offsets, d_sig_out, d_nb_bases_out, st, kp);
         if (rc) return rc;
         GSB_CUDA_TRY(cudaMemcpyAsync(h->h_retry.p, h->d_retry.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -817,18 +952,23 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
         collect_spans(h);
         const uint32_t *hr = h->h_retry.as<uint32_t>();
         const uint32_t *ho = prob ? h->h_overflow.as<uint32_t>() : nullptr;
-        std::vector<uint32_t> next;
-        std::vector<double> next_t;
+        std::vector<uint32_t> next, fallback;
+        std::vector<double> next_t, fallback_t;
         for (size_t i = 0; i < todo.size(); i++) {
             const uint32_t f = todo[i];
             const uint32_t status = hr[f] >> 8;
             if (status == 5) {
-                set_error("file %u does not start with '>' (not FASTA)", h->file_base + f);
+                set_error("file %u starts with neither '>' nor '@' (not FASTA / FASTQ)", h->file_base + f);
                 return GSB_ERR_BAD_INPUT;
             }
             if (status == 8) {
                 set_error("file %u: record-boundary pool exhausted", h->file_base + f);
                 return GSB_ERR_CAPACITY;
+            }
+            if (ho && newpath && (ho[i] & 3u)) {  // does not fit the partition geometry: general path
+                fallback.push_back(f);
+                fallback_t.push_back(tmult[i]);
+                continue;
             }
             if (ho && ho[i]) {
                 // candidate list overflow: counters may be dirty; clear and fail loudly
@@ -846,10 +986,27 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
             }
             if (hr[f] & 2u) seq_files.push_back(f);
         }
-        h->retries += next.size();
-        todo.swap(next);
-        tmult.swap(next_t);
+        h->retries += next.size() + fallback.size();
+        h->fallbacks += fallback.size();
+        if (!next.empty()) {  // bound retries of this path first; flagged files wait for their turn
+            todo.swap(next);
+            tmult.swap(next_t);
+            if (!fallback.empty()) {
+                h->pending_fallback.insert(h->pending_fallback.end(), fallback.begin(), fallback.end());
+                h->pending_fallback_t.insert(h->pending_fallback_t.end(), fallback_t.begin(), fallback_t.end());
+            }
+        } else {
+            fallback.insert(fallback.end(), h->pending_fallback.begin(), h->pending_fallback.end());
+            fallback_t.insert(fallback_t.end(), h->pending_fallback_t.begin(), h->pending_fallback_t.end());
+            h->pending_fallback.clear();
+            h->pending_fallback_t.clear();
+            todo.swap(fallback);
+            tmult.swap(fallback_t);
+            if (!todo.empty()) newpath = false;
+        }
     }
+    h->pending_fallback.clear();
+    h->pending_fallback_t.clear();
     if (!todo.empty()) {
         set_error("early-stop bound did not converge for %zu file(s)", todo.size());
         return GSB_ERR_CUDA;

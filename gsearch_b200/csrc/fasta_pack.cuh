@@ -236,6 +236,26 @@ __device__ __forceinline__ void fold16(const uint8_t *p /* own 16 bytes; p[-1], 
 __device__ __forceinline__ uint32_t block_scan_fn(uint32_t f, uint32_t *warp_tot /* 8 */,
                                                   uint32_t *total) {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    // The common tile has no record start and no "capsid" text: every thread's function is then the
+    // identity (no newline in its 16 bytes) or A: s -> s & 2 (a newline ends the header).  A is
+    // idempotent and absorbs the identity, so the exclusive prefix is "A iff an earlier thread saw
+    // a newline": one ballot per warp instead of a scan of function compositions.
+    constexpr uint32_t kFnNl = kFnIdent & 0xAAu;
+    if (__syncthreads_and(f == kFnIdent || f == kFnNl)) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, f == kFnNl);
+        if (lane == 0) warp_tot[warp] = bal;
+        __syncthreads();
+        uint32_t before = bal & ((1u << lane) - 1u), any = 0;
+#pragma unroll
+        for (int w = 0; w < kK1Threads / 32; w++) {
+            const uint32_t v = warp_tot[w];
+            if ((uint32_t)w < warp) before |= v;
+            any |= v;
+        }
+        if (total) *total = any ? kFnNl : kFnIdent;
+        __syncthreads();
+        return before ? kFnNl : kFnIdent;
+    }
     uint32_t incl = f;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

@@ -14,49 +14,6 @@ namespace gsb {
 
 constexpr int kHamThreads = 512;
 
-// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ----
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-                 "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(phase)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    while (!mbar_try_wait(bar, phase)) {
-    }
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
-                                             uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            (uint32_t)__cvta_generic_to_shared(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-        : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 // stage `bytes` (multiple of 16, 16-byte aligned source) into shared memory with TMA bulk
 // copies of at most 64 KiB each; all threads return after the data has landed
 __device__ __forceinline__ void stage_query(uint8_t *smem_q, const uint8_t *gq, uint32_t bytes,

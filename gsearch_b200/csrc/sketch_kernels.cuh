@@ -40,7 +40,8 @@ constexpr uint32_t kNoSlot = 0xFFFFFFFFu;         // list entry of a k-mer that 
 struct ListEntry {
     uint64_t kmer;
     uint32_t slot;
-    uint32_t kind;  // 0 = light (first occurrence, first draw below T), 1 = repeated
+    uint32_t kind;  // 0 = light (first occurrence, first draw below T), 1 = repeated,
+                    // 2 = from the partition path (prob_partition.cuh): `slot` is the weight itself
 };
 
 // per-genome device-side job state for the prob path
@@ -64,6 +65,11 @@ struct ProbJob {
     unsigned long long *hmin;  // [m] ordered bits of min h per slot
     unsigned long long *sigw;  // [m] winning k-mer per slot
     double tmult;        // early-stop bound multiplier (1 = default, grown on retry)
+    // partition path (prob_partition.cuh)
+    void *buckets;       // [kNB][cap_g] keys
+    uint32_t *cursor;    // [kNB] keys appended to each bucket
+    uint32_t cap_g;      // capacity of one bucket array
+    uint32_t newpath;    // 1: this job runs the partition path (no extra-occurrence counters to clear)
 };
 
 struct ProbBound {  // written by k_prob_reset
@@ -106,7 +112,9 @@ __device__ __forceinline__ uint64_t dna_extract(const uint32_t *__restrict__ w, 
     return nb ? (hi >> (64 - 2 * nb)) : 0ull;
 }
 
-template <typename KT>
+// KC > 0 fixes k at compile time (constant shifts and masks in the rolling update); KC = 0 reads it
+// from the arguments
+template <typename KT, int KC = 0>
 struct SrcDNA {
     uint64_t nw;  // the next bases to enter the window, first one in the top two bits
     KT fw, rc, mask;
@@ -115,7 +123,7 @@ struct SrcDNA {
     uint32_t nbounds, N;
 
     __device__ __forceinline__ void init(const SeqView &sv, uint32_t p0_, uint32_t k_) {
-        k = k_;
+        k = KC ? (uint32_t)KC : k_;
         p0 = p0_;
         N = sv.N;
         bounds = sv.bounds;
@@ -144,13 +152,15 @@ struct SrcDNA {
     __device__ __forceinline__ void roll(KT &canon) {
         const uint32_t b = (uint32_t)(nw >> 62);
         nw <<= 2;
-        fw = (KT)(((fw << 2) | b) & mask);
-        rc = (KT)((rc >> 2) | ((KT)(3u - b) << (2 * (k - 1))));
+        const uint32_t kk = KC ? (uint32_t)KC : k;
+        const KT m = KC ? (KT)((KC >= 32) ? ~0ull : ((1ull << (2 * (KC ? KC : 1))) - 1)) : mask;
+        fw = (KT)(((fw << 2) | b) & m);
+        rc = (KT)((rc >> 2) | ((KT)(3u - b) << (2 * (kk - 1))));
         canon = fw < rc ? fw : rc;
     }
     // true if the k-mers starting at p0+i0 .. p0+i0+n-1 are all inside one record
     __device__ __forceinline__ bool all_valid(uint32_t i0, uint32_t n) const {
-        return p0 + i0 + n - 1 + k <= nb;  // nb <= N always
+        return p0 + i0 + n - 1 + (KC ? (uint32_t)KC : k) <= nb;  // nb <= N always
     }
     // advance to the k-mer starting at p0 + i (steps must be taken in order); returns false
     // if it crosses a record boundary or the end of the sequence
@@ -162,7 +172,8 @@ struct SrcDNA {
             nb = bi < nbounds ? __ldg(&bounds[bi]) : N;
             if (bi >= nbounds) break;
         }
-        return pos + k <= nb && pos + k <= N;
+        const uint32_t kk = KC ? (uint32_t)KC : k;
+        return pos + kk <= nb && pos + kk <= N;
     }
     // same, when all_valid() held for the block containing i
     __device__ __forceinline__ bool step_fast(uint32_t, KT &canon) {
@@ -623,10 +634,16 @@ k3_prob_points(const ProbJob *__restrict__ jobs, uint32_t njobs,
     const double T = bound[j].T;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const ListEntry le = job.list[e];
-        const uint32_t extra = le.slot == kNoSlot ? 0u : job.cnt[le.slot];
-        if (le.kind == 0 && extra != 0) continue;  // handled through its "repeated" entry
+        uint32_t w;
+        if (le.kind == 2) {
+            w = le.slot;
+        } else {
+            const uint32_t extra = le.slot == kNoSlot ? 0u : job.cnt[le.slot];
+            if (le.kind == 0 && extra != 0) continue;  // handled through its "repeated" entry
+            w = 1u + extra;
+        }
         const KT d = (KT)le.kmer;
-        pmh_points<KT>(d, 1u + extra, T, sc, [&](double h, uint32_t k) {
+        pmh_points<KT>(d, w, T, sc, [&](double h, uint32_t k) {
             const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
             if (PASS == 0) {
                 atomicMin(&job.hmin[k], hb);
@@ -668,7 +685,7 @@ k3_prob_finalize(const ProbJob *__restrict__ jobs, uint32_t njobs,
         // the extra-occurrence counters touched by this genome are cleared by the slot's next
         // k_prob_reset (full grid) from the list left here
         const uint32_t n = *job.list_n;
-        *job.prev_n = n > job.list_cap ? job.list_cap : n;
+        *job.prev_n = job.newpath ? 0u : (n > job.list_cap ? job.list_cap : n);
     }
 }
 

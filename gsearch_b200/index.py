@@ -100,6 +100,13 @@ class Hnsw:
                                                      p(neval)))
         return out, counts, neval
 
+    def search_device(self, d_queries_ptr, nq, knbn, ef, d_out_ptr, d_counts_ptr, d_nb_eval_ptr=0):
+        """gsb_index_search_batch_dev: queries and results in device memory (raw pointers); out is
+        nq x knbn gsb_neighbour (24 B each), counts nq x u32, nb_eval nq x u64 (optional)"""
+        _lib.check(_lib.lib().gsb_index_search_batch_dev(self._h, C.c_void_p(d_queries_ptr), nq, knbn, ef,
+                                                         C.c_void_p(d_out_ptr), C.c_void_p(d_counts_ptr),
+                                                         C.c_void_p(d_nb_eval_ptr) if d_nb_eval_ptr else C.c_void_p(0)))
+
     def parallel_search(self, queries, knbn, ef):
         """parallel_search(&[Vec<Sig>], knbn, ef) -> Vec<Vec<Neighbour>>"""
         out, counts, _ = self.search_raw(queries, knbn, ef)

@@ -80,6 +80,15 @@ class Sketcher:
     def retry_count(self):
         return _lib.lib().gsb_sketcher_retry_count(self._h)
 
+    @property
+    def fallback_count(self):
+        """genomes the partition path handed to the general filter path (ProbMinHash only)"""
+        return _lib.lib().gsb_sketcher_fallback_count(self._h)
+
+    def set_prob_path(self, path):
+        """0 = partition path (filter path as fallback), 1 = filter path only"""
+        _lib.check(_lib.lib().gsb_sketcher_set_prob_path(self._h, int(path)))
+
     def enable_timing(self, on=True):
         _lib.lib().gsb_sketcher_enable_timing(self._h, 1 if on else 0)
 

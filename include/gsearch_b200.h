@@ -148,6 +148,13 @@ GSB_API int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_bytes,
 GSB_API uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h);
 /* number of genomes whose early-stop bound had to be widened and re-run so far */
 GSB_API uint64_t gsb_sketcher_retry_count(const gsb_sketcher *h);
+/* number of genomes the ProbMinHash partition path handed to the general filter path so far (a
+ * bucket array or a counting round overflowed: very large or very repetitive inputs) */
+GSB_API uint64_t gsb_sketcher_fallback_count(const gsb_sketcher *h);
+/* ProbMinHash multiplicity counting: 0 (default) = hash-partition + shared-memory counting, with the
+ * filter path as the fallback for the files it flags; 1 = filter path only (also GSB_PROB_PATH=filter).
+ * Both are exact; the switch exists for tests and measurements. */
+GSB_API int gsb_sketcher_set_prob_path(gsb_sketcher *h, int path);
 /* Optional device timing of the kernel families (CUDA events on the launching stream):
  * index 0 = K1 FASTA pack, 1 = K2 k-mer scan (the dominant kernel family), 2 = K3 slot
  * update + finalize, 3 = per-group reset; 4..6 split K2 into its filter-mark, classify and
@@ -224,6 +231,12 @@ GSB_API int gsb_index_insert_batch_dev(gsb_index *idx, const void *d_sigs, const
 GSB_API int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t nq,
                                    uint32_t knbn, uint32_t ef, gsb_neighbour *out,
                                    uint32_t *counts_out, uint64_t *nb_eval_out);
+/* same with queries and all three outputs in DEVICE memory (the query signatures straight from
+ * the sketcher; results for a device-side gather).  Returns after the index stream has been
+ * synchronised.                                                                            */
+GSB_API int gsb_index_search_batch_dev(gsb_index *idx, const void *d_queries, uint32_t nq,
+                                       uint32_t knbn, uint32_t ef, gsb_neighbour *d_out,
+                                       uint32_t *d_counts_out, uint64_t *d_nb_eval_out);
 /* get_nb_point() */
 GSB_API uint64_t gsb_index_nb_point(const gsb_index *idx);
 /* Load an externally built graph (CSR-like image) so a graph built elsewhere

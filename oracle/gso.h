@@ -126,6 +126,9 @@ int gso_hnsw_insert(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t
  * wave_max = 1 is identical to gso_hnsw_insert */
 int gso_hnsw_insert_waves(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
                           uint32_t wave_max);
+/* same graph, phase A of every wave on `nthreads` host threads */
+int gso_hnsw_insert_waves_mt(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
+                             uint32_t wave_max, int nthreads);
 uint32_t gso_hnsw_wave_size(uint64_t nb_point, uint32_t wave_max);
 uint64_t gso_hnsw_nb_point(const gso_hnsw *h);
 uint64_t gso_hnsw_nb_eval(const gso_hnsw *h); /* distance evaluations so far */

@@ -28,6 +28,9 @@
  * discovery order, and neighbour lists are sorted by (distance, internal index).
  */
 #include "gso.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <math.h>
 #include <stdlib.h>
@@ -603,6 +606,85 @@ int gso_hnsw_insert_waves(gso_hnsw *h, const void *sigs, const uint64_t *ids, ui
     free(selbuf);
     free(ret.a);
     free(cand.a);
+    return rc;
+}
+
+/* The same wave insertion with phase A spread over host threads (one point per task): phase A
+ * only READS the pre-wave graph and the signatures / levels of the wave, so every worker runs it
+ * on a private shallow copy of the handle (own visited stamps, heaps, eval counter) and the graph
+ * that comes out is bit-identical to gso_hnsw_insert_waves.  This is how bench.py's CPU reference
+ * arm builds its index within minutes (the reference's parallel_insert is multi-threaded too,
+ * src/dna/dnasketch.rs:435). */
+int gso_hnsw_insert_waves_mt(gso_hnsw *h, const void *sigs, const uint64_t *ids, uint64_t n,
+                             uint32_t wave_max, int nthreads) {
+    if (nthreads <= 1) return gso_hnsw_insert_waves(h, sigs, ids, n, wave_max);
+    if (h->n + n > h->capacity) return 8;
+    if (grow(h, h->n + n)) return 4; /* no reallocation while workers hold copies of the handle */
+    if (wave_max < 1) wave_max = 1;
+    const uint64_t cap = h->cap_pts;
+    uint32_t **tstamp = (uint32_t **)calloc((size_t)nthreads, sizeof(uint32_t *));
+    uint32_t *tcur = (uint32_t *)calloc((size_t)nthreads, sizeof(uint32_t));
+    heap *tret = (heap *)calloc((size_t)nthreads, sizeof(heap));
+    heap *tcand = (heap *)calloc((size_t)nthreads, sizeof(heap));
+    sel **tsel = (sel **)calloc((size_t)nthreads, sizeof(sel *));
+    uint64_t *teval = (uint64_t *)calloc((size_t)nthreads, sizeof(uint64_t));
+    for (int t = 0; t < nthreads; t++) {
+        tstamp[t] = (uint32_t *)calloc(cap, sizeof(uint32_t));
+        tsel[t] = (sel *)malloc((2 * h->M + 2) * sizeof(sel));
+    }
+    int rc = 0;
+    uint64_t i = 0;
+    while (i < n && !rc) {
+        if (h->entry < 0) {
+            rc = add_point(h, (const uint8_t *)sigs + i * h->row, ids[i]);
+            if (!rc) h->entry = (int64_t)(h->n - 1);
+            i++;
+            continue;
+        }
+        uint64_t W = gso_hnsw_wave_size(h->n, wave_max);
+        if (W > n - i) W = n - i;
+        const uint32_t first = (uint32_t)h->n;
+        for (uint64_t t = 0; t < W && !rc; t++)
+            rc = add_point(h, (const uint8_t *)sigs + (i + t) * h->row, ids[i + t]);
+        if (rc) break;
+        wave_sel *ws = (wave_sel *)calloc(W, sizeof(wave_sel));
+        const uint32_t entry = (uint32_t)h->entry;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+        for (int64_t t = 0; t < (int64_t)W; t++) {
+#ifdef _OPENMP
+            const int me = omp_get_thread_num();
+#else
+            const int me = 0;
+#endif
+            gso_hnsw local = *h;
+            local.stamp = tstamp[me];
+            local.cur_stamp = tcur[me];
+            local.nb_eval = 0;
+            wave_phase_a(&local, first + (uint32_t)t, first, entry, &tret[me], &tcand[me], tsel[me], &ws[t]);
+            tcur[me] = local.cur_stamp;
+            teval[me] += local.nb_eval;
+        }
+        for (uint64_t t = 0; t < W; t++) wave_phase_b_own(h, first + (uint32_t)t, &ws[t]);
+        for (uint64_t t = 0; t < W; t++) {
+            wave_phase_b_reverse(h, first + (uint32_t)t, &ws[t]);
+            for (int l = 0; l < 17; l++) free(ws[t].l[l]);
+        }
+        free(ws);
+        i += W;
+    }
+    for (int t = 0; t < nthreads; t++) {
+        h->nb_eval += teval[t];
+        free(tstamp[t]);
+        free(tsel[t]);
+        free(tret[t].a);
+        free(tcand[t].a);
+    }
+    free(tstamp);
+    free(tcur);
+    free(tret);
+    free(tcand);
+    free(tsel);
+    free(teval);
     return rc;
 }
 

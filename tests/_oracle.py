@@ -65,6 +65,7 @@ def L():
         lib.gso_hnsw_free.argtypes = [C.c_void_p]
         lib.gso_hnsw_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.gso_hnsw_insert_waves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        lib.gso_hnsw_insert_waves_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int]
         lib.gso_hnsw_wave_size.argtypes = [C.c_uint64, C.c_uint32]
         lib.gso_hnsw_wave_size.restype = C.c_uint32
         lib.gso_hnsw_nb_point.restype = C.c_uint64
@@ -221,10 +222,15 @@ class Hnsw:
         rc = L().gso_hnsw_insert(self.h, _p(sigs), _p(ids), len(ids))
         assert rc == 0, rc
 
-    def insert_waves(self, sigs, ids, wave_max):
+    def insert_waves(self, sigs, ids, wave_max, nthreads=1):
+        """deterministic wave insertion; nthreads > 1 spreads phase A of each wave over host threads
+        (same graph)"""
         sigs = np.ascontiguousarray(sigs, dtype=self.dtype)
         ids = np.ascontiguousarray(ids, dtype=np.uint64)
-        rc = L().gso_hnsw_insert_waves(self.h, _p(sigs), _p(ids), len(ids), wave_max)
+        if nthreads > 1:
+            rc = L().gso_hnsw_insert_waves_mt(self.h, _p(sigs), _p(ids), len(ids), wave_max, nthreads)
+        else:
+            rc = L().gso_hnsw_insert_waves(self.h, _p(sigs), _p(ids), len(ids), wave_max)
         assert rc == 0, rc
 
     def import_graph(self, sigs, gr):

@@ -269,6 +269,24 @@ def test_hnsw_wave_insert_of_one_is_sequential_insert(oracle):
         assert np.array_equal(ga[k], gb[k]), k
 
 
+def test_hnsw_wave_insert_threads_build_the_same_graph(oracle):
+    """gso_hnsw_insert_waves_mt (phase A of a wave spread over host threads: how bench.py's CPU
+    reference arm builds its index) must produce the single-threaded graph bit for bit, and the
+    same evaluation count."""
+    base = _tree_sigs(600, 96, seed=11)
+    ids = np.arange(600, dtype=np.uint64)
+    a = oracle.Hnsw(8, 40, 96, np.uint64)
+    a.insert_waves(base[:250], ids[:250], 37)    # (a call boundary ends a wave: same calls on both sides)
+    a.insert_waves(base[250:], ids[250:], 37)
+    b = oracle.Hnsw(8, 40, 96, np.uint64)
+    b.insert_waves(base[:250], ids[:250], 37, nthreads=4)
+    b.insert_waves(base[250:], ids[250:], 37, nthreads=3)   # second call: grown buffers, warm stamps
+    ga, gb = a.export(), b.export()
+    assert ga["entry_point"] == gb["entry_point"] and a.nb_eval() == b.nb_eval()
+    for k in ("levels", "ranks", "ids", "nbr_offsets", "nbr_index", "nbr_dist"):
+        assert np.array_equal(ga[k], gb[k]), k
+
+
 def test_hnsw_wave_insert_keeps_recall(oracle):
     """Points of one wave do not see each other's lists, only each other's data; recall against
     brute force must stay at the level of the sequential build."""

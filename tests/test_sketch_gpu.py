@@ -10,8 +10,18 @@ pytestmark = pytest.mark.gpu
 
 
 def run_both(oracle, files, k, S, algo=g.ALGO_PROB3A, data_t=g.DATA_DNA, block=False, spec=0):
+    """CUDA vs oracle.  ProbMinHash has two exact multiplicity-counting paths on the device (hash
+    partition + shared-memory counting, and the L2 filter that is its fallback): both are run and
+    must give the same bytes."""
     sk = g.Sketcher(g.SeqSketcherParams(k, S, algo, data_t, block, spec))
     got, nb = sk.sketch_files(files)
+    if algo == g.ALGO_PROB3A:
+        sk.set_prob_path(1)
+        got1, nb1 = sk.sketch_files(files)
+        assert got1.tobytes() == got.tobytes() and nb1.tolist() == nb.tolist(), "the two prob paths differ"
+        sk.set_prob_path(0)
+        got2, _ = sk.sketch_files(files)   # and back, on slots the filter path has used
+        assert got2.tobytes() == got.tobytes()
     want, wnb = oracle.sketch_files(files, k, S, algo, data_t, block, spec, nthreads=8)
     sk.close()
     return got, nb, want, wnb
@@ -46,6 +56,33 @@ def test_prob_dna_baseline_config1_shape(oracle):
     # BASELINE configs[1] per-genome shape: 5 Mbp, k=21, s=18000 (2 genomes)
     files = [g.synth.dna_genome(i, 5_000_000) for i in (0, 1)]
     assert_same(*run_both(oracle, files, 21, 18000))
+
+
+def test_prob_partition_path_is_the_one_that_runs(oracle):
+    """ordinary genomes stay on the partition path (no fallback, no retry); a file that cannot fit
+    its geometry (one k-mer filling a whole tile) is handed to the filter path and still exact"""
+    files = [g.synth.dna_genome(i, 1_000_000, ncontigs=1 + i) for i in range(3)]
+    sk = g.Sketcher(g.SeqSketcherParams(21, 4096))
+    got, nb = sk.sketch_files(files)
+    assert sk.fallback_count == 0 and sk.retry_count == 0
+    want, wnb = oracle.sketch_files(files, 21, 4096, nthreads=8)
+    assert_same(got, nb, want, wnb)
+    rep = [fasta([("poly", "A" * 60000)]), files[0]]
+    got, nb = sk.sketch_files(rep)
+    assert sk.fallback_count == 1
+    want, wnb = oracle.sketch_files(rep, 21, 4096, nthreads=8)
+    assert_same(got, nb, want, wnb)
+    sk.close()
+
+
+def test_prob_partition_large_k_uses_64_bit_keys(oracle):
+    # k = 31 (62-bit k-mers): keys do not fit 31 bits -> the 64-bit key instantiation
+    files = [g.synth.dna_genome(40 + i, 300_000) for i in range(2)]
+    sk = g.Sketcher(g.SeqSketcherParams(31, 2000))
+    got, nb = sk.sketch_files(files)
+    assert sk.fallback_count == 0
+    assert_same(got, nb, *oracle.sketch_files(files, 31, 2000, nthreads=8))
+    sk.close()
 
 
 def test_prob_heavy_repeats(oracle):
