@@ -15,3 +15,4 @@ from .sketcher import Sketcher  # noqa: F401
 from .distance import DistHamming  # noqa: F401
 from .index import Hnsw, Neighbour  # noqa: F401
 from . import synth  # noqa: F401
+from . import comm  # noqa: F401

@@ -41,12 +41,17 @@ SYMBOLS = {
     "gsb_sketcher_elem_size": (_u32, [_vp]),
     "gsb_sketch_fasta_batch": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "gsb_sketch_fasta_batch_dev": (_int, [_vp, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "gsb_sketch_fasta_batch_to_dev": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "gsb_sketcher_launch_count": (_u64, [_vp]),
     "gsb_sketcher_retry_count": (_u64, [_vp]),
     "gsb_sketcher_fallback_count": (_u64, [_vp]),
     "gsb_sketcher_set_prob_path": (_int, [_vp, _int]),
     "gsb_sketcher_enable_timing": (None, [_vp, _int]),
     "gsb_sketcher_kernel_times": (None, [_vp, _vp, _vp]),
+    "gsb_dist_hamming_u16": (C.c_float, [_vp, _vp, C.c_ulonglong]),
+    "gsb_dist_hamming_u32": (C.c_float, [_vp, _vp, C.c_ulonglong]),
+    "gsb_dist_hamming_u64": (C.c_float, [_vp, _vp, C.c_ulonglong]),
+    "gsb_dist_hamming_f32": (C.c_float, [_vp, _vp, C.c_ulonglong]),
     "gsb_hamming_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _int]),
     "gsb_hamming_matrix": (_int, [_vp, _u32, _vp, _u32, _u32, _u32, _vp, _int]),
     "gsb_hamming_matrix_dev": (_int, [_vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp]),
@@ -56,6 +61,21 @@ SYMBOLS = {
     "gsb_index_insert_batch_dev": (_int, [_vp, _vp, _vp, _u64]),
     "gsb_index_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "gsb_index_search_batch_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "gsb_index_insert_batch_sharded": (_int, [_vp, _vp, _vp, _vp, _u64]),
+    "gsb_comm_unique_id": (_int, [_vp]),
+    "gsb_comm_create": (_int, [_vp, _int, _int, _int, C.POINTER(_vp)]),
+    "gsb_comm_destroy": (None, [_vp]),
+    "gsb_comm_rank": (_int, [_vp]),
+    "gsb_comm_size": (_int, [_vp]),
+    "gsb_comm_all_gather": (_int, [_vp, _vp, _vp, _u64, _vp]),
+    "gsb_comm_broadcast": (_int, [_vp, _vp, _u64, _int, _vp]),
+    "gsb_comm_all_gather_rows": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp]),
+    "gsb_device_malloc": (_int, [_int, _u64, C.POINTER(_vp)]),
+    "gsb_device_free": (None, [_int, _vp]),
+    "gsb_memcpy_h2d": (_int, [_int, _vp, _vp, _u64]),
+    "gsb_memcpy_d2h": (_int, [_int, _vp, _vp, _u64]),
+    "gsb_host_alloc_pinned": (_int, [_u64, C.POINTER(_vp)]),
+    "gsb_host_free_pinned": (None, [_vp]),
     "gsb_index_nb_point": (_u64, [_vp]),
     "gsb_index_load_graph": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64]),
     "gsb_index_graph_sizes": (_int, [_vp, _vp, _vp]),

@@ -1,6 +1,8 @@
 """`gsearch` command line over the B200 path: the reference's tohnsw / add / request sub-commands
-with the same flags, file names and text formats (src/bin/gsearch.rs:417-587), so that a user of
-the reference can switch binaries.  Host side only walks directories, inflates files and writes
+with the same flags, file names and text formats (src/bin/gsearch.rs:417-587).  The side files
+(seqdict.json, parameters.json, processing_state.json, gsearch.neighbors.txt) are byte-compatible
+with the reference's; hnswdump.hnsw.{graph,data} keep the reference's NAMES but this library's own
+layout, so a database is served by the binary that built it.  Host side only walks directories, inflates files and writes
 JSON / text; sketching, HNSW construction and search all run in libgsearch_b200.so on the GPU.
 
   gsearch [--pio N] [--nbthreads N] tohnsw -d DIR -k K -s S -n NBNG [--ef EF]
@@ -129,25 +131,62 @@ def read_all(paths, nbthreads):
         return list(ex.map(read_inflated, paths))
 
 
-def sketch_directory(g, directory, p, pio, device=0, nbthreads=0):
-    files = walk_fasta(directory, p["aa"])
-    if not files:
-        raise SystemExit(f"no fasta file found in {directory}")
-    algo = g.SeqSketcherParams.algo_from_name(p["algo"]) if hasattr(g.SeqSketcherParams, "algo_from_name") else \
-        {"prob": g.ALGO_PROB3A, "super": g.ALGO_SUPER, "optdens": g.ALGO_OPTDENS}[p["algo"]]
-    sk = g.Sketcher(g.SeqSketcherParams(p["kmer"], p["sketch"], algo, g.DATA_AA if p["aa"] else g.DATA_DNA,
-                                        bool(p["block"])), device=device)
-    sigs, items = [], []
-    batch = max(1, min(pio, 256))
-    for b in range(0, len(files), batch):
-        chunk = files[b:b + batch]
-        sig, nb = sk.sketch_files(read_all(chunk, nbthreads or (os.cpu_count() or 1)))
-        sigs.append(sig)
-        # ItemDict ids: seq mode keeps an empty fasta_id (src/dna/dnafiles.rs:86-93), block mode the
-        # literal "-total-sequence" (src/dna/dnafiles.rs:268-272)
-        fid = "-total-sequence" if p["block"] else ""
-        items += [(f, fid, int(n)) for f, n in zip(chunk, nb)]
-    return np.concatenate(sigs), items, sk.dtype
+def algo_id(g, name):
+    """--algo names as the reference spells them (src/bin/gsearch.rs:181-196); the library rejects the
+    ones that are not built with GSB_ERR_UNSUPPORTED and says so"""
+    return g.SeqSketcherParams.algo_from_cli(name)
+
+
+class DeviceSignatures:
+    """signatures of a list of files, sketched on one GPU and LEFT on it (n x S, row i = file i):
+    the files are read and inflated by host threads into a pinned staging buffer, the library copies
+    them to the device under its kernels, and the result never visits host memory -- it feeds
+    gsb_index_insert_batch_dev / gsb_index_search_batch_dev or the all-gather directly"""
+
+    def __init__(self, g, files, p, pio, device=0, nbthreads=0, rows=None):
+        from .comm import DeviceBuffer, PinnedBuffer
+        self.g, self.files, self.device = g, files, device
+        self.sk = g.Sketcher(g.SeqSketcherParams(p["kmer"], p["sketch"], algo_id(g, p["algo"]),
+                                                 g.DATA_AA if p["aa"] else g.DATA_DNA, bool(p["block"])), device=device)
+        self.dtype = self.sk.dtype
+        self.row = p["sketch"] * self.sk.elem_size
+        self.rows = max(len(files), 1) if rows is None else max(rows, 1)
+        self.d_sig = DeviceBuffer(self.rows * self.row, device)
+        self.d_nb = DeviceBuffer(self.rows * 8, device)
+        self.d_nb.upload(np.zeros(self.rows, dtype=np.uint64))
+        batch = max(1, min(pio, 256))
+        pinned = None
+        threads = nbthreads or (os.cpu_count() or 1)
+        for b in range(0, len(files), batch):
+            blobs = read_all(files[b:b + batch], threads)
+            total = sum(len(x) for x in blobs)
+            if pinned is None or pinned.nbytes < total:
+                if pinned is not None:
+                    pinned.free()
+                pinned = PinnedBuffer(int(total * 1.25) + 4096)
+            offs = np.zeros(len(blobs) + 1, dtype=np.uint64)
+            pos = 0
+            for i, x in enumerate(blobs):
+                pinned.array[pos:pos + len(x)] = np.frombuffer(x, dtype=np.uint8)
+                pos += len(x)
+                offs[i + 1] = pos
+            self.sk.sketch_buffer_to_device(pinned.array, offs, self.d_sig.ptr + b * self.row, self.d_nb.ptr + b * 8)
+        if pinned is not None:
+            pinned.free()
+
+    def nb_bases(self, n=None):
+        return self.d_nb.download(np.uint64, self.rows)[:len(self.files) if n is None else n]
+
+    def host_signatures(self):
+        n = len(self.files)
+        S = self.row // np.dtype(self.dtype).itemsize
+        return self.d_sig.download(self.dtype, n * S).reshape(n, S)
+
+
+def item_of(path, nb, block):
+    # ItemDict ids: seq mode keeps an empty fasta_id (src/dna/dnafiles.rs:86-93), block mode the
+    # literal "-total-sequence" (src/dna/dnafiles.rs:268-272)
+    return (path, "-total-sequence" if block else "", int(nb))
 
 
 def open_index(g, p, dtype, device=0):
@@ -163,54 +202,171 @@ def dumpall(idx, dirpath, seqdict, p, nb_file, elapsed):
     dump_state(dirpath, len(seqdict), nb_file, elapsed)
 
 
-def cmd_tohnsw(a):
+WAVE_PER_GPU = 296   # one insertion wave = two points per SM of every GPU (capped by the library)
+WAVE_CAP = 512
+
+
+def build_worker(rank, world, uid, files, p, pio, nbthreads, load_dir, out_dir, first_id, result_q):
+    """one process per GPU: sketch this rank's files (file i -> rank i mod world), all-gather the
+    signatures in file order, insert them (sharded by point inside every wave) and, on rank 0, dump"""
     import gsearch_b200 as g
+    from .comm import Comm, DeviceBuffer, shard_rows
+    t0 = time.time()
+    n = len(files)
+    per = shard_rows(n, world)
+    local = DeviceSignatures(g, files[rank::world], p, pio, device=rank, nbthreads=nbthreads, rows=per)
+    t1 = time.time()
+    comm = None
+    if world > 1:
+        comm = Comm(uid, world, rank, rank)
+        d_tmp = DeviceBuffer(world * per * local.row, rank)
+        d_all = DeviceBuffer(n * local.row, rank)
+        comm.all_gather_rows(local.d_sig.ptr, per, local.row, n, d_tmp.ptr, d_all.ptr)
+        d_nb_all = DeviceBuffer(n * 8, rank)
+        comm.all_gather_rows(local.d_nb.ptr, per, 8, n, d_tmp.ptr, d_nb_all.ptr)
+        nb = d_nb_all.download(np.uint64, n)
+        d_tmp.free()
+        local.d_sig.free()
+    else:
+        d_all, nb = local.d_sig, local.nb_bases()
+    idx = open_index(g, p, local.dtype, device=rank)
+    if load_dir is not None:
+        idx.load(load_dir, "hnswdump")
+        assert idx.get_nb_point() == first_id                       # src/dna/dnasketch.rs:438
+    ids = np.arange(first_id, first_id + n, dtype=np.uint64)
+    if world > 1:
+        idx.set_wave_max(min(WAVE_CAP, WAVE_PER_GPU * world))
+        idx.insert_sharded(comm, d_all.ptr, ids)
+    else:
+        idx.insert_device(d_all.ptr, ids)
+    t2 = time.time()
+    if rank == 0:
+        idx.file_dump(out_dir, "hnswdump")
+        result_q.put(([item_of(f, nb[i], p["block"]) for i, f in enumerate(files)], t1 - t0, t2 - t1))
+    if comm is not None:
+        comm.close()
+
+
+def run_build(a, files, p, load_dir, out_dir, first_id):
+    """-> (items of the new files, sketch seconds, insertion seconds); hnswdump.* written to out_dir"""
+    world = max(1, a.gpus)
+    if world == 1:
+        import queue
+        q = queue.Queue()
+        build_worker(0, 1, None, files, p, a.pio, a.nbthreads, load_dir, out_dir, first_id, q)
+        return q.get()
+    import multiprocessing as mp
+    import gsearch_b200 as g
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    uid = g.comm.unique_id()
+    procs = [ctx.Process(target=build_worker, args=(r, world, uid, files, p, a.pio, a.nbthreads, load_dir, out_dir,
+                                                    first_id, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    items, ts, ti = q.get()
+    for pr in procs:
+        pr.join()
+        if pr.exitcode != 0:
+            raise SystemExit(f"a GPU worker failed (exit code {pr.exitcode})")
+    return items, ts, ti
+
+
+def cmd_tohnsw(a):
     p = {"capacity": 1_500_000, "ef": a.ef, "nbng": a.nbng & 0xFF, "scale": a.scale_modify_f, "kmer": a.kmer,
          "sketch": a.sketch, "algo": a.algo, "aa": a.aa, "block": a.block}   # `nbng as u8`, gsearch.rs:268
+    files = walk_fasta(a.dir, p["aa"])
+    if not files:
+        raise SystemExit(f"no fasta file found in {a.dir}")
     t0 = time.time()
-    sig, items, dtype = sketch_directory(g, a.dir, p, a.pio, nbthreads=a.nbthreads)
-    t1 = time.time()
-    idx = open_index(g, p, dtype)
-    idx.parallel_insert(sig, np.arange(len(items), dtype=np.uint64))
-    t2 = time.time()
-    dumpall(idx, ".", items, p, len(items), t2 - t0)
-    print(f"tohnsw: {len(items)} files, sketch {t1 - t0:.2f} s, hnsw insertion {t2 - t1:.2f} s")
+    items, ts, ti = run_build(a, files, p, None, ".", 0)
+    dump_seqdict(".", items)
+    dump_parameters(".", p)
+    dump_state(".", len(items), len(items), time.time() - t0)
+    print(f"tohnsw: {len(items)} files on {max(1, a.gpus)} GPU(s), sketch {ts:.2f} s, hnsw insertion {ti:.2f} s")
 
 
 def cmd_add(a):
-    import gsearch_b200 as g
     p = reload_parameters(a.hnsw)
     seqdict = reload_seqdict(a.hnsw)
+    files = walk_fasta(a.new, p["aa"])
+    if not files:
+        raise SystemExit(f"no fasta file found in {a.new}")
     t0 = time.time()
-    sig, items, dtype = sketch_directory(g, a.new, p, a.pio, nbthreads=a.nbthreads)
-    idx = open_index(g, p, dtype)
-    idx.load(a.hnsw, "hnswdump")
-    assert idx.get_nb_point() == len(seqdict)                       # src/dna/dnasketch.rs:438
-    idx.parallel_insert(sig, np.arange(len(seqdict), len(seqdict) + len(items), dtype=np.uint64))
+    items, ts, ti = run_build(a, files, p, a.hnsw, a.hnsw, len(seqdict))
     seqdict += items
-    dumpall(idx, a.hnsw, seqdict, p, len(seqdict), time.time() - t0)
+    dump_seqdict(a.hnsw, seqdict)
+    dump_parameters(a.hnsw, p)
+    dump_state(a.hnsw, len(seqdict), len(seqdict), time.time() - t0)
     print(f"add: {len(items)} new files, database now holds {len(seqdict)}")
 
 
-def cmd_request(a):
+def request_worker(rank, world, files, p, pio, nbthreads, dbdir, knbn, result_q):
+    """replicated index, query j -> rank j mod world (src/dna/dnarequest.rs:353: one query = one task);
+    query signatures go from the sketcher to the search kernel without leaving the device"""
     import gsearch_b200 as g
+    from .comm import DeviceBuffer
+    from .index import NEIGHBOUR_DTYPE
+    mine = files[rank::world]
+    q = DeviceSignatures(g, mine, p, pio, device=rank, nbthreads=nbthreads)
+    idx = open_index(g, p, q.dtype, device=rank)
+    idx.load(dbdir, "hnswdump")
+    nq = len(mine)
+    out = np.zeros((nq, knbn), dtype=NEIGHBOUR_DTYPE)
+    cnt = np.zeros(nq, dtype=np.uint32)
+    if nq:
+        d_out = DeviceBuffer(nq * knbn * NEIGHBOUR_DTYPE.itemsize, rank)
+        d_cnt = DeviceBuffer(nq * 4, rank)
+        idx.search_device(q.d_sig.ptr, nq, knbn, EF_SEARCH, d_out.ptr, d_cnt.ptr)
+        out = d_out.download(np.uint8, nq * knbn * NEIGHBOUR_DTYPE.itemsize).view(NEIGHBOUR_DTYPE).reshape(nq, knbn)
+        cnt = d_cnt.download(np.uint32, nq)
+    nb = q.nb_bases()
+    result_q.put((rank, [item_of(f, nb[i], p["block"]) for i, f in enumerate(mine)],
+                  out["d_id"].copy(), out["distance"].copy(), cnt))
+
+
+def cmd_request(a):
     p = reload_parameters(a.hnsw)
     seqdict = reload_seqdict(a.hnsw)
-    sig, items, dtype = sketch_directory(g, a.query, p, a.pio, nbthreads=a.nbthreads)
-    idx = open_index(g, p, dtype)
-    idx.load(a.hnsw, "hnswdump")
-    out, counts, _ = idx.search_raw(sig, a.nbanswers, EF_SEARCH)
+    files = walk_fasta(a.query, p["aa"])
+    if not files:
+        raise SystemExit(f"no fasta file found in {a.query}")
+    world = max(1, a.gpus)
+    if world == 1:
+        import queue
+        q = queue.Queue()
+        request_worker(0, 1, files, p, a.pio, a.nbthreads, a.hnsw, a.nbanswers, q)
+        parts = [q.get()]
+    else:
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=request_worker, args=(r, world, files, p, a.pio, a.nbthreads, a.hnsw,
+                                                          a.nbanswers, q)) for r in range(world)]
+        for pr in procs:
+            pr.start()
+        parts = [q.get() for _ in procs]
+        for pr in procs:
+            pr.join()
+            if pr.exitcode != 0:
+                raise SystemExit(f"a GPU worker failed (exit code {pr.exitcode})")
+    by_rank = {r: (items, ids, dd, cnt) for r, items, ids, dd, cnt in parts}
     with open("gsearch.neighbors.txt", "w") as f:
-        for r, item in enumerate(items):
-            nbrs = [(int(out["d_id"][r, j]), float(out["distance"][r, j])) for j in range(counts[r])]
-            f.write(format_answers(r, item, nbrs, seqdict))
-    print(f"request: {len(items)} queries answered in gsearch.neighbors.txt")
+        for j in range(len(files)):   # query order = file order, whatever the number of GPUs
+            items, ids, dd, cnt = by_rank[j % world]
+            t = j // world
+            nbrs = [(int(ids[t, i]), float(dd[t, i])) for i in range(cnt[t])]
+            f.write(format_answers(j, items[t], nbrs, seqdict))
+    print(f"request: {len(files)} queries answered in gsearch.neighbors.txt")
 
 
 def build_parser():
     ap = argparse.ArgumentParser(prog="gsearch", description="GSearch sketch-and-search path on B200")
     ap.add_argument("--pio", type=int, default=64, help="files read and sketched together")
     ap.add_argument("--nbthreads", type=int, default=0, help="host threads that read and inflate files (0 = all cores)")
+    ap.add_argument("--gpus", type=int, default=1, help="GPUs of this node (the only extension of the reference's "
+                                                       "command line): one process per GPU, NCCL all-gather of the "
+                                                       "signatures, HNSW insertion sharded inside every wave")
     sub = ap.add_subparsers(dest="cmd", required=True)
     t = sub.add_parser("tohnsw")
     t.add_argument("-d", "--dir", required=True)

@@ -3,6 +3,9 @@
 
 #include <new>
 
+#include <math.h>
+#include <stdlib.h>
+
 #include "api_common.h"
 #include "hamming.cuh"
 
@@ -165,4 +168,76 @@ extern "C" int gsb_hamming_matrix(const void *queries, uint32_t nq, const void *
 extern "C" int gsb_hamming_batch(const void *q, const void *cands, uint32_t n, uint32_t S, uint32_t sig_type,
                                  float *out, int device) {
     return gsb_hamming_matrix(q, 1, cands, n, S, sig_type, out, device);
+}
+
+// ---- scalar Distance::eval-shaped exports (anndists DistCFFI plug point [U]: `extern "C" fn(*const T,
+// *const T, len: u64) -> f32`).  A convenience: ONE pair per call, both rows travel to
+// device 0 (GSB_DEVICE overrides) and one K6 launch evaluates them -- correct and bit-identical to
+// the batched forms, but latency bound; anything hot should use gsb_hamming_matrix / the index.
+// Errors cannot be returned through this signature: the result is NaN and gsb_last_error() says why.
+static float dist_hamming_scalar(const void *a, const void *b, unsigned long long len, uint32_t sig_type) {
+    if (!a || !b || len == 0 || len > 0xFFFFFFFFull) {
+        set_error("gsb_dist_hamming: NULL argument or bad length %llu", len);
+        return nanf("");
+    }
+    static int device = -1;
+    if (device < 0) {
+        const char *e = getenv("GSB_DEVICE");
+        device = e ? atoi(e) : 0;
+    }
+    float out = nanf("");
+    if (gsb_hamming_matrix(a, 1, b, 1, (uint32_t)len, sig_type, &out, device) != GSB_OK) return nanf("");
+    return out;
+}
+extern "C" float gsb_dist_hamming_u16(const uint16_t *a, const uint16_t *b, unsigned long long len) {
+    return dist_hamming_scalar(a, b, len, GSB_SIG_U16);
+}
+extern "C" float gsb_dist_hamming_u32(const uint32_t *a, const uint32_t *b, unsigned long long len) {
+    return dist_hamming_scalar(a, b, len, GSB_SIG_U32);
+}
+extern "C" float gsb_dist_hamming_u64(const uint64_t *a, const uint64_t *b, unsigned long long len) {
+    return dist_hamming_scalar(a, b, len, GSB_SIG_U64);
+}
+extern "C" float gsb_dist_hamming_f32(const float *a, const float *b, unsigned long long len) {
+    return dist_hamming_scalar(a, b, len, GSB_SIG_F32);
+}
+
+// ---- device / pinned-host buffers for hosts that have no CUDA binding of their own (the Rust side
+// of INTEGRATION.md, gsearch_b200/cli.py): plain cudaMalloc / cudaMallocHost / cudaMemcpy
+extern "C" int gsb_device_malloc(int device, uint64_t bytes, void **out) {
+    if (!out) {
+        set_error("gsb_device_malloc: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    GSB_CUDA_TRY(cudaSetDevice(device));
+    GSB_CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+    return GSB_OK;
+}
+extern "C" void gsb_device_free(int device, void *p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+extern "C" int gsb_memcpy_h2d(int device, void *d_dst, const void *src, uint64_t bytes) {
+    GSB_CUDA_TRY(cudaSetDevice(device));
+    GSB_CUDA_TRY(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice));
+    return GSB_OK;
+}
+extern "C" int gsb_memcpy_d2h(int device, void *dst, const void *d_src, uint64_t bytes) {
+    GSB_CUDA_TRY(cudaSetDevice(device));
+    GSB_CUDA_TRY(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return GSB_OK;
+}
+extern "C" int gsb_host_alloc_pinned(uint64_t bytes, void **out) {
+    if (!out) {
+        set_error("gsb_host_alloc_pinned: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    GSB_CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return GSB_OK;
+}
+extern "C" void gsb_host_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
 }

@@ -530,8 +530,22 @@ uint32_t wave_size(uint64_t nb_point, uint32_t wave_max) {  // == gso_hnsw_wave_
     return (uint32_t)w;
 }
 
+}  // namespace
+namespace gsb {
+int comm_all_gather3(gsb_comm *c, void *a, size_t a_bytes, void *b, size_t b_bytes, void *d, size_t d_bytes,
+                     cudaStream_t st);
+int comm_rank(const gsb_comm *c);
+int comm_size(const gsb_comm *c);
+int comm_device(const gsb_comm *c);
+}  // namespace gsb
+namespace {
+
+// One wave.  With a communicator, phase A (K8: search + selection, all the distance evaluations)
+// runs only for this rank's slice of the wave; the selections (a few KB per point) are all-gathered
+// in place and phase B (K9) is applied by every rank to its own replica: the replicas stay
+// bit-identical and the graph is the one a single GPU builds with the same wave size.
 template <int ELEM, bool F32>
-int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
+int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st, gsb_comm *comm) {
     const uint32_t ef_c = idx->p.ef_construction;
     const size_t row = (size_t)idx->p.sketch_size * ELEM;
     const size_t ret_bytes = ((size_t)ef_c + 2) * sizeof(HItem);
@@ -547,12 +561,17 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     // the same process gets the opt-in too
     GSB_CUDA_TRY(cudaFuncSetAttribute(k8_hnsw_insert_select<ELEM, F32>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    const uint32_t nctas = std::min<uint32_t>(W, (uint32_t)idx->nsm * (staged ? 1u : 2u));
+    const uint32_t world = comm ? (uint32_t)comm_size(comm) : 1u, rank = comm ? (uint32_t)comm_rank(comm) : 0u;
+    const uint32_t per = (W + world - 1) / world;  // points of the wave per rank (the last slices may be short or empty)
+    const uint32_t t_begin = std::min(W, rank * per), t_end = std::min(W, t_begin + per);
+    const uint32_t nctas = std::max<uint32_t>(1u, std::min<uint32_t>(t_end - t_begin, (uint32_t)idx->nsm * (staged ? 1u : 2u)));
     int rc;
     if ((rc = ensure_workspace(idx, nctas, (uint64_t)first + W, ef_c))) return rc;
     WaveView wv;
     wv.first = first;
     wv.W = W;
+    wv.t_begin = t_begin;
+    wv.t_end = t_end;
     wv.entry = idx->entry;
     wv.ef_c = ef_c;
     wv.extend = idx->p.extend_candidates;
@@ -563,8 +582,15 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
     GSB_CUDA_TRY(cudaMemsetAsync(idx->d_counter.p, 0, 256, st));
     GraphView g = graph_view(idx);
     g.n = first + W;
-    k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem, bm_words, staged,
-                                                                         idx->d_ws.as<uint8_t>(), idx->wl);
+    if (t_end > t_begin)
+        k8_hnsw_insert_select<ELEM, F32><<<nctas, kInsertThreads, smem, st>>>(g, wv, ret_in_smem, bm_words, staged,
+                                                                             idx->d_ws.as<uint8_t>(), idx->wl);
+    if (world > 1) {
+        const size_t M = idx->M;
+        if ((rc = comm_all_gather3(comm, wv.sel_n, (size_t)per * kMaxLayers * 4, wv.sel_idx, (size_t)per * 18 * M * 4,
+                                   wv.sel_d, (size_t)per * 18 * M * 4, st)))
+            return rc;
+    }
     k9_write_own_lists<<<W, 256, 0, st>>>(g, wv);
     k9_reverse_updates<<<W, 256, 0, st>>>(g, wv);
     GSB_CUDA_TRY(cudaGetLastError());
@@ -573,7 +599,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n) {
+static int insert_batch_impl(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n, gsb_comm *comm) {
     std::unique_lock<std::recursive_mutex> lock_;
     if (idx) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<gsb_index *>(idx)->mu);
     if (!idx || (n && (!sigs || !ids))) {
@@ -626,9 +652,11 @@ extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const ui
     idx->nU = nU;
     const uint32_t wmax = idx->wave_max;
     const size_t M = idx->M;
-    if ((rc = idx->d_sel_n.ensure((size_t)wmax * kMaxLayers * 4))) return rc;
-    if ((rc = idx->d_sel_idx.ensure((size_t)wmax * 18 * M * 4))) return rc;
-    if ((rc = idx->d_sel_d.ensure((size_t)wmax * 18 * M * 4))) return rc;
+    // room for world * ceil(W / world) points: the all-gather works on equal slices
+    const size_t wcap = (size_t)wmax + (comm ? (size_t)comm_size(comm) : 0);
+    if ((rc = idx->d_sel_n.ensure(wcap * kMaxLayers * 4))) return rc;
+    if ((rc = idx->d_sel_idx.ensure(wcap * 18 * M * 4))) return rc;
+    if ((rc = idx->d_sel_d.ensure(wcap * 18 * M * 4))) return rc;
     if ((rc = idx->d_counter.ensure(256))) return rc;
     // ---- waves
     uint64_t i = 0;
@@ -643,10 +671,10 @@ extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const ui
         if (W > n - i) W = (uint32_t)(n - i);
         const uint32_t first = (uint32_t)idx->n;
         switch (idx->p.sig_type) {
-        case GSB_SIG_U64: rc = launch_wave<8, false>(idx, first, W, st); break;
-        case GSB_SIG_U32: rc = launch_wave<4, false>(idx, first, W, st); break;
-        case GSB_SIG_F32: rc = launch_wave<4, true>(idx, first, W, st); break;
-        default: rc = launch_wave<2, false>(idx, first, W, st); break;
+        case GSB_SIG_U64: rc = launch_wave<8, false>(idx, first, W, st, comm); break;
+        case GSB_SIG_U32: rc = launch_wave<4, false>(idx, first, W, st, comm); break;
+        case GSB_SIG_F32: rc = launch_wave<4, true>(idx, first, W, st, comm); break;
+        default: rc = launch_wave<2, false>(idx, first, W, st, comm); break;
         }
         if (rc) return rc;
         for (uint32_t t = 0; t < W; t++)
@@ -658,8 +686,29 @@ extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const ui
     return GSB_OK;
 }
 
+extern "C" int gsb_index_insert_batch(gsb_index *idx, const void *sigs, const uint64_t *ids, uint64_t n) {
+    return insert_batch_impl(idx, sigs, ids, n, nullptr);
+}
+
 extern "C" int gsb_index_insert_batch_dev(gsb_index *idx, const void *d_sigs, const uint64_t *ids, uint64_t n) {
-    return gsb_index_insert_batch(idx, d_sigs, ids, n);
+    return insert_batch_impl(idx, d_sigs, ids, n, nullptr);
+}
+
+// Sharded construction: EVERY rank of `comm` calls this with the same signatures (host or device
+// pointer), ids and index parameters (same level_seed, same wave_max); every rank ends with the same
+// graph, the one gsb_index_insert_batch builds on one GPU with that wave_max.
+extern "C" int gsb_index_insert_batch_sharded(gsb_index *idx, gsb_comm *comm, const void *sigs, const uint64_t *ids,
+                                              uint64_t n) {
+    if (!comm) {
+        set_error("gsb_index_insert_batch_sharded: NULL communicator");
+        return GSB_ERR_INVALID_ARG;
+    }
+    if (idx && comm_device(comm) != idx->device) {
+        set_error("gsb_index_insert_batch_sharded: the communicator lives on device %d, the index on device %d",
+                  comm_device(comm), idx->device);
+        return GSB_ERR_INVALID_ARG;
+    }
+    return insert_batch_impl(idx, sigs, ids, n, comm);
 }
 
 // ------------------------------------------------------------------------------ export / dump

@@ -54,7 +54,7 @@ static int prob_slots() {
 
 struct ProbSlot {
     DevBuf bitmap, table, cnt, list, ovf, misc, hmin, sigw;
-    DevBuf buckets, cursor;  // partition path
+    DevBuf buckets, cursor, slot2;  // partition path
     size_t cnt_dirty = 0;
 };
 
@@ -306,6 +306,7 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
         s.sigw.release();
         s.buckets.release();
         s.cursor.release();
+        s.slot2.release();
     }
     PinBuf *pb[] = {&h->h_files, &h->h_tile_prefix, &h->h_jobs, &h->h_chunk_prefix, &h->h_retry, &h->h_overflow};
     for (PinBuf *b : pb) b->release();
@@ -492,19 +493,30 @@ void launch_part_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
         }
         {
             Timed tc_(h, CAT_K2_CLASSIFY, st);
-            k2p_count<KT, KEY><<<dim3(kNB, njobs), kCThreads, csm, st>>>(jobs, njobs, res, h->sc, pc, ovf);
+            CountArgs ca;
+            const ProbJob *hj = h->h_jobs.as<ProbJob>() + joff;  // host copy of the descriptors
+            for (uint32_t i = 0; i < kMaxGroupJobs; i++) {
+                const ProbJob &pj = hj[i < njobs ? i : 0];
+                ca.buckets[i] = pj.buckets;
+                ca.cursor[i] = pj.cursor;
+                ca.slot2[i] = pj.slot2;
+                ca.cap_g[i] = pj.cap_g;
+            }
+            // GSB_COUNT_R > 0: persistent CTAs (R per SM) that prefetch the next bucket's run; 0 (default,
+            // measured faster): one CTA per (genome, bucket), the hardware scheduler does the balancing
+            const int cr = env_int("GSB_COUNT_R", 0, 0, 8);
+            const uint32_t cgrid = cr ? std::min<uint32_t>(njobs * kNB, (uint32_t)(h->nsm * cr)) : njobs * kNB;
+            k2p_count<KT, KEY><<<cgrid, kCThreads, csm, st>>>(ca, njobs, bound, h->sc, pc, ovf);
         }
     }
     Timed t3_(h, CAT_K3, st);
-    k3_prob_points<KT, 0><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
-    k3_prob_points<KT, 1><<<dim3(148, njobs), 256, 0, st>>>(jobs, njobs, bound, h->sc);
     if (h->elem == 8)
-        k3_prob_finalize<uint64_t><<<dim3(kFinParts, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint64_t *)d_sig,
-                                                          d_nb, h->d_retry.as<uint32_t>());
+        k3p_finalize128<uint64_t><<<dim3(24, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint64_t *)d_sig, d_nb,
+                                                                  h->d_retry.as<uint32_t>());
     else
-        k3_prob_finalize<uint32_t><<<dim3(kFinParts, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig,
-                                                          d_nb, h->d_retry.as<uint32_t>());
-    h->launches += nchunks ? 6 : 4;
+        k3p_finalize128<uint32_t><<<dim3(24, njobs), 256, 0, st>>>(jobs, njobs, bound, res, h->sc, (uint32_t *)d_sig, d_nb,
+                                                                  h->d_retry.as<uint32_t>());
+    h->launches += nchunks ? 4 : 2;
 }
 
 template <class Src, typename KT>
@@ -588,11 +600,10 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
             const void *old_misc = sl.misc.p;
             if ((rc = sl.buckets.ensure((size_t)kNB * part_cap_g(max_len) * key_bytes + 64))) return rc;
             if ((rc = sl.cursor.ensure((size_t)kNB * 4))) return rc;
-            if ((rc = sl.list.ensure(list_cap_max * sizeof(ListEntry)))) return rc;
+            if ((rc = sl.list.ensure(4096))) return rc;  // (only the filter path fills a candidate list)
             if ((rc = sl.misc.ensure(256))) return rc;
             if (sl.misc.p != old_misc) GSB_CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 256, st));
-            if ((rc = sl.hmin.ensure((size_t)h->sc.m * 8))) return rc;
-            if ((rc = sl.sigw.ensure((size_t)h->sc.m * 8))) return rc;
+            if ((rc = sl.slot2.ensure((size_t)h->sc.m * 16))) return rc;
             continue;
         }
         const void *old_cnt = sl.cnt.p, *old_list = sl.list.p, *old_misc = sl.misc.p;
@@ -658,6 +669,7 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 j.cursor = sl.cursor.as<uint32_t>();
                 j.cap_g = (uint32_t)part_cap_g(len);
                 j.newpath = newpath ? 1u : 0u;
+                j.slot2 = sl.slot2.as<ulonglong2>();
                 acc += (uint32_t)((len + kChunk - 1) / kChunk);
             }
         }
@@ -1018,8 +1030,10 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
     return GSB_OK;
 }
 
-extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets,
-                                      uint32_t n, void *sig_out, uint64_t *nb_bases_out) {
+// host FASTA in; signatures (and encoded lengths) out to host memory or, with out_dev, straight to the
+// caller's device buffers (e.g. this rank's slice of the replicated signature matrix)
+static int sketch_host_in(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets, uint32_t n, void *sig_out,
+                          uint64_t *nb_bases_out, bool out_dev) {
     if (!h || !offsets || (n && !sig_out)) {
         set_error("gsb_sketch_fasta_batch: NULL argument");
         return GSB_ERR_INVALID_ARG;
@@ -1035,8 +1049,8 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
     const size_t sig_row = (size_t)h->sc.m * h->elem;
     int rc;
     if ((rc = h->d_bytes.ensure(hi - lo + 64))) return rc;
-    if ((rc = h->d_sig.ensure((size_t)n * sig_row))) return rc;
-    if ((rc = h->d_nb.ensure((size_t)n * 8))) return rc;
+    if (!out_dev && (rc = h->d_sig.ensure((size_t)n * sig_row))) return rc;
+    if ((!out_dev || !nb_bases_out) && (rc = h->d_nb.ensure((size_t)n * 8))) return rc;
     cudaStream_t st = h->stream;
     if (!h->copy_stream) {
         GSB_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1077,17 +1091,28 @@ extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, con
     std::vector<uint64_t> rel(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
     h->h2d_active = true;
-    rc = sketch_batch_dev_locked(h, h->d_bytes.as<uint8_t>(), rel.data(), n, h->d_sig.p, h->d_nb.as<uint64_t>(),
-                                 (void *)st);
+    rc = sketch_batch_dev_locked(h, h->d_bytes.as<uint8_t>(), rel.data(), n, out_dev ? sig_out : h->d_sig.p,
+                                 (out_dev && nb_bases_out) ? nb_bases_out : h->d_nb.as<uint64_t>(), (void *)st);
     h->h2d_active = false;
     if (rc) {
         cudaStreamSynchronize(h->copy_stream);
         return rc;
     }
+    if (out_dev) return GSB_OK;  // batch_dev returned after synchronising `st`
     // batch_dev returned after synchronising `st`: the results are complete
     GSB_CUDA_TRY(cudaMemcpyAsync(sig_out, h->d_sig.p, (size_t)n * sig_row, cudaMemcpyDeviceToHost, h->d2h_stream));
     if (nb_bases_out)
         GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out, h->d_nb.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
     GSB_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
     return GSB_OK;
+}
+
+extern "C" int gsb_sketch_fasta_batch(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets,
+                                      uint32_t n, void *sig_out, uint64_t *nb_bases_out) {
+    return sketch_host_in(h, bytes, offsets, n, sig_out, nb_bases_out, false);
+}
+
+extern "C" int gsb_sketch_fasta_batch_to_dev(gsb_sketcher *h, const uint8_t *bytes, const uint64_t *offsets,
+                                             uint32_t n, void *d_sig_out, uint64_t *d_nb_bases_out) {
+    return sketch_host_in(h, bytes, offsets, n, d_sig_out, d_nb_bases_out, true);
 }

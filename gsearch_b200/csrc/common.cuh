@@ -77,6 +77,16 @@ struct Exp01 {
     double lambda, c1, c2, c3;  // computed on the host with libm, exactly as the oracle does
 };
 
+// expm1 on [0, ln 2] as the SPEC freezes it (oracle/rng.c gso_expm1_spec): degree-24 Taylor polynomial,
+// Horner form, one correctly rounded operation per step -- identical bits on the host and here,
+// which libm's expm1 (1-ulp differences between implementations) cannot promise.
+__device__ __forceinline__ double expm1_spec(double z) {
+    double r = 1.0;
+#pragma unroll 1
+    for (int k = 24; k >= 2; k--) r = __dadd_rn(1.0, __dmul_rn(__ddiv_rn(z, (double)k), r));
+    return __dmul_rn(z, r);
+}
+
 // ExpRestricted01::sample, entered after the first uniform has been drawn (u0)
 __device__ __forceinline__ double exp01_sample_from(const Exp01 &e, double u0, Xoshiro &rng) {
     double x = __dmul_rn(e.c1, u0);
@@ -91,12 +101,40 @@ __device__ __forceinline__ double exp01_sample_from(const Exp01 &e, double u0, X
         }
         if (x <= __dmul_rn(e.c3, __dadd_rn(1.0, -y))) return x;
         if (__dmul_rn(e.c1, y) <= __dadd_rn(1.0, -x)) return x;
-        if (__dmul_rn(__dmul_rn(y, e.c1), e.lambda) <= expm1(__dmul_rn(e.lambda, __dadd_rn(1.0, -x))))
+        if (__dmul_rn(__dmul_rn(y, e.c1), e.lambda) <= expm1_spec(__dmul_rn(e.lambda, __dadd_rn(1.0, -x))))
             return x;
     }
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---- 128-bit compare-and-swap in global memory (atom.global.cas.b128, SASS ATOMG.E.CAS.128) and the
+// lexicographic minimum it gives: slot = min over (ordered bits of h, k-mer).  One atomic object per
+// MinHash slot replaces the two passes "atomicMin of h" / "owners of the minimum write the k-mer".
+__device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, ulonglong2 nw) {
+    ulonglong2 prev;
+    asm volatile(
+        "{\n"
+        ".reg .b128 c, n, r;\n"
+        "mov.b128 c, {%2, %3};\n"
+        "mov.b128 n, {%4, %5};\n"
+        "atom.global.cas.b128 r, [%6], c, n;\n"
+        "mov.b128 {%0, %1}, r;\n"
+        "}\n"
+        : "=l"(prev.x), "=l"(prev.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(nw.x), "l"(nw.y), "l"(addr)
+        : "memory");
+    return prev;
+}
+__device__ __forceinline__ void slot_min128(ulonglong2 *addr, unsigned long long hb, unsigned long long d) {
+    ulonglong2 old = __ldcg(addr);  // a stale (larger) value only costs one more trip
+    for (;;) {
+        if (!(hb < old.x || (hb == old.x && d < old.y))) return;
+        const ulonglong2 prev = cas128(addr, old, make_ulonglong2(hb, d));
+        if (prev.x == old.x && prev.y == old.y) return;
+        old = prev;
+    }
+}
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

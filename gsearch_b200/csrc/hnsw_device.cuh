@@ -497,6 +497,8 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
 // =========================================================================== construction
 struct WaveView {
     uint32_t first, W;       // the wave = points [first, first + W)
+    uint32_t t_begin, t_end; // phase A runs the points [t_begin, t_end) of the wave on this GPU (all of
+                             // them on one GPU; a rank's slice when the insertion is sharded)
     uint32_t entry;          // entry point before the wave
     uint32_t ef_c, extend;   // ef_construction, extend_candidates (layer 0 only)
     uint32_t *sel_n;         // [W x kMaxLayers] selected neighbours per layer
@@ -551,10 +553,10 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
     const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_t = atomicAdd(wv.counter, 1u);
+        if (threadIdx.x == 0) s_t = wv.t_begin + atomicAdd(wv.counter, 1u);
         __syncthreads();
         const uint32_t t = s_t;
-        if (t >= wv.W) break;
+        if (t >= wv.t_end) break;
         const uint32_t np = wv.first + t;
         const uint32_t level = g.levels[np];
         const uint8_t *qrow = g.sigs + (size_t)np * row;

@@ -40,7 +40,7 @@ constexpr uint32_t kNB = 1u << kPB;         // buckets per genome
 constexpr uint32_t kRegion = 7;             // staged keys per (tile, bucket); tile mean is 4 (7: three CTAs per SM)
 constexpr uint32_t kSpillCap = 1024;        // per-tile spill list (keys beyond a full region)
 constexpr uint32_t kCTab = 8192;            // slots of the counting table
-constexpr uint32_t kCRound = 4096;          // keys per counting round (load <= 1/2)
+constexpr uint32_t kCRound = 3584;          // keys per counting round / stage chunk (14 per thread; 3 CTAs per SM)
 constexpr uint32_t kCapGMax = 60000;        // duplicate counters are 16 bits wide
 constexpr uint64_t kBMixC1 = 0x9E3779B97F4A7C15ULL, kBMixC2 = 0xD6E8FEB86659FD93ULL;
 constexpr uint64_t kBMixC1Inv = 0xF1DE83E19937733DULL, kBMixC2Inv = 0xCFEE444D8B59A89BULL;
@@ -103,10 +103,6 @@ template <typename KEY>
 constexpr size_t part_smem_bytes() {
     return (size_t)kNB * kRegion * sizeof(KEY) + kNB * 4 + kSpillCap * sizeof(SpillEntry<KEY>);
 }
-template <typename KEY>
-constexpr size_t count_smem_bytes() {
-    return (size_t)kCRound * sizeof(KEY) + (size_t)kCTab * sizeof(KEY) + kCTab * 2 + 512 * 8 * 2;
-}
 
 // per group: reset cursors / slots / candidate cursor, compute the bounds (new path)
 __global__ void __launch_bounds__(256)
@@ -125,10 +121,8 @@ k2p_reset(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult *__
         }
     }
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < kNB; b += gridDim.x * blockDim.x) job.cursor[b] = 0;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < sc.m; k += gridDim.x * blockDim.x) {
-        job.hmin[k] = 0x7FEFFFFFFFFFFFFFull;  // f64::MAX
-        job.sigw[k] = ~0ull;
-    }
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < sc.m; k += gridDim.x * blockDim.x)
+        job.slot2[k] = make_ulonglong2(0x7FEFFFFFFFFFFFFFull /* f64::MAX */, ~0ull);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *job.list_n = 0;
         overflow[j] = 0;
@@ -267,166 +261,293 @@ k2p_partition(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chu
     }
 }
 
-// ---- pass C: count.  grid = (kNB, njobs), kCThreads threads
+// ---- pass C: count.  Persistent CTAs over the (genome, bucket) items of a group.
 //
-// The bucket's run is staged in shared memory by one TMA bulk copy per chunk of kCRound keys
-// (cp.async.bulk + mbarrier: SASS UBLKCP), then every lane drains its share of the stage through a
-// per-lane queue: one probe (atomicCAS) per loop trip for whichever key the lane holds, so lanes
-// that need a second probe do not idle the others.  A key becomes a candidate exactly once -- at its
-// first occurrence if it is light, at its second occurrence otherwise -- and only its table slot is
-// remembered, in a private segment of the thread (no atomic, no vote); after the round the segments
-// are compacted by a block-wide prefix sum and all threads turn the slots into (k-mer, weight)
-// entries that leave with one global atomicAdd per CTA.
-constexpr int kCThreads = 512;
-constexpr uint32_t kCSeg = 8;  // candidate slots a thread can remember per round
+// Every CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ...  The run of item k+1 is already on
+// its way into the other half of a double-buffered stage (TMA bulk copy, cp.async.bulk + mbarrier:
+// SASS UBLKCP; its length was read one item earlier still) while item k is counted, so no global
+// latency is exposed after the first item.  Counting itself:
+//   phase A  straight-line: every lane takes its keys four at a time, ONE atomicCAS each into a
+//            shared-memory table; a key that found its slot empty is counted, anything else (a second
+//            occurrence, or a different key in the slot: ~16 %) is parked in a pool of the WARP
+//            (ballot compaction, no atomic);
+//   phase B  drains the pool, 32 parked keys per trip: probe on, or count one more occurrence in a
+//            small side table keyed by the slot (repeats are rare: a counter per slot would triple
+//            the table's footprint and cost a resident CTA);
+//   emit     a key becomes a candidate exactly once -- at its first occurrence if it is light, at its
+//            second occurrence otherwise -- and only its slot is remembered, per warp; after ONE block
+//            barrier (the occurrence counts are final) the slots leave as (k-mer, weight) entries
+//            into the bucket's own region of the genome's candidate list: plain coalesced stores, no
+//            global atomic.  k3p_points128 consumes them.
+constexpr int kCThreads = 256;
+constexpr uint32_t kCWarps = kCThreads / 32;
+constexpr uint32_t kCPark = kCRound / kCWarps;   // parked keys per warp and chunk (all of them, at worst)
+constexpr uint32_t kCCand = 256;                 // candidate slots per warp and round
+constexpr uint32_t kCDup = 512;                  // side table: distinct repeated keys per round (load <= 3/4)
+constexpr uint32_t kMaxGroupJobs = 8;            // genomes per group (kMaxSlots / 2)
+
+struct CountArgs {
+    const void *buckets[kMaxGroupJobs];
+    const uint32_t *cursor[kMaxGroupJobs];
+    ulonglong2 *slot2[kMaxGroupJobs];    // [m] (ordered bits of min h, winning k-mer) per MinHash slot
+    uint32_t cap_g[kMaxGroupJobs];
+};
+
+template <typename KEY>
+constexpr size_t count_smem_bytes() {
+    return 2 * (size_t)kCRound * sizeof(KEY) + (size_t)kCTab * sizeof(KEY) + kCDup * 4 + kCWarps * kCPark * 2 +
+           kCWarps * kCCand * 2;
+}
+
+// extra occurrences of the key in table slot `s` (0 if it never repeated)
+__device__ __forceinline__ uint32_t dup_lookup(const uint32_t *s_dup, uint32_t s) {
+    uint32_t h = (s * 0x9E3779B1u) >> 23;  // 9 bits
+    for (uint32_t p = 0; p < kCDup; p++) {
+        const uint32_t e = s_dup[h];
+        if (e == 0) return 0;
+        if ((e >> 16) == s + 1) return e & 0xFFFFu;
+        h = (h + 1) & (kCDup - 1);
+    }
+    return 0;
+}
+// one more occurrence of the key in slot `s`; returns the number of extra occurrences BEFORE this
+// one, or 0xFFFFFFFF if the side table is full
+__device__ __forceinline__ uint32_t dup_bump(uint32_t *s_dup, uint32_t s) {
+    uint32_t h = (s * 0x9E3779B1u) >> 23;
+    for (uint32_t p = 0; p < kCDup; p++) {
+        const uint32_t e = atomicCAS(&s_dup[h], 0u, ((s + 1) << 16) | 1u);
+        if (e == 0) return 0;
+        if ((e >> 16) == s + 1) return atomicAdd(&s_dup[h], 1u) & 0xFFFFu;
+        h = (h + 1) & (kCDup - 1);
+    }
+    return 0xFFFFFFFFu;
+}
 
 template <typename KT, typename KEY>
-__global__ void __launch_bounds__(kCThreads)
-k2p_count(const ProbJob *__restrict__ jobs, uint32_t njobs, const FileResult *__restrict__ res, SketchConsts sc,
-          PartConsts pc, uint32_t *__restrict__ overflow) {
+__global__ void __launch_bounds__(kCThreads, 3)
+k2p_count(CountArgs args, uint32_t njobs, const ProbBound *__restrict__ bound, SketchConsts sc, PartConsts pc,
+          uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    KEY *s_stage = reinterpret_cast<KEY *>(s_raw);                        // [kCRound] keys of the current chunk
-    KEY *s_key = s_stage + kCRound;                                       // [kCTab]
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_key + kCTab);        // [kCTab / 2] u16 pairs: extra occurrences
-    uint16_t *s_seg = reinterpret_cast<uint16_t *>(s_cnt + kCTab / 2);    // [kCThreads][kCSeg] candidate slots
-    uint16_t *s_dense = reinterpret_cast<uint16_t *>(s_stage);            // compacted slots (the stage is free by then)
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_wsum[kCThreads / 32];
-    __shared__ uint32_t s_base, s_special;
-    const uint32_t j = blockIdx.y, b = blockIdx.x;
-    if (j >= njobs) return;
-    const ProbJob job = jobs[j];
-    if (res[job.file].status != 0) return;
-    uint32_t n = job.cursor[b];
-    if (n == 0) return;
-    if (n > job.cap_g) n = job.cap_g;  // the genome is flagged already (k2p_partition)
-    const KEY *run = reinterpret_cast<const KEY *>(job.buckets) + (size_t)b * job.cap_g;
-    const uint32_t rn = (n + kCRound - 1) / kCRound;          // counting rounds (1 for ordinary genomes)
-    const uint32_t nchunk = rn;                               // stage loads per round
-    // table sized to the round: 2 x keys rounded up to a power of two, at least 256 slots
-    uint32_t lg = 8;
-    {
-        const uint32_t per = rn > 1 ? kCRound : n;
-        while ((1u << lg) < 2 * per && (1u << lg) < kCTab) lg++;
-    }
-    const uint32_t ts = 1u << lg, tmask = ts - 1;
+    KEY *s_stage0 = reinterpret_cast<KEY *>(s_raw);                       // [2][kCRound] double-buffered runs
+    KEY *s_key = s_stage0 + 2 * kCRound;                                  // [kCTab]
+    uint32_t *s_dup = reinterpret_cast<uint32_t *>(s_key + kCTab);        // [kCDup] (slot + 1) << 16 | extra occurrences
+    uint16_t *s_park = reinterpret_cast<uint16_t *>(s_dup + kCDup);       // [kCWarps][kCPark] parked stage indices
+    uint16_t *s_cand = s_park + kCWarps * kCPark;                         // [kCWarps][kCCand] candidate slots
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_special;
+    static_assert(kCTab == 1u << 13, "table size");
+    static_assert(kCRound % kCThreads == 0, "chunk size");
     const KEY keymask = pc.keybits >= 8 * sizeof(KEY) ? (KEY)~(KEY)0 : (KEY)(((KEY)1 << pc.keybits) - 1);
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint16_t *wpark = s_park + warp * kCPark, *wcand = s_cand + warp * kCCand;
+    const uint32_t nitems = njobs * kNB;
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         fence_barrier_init();
     }
-    uint32_t phase = 0;
-    for (uint32_t r = 0; r < rn; r++) {
-        __syncthreads();  // previous round's flush is done (and the barrier is initialised)
-        {
-            const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u), z4 = make_uint4(0, 0, 0, 0);
-            uint4 *k4 = reinterpret_cast<uint4 *>(s_key);
-            for (uint32_t s = threadIdx.x; s < ts * sizeof(KEY) / 16; s += kCThreads) k4[s] = e4;
-            uint4 *c4 = reinterpret_cast<uint4 *>(s_cnt);
-            for (uint32_t s = threadIdx.x; s < ts / 8; s += kCThreads) c4[s] = z4;
+    // item -> (genome, bucket): consecutive items are consecutive buckets of one genome
+    auto item_n = [&](uint32_t it) -> uint32_t {
+        if (it >= nitems) return 0u;
+        const uint32_t j = it / kNB, b = it % kNB;
+        const uint32_t n = __ldg(args.cursor[j] + b), cap = args.cap_g[j];
+        return n < cap ? n : cap;  // (an overfull bucket: the genome is flagged already, k2p_partition)
+    };
+    auto issue = [&](uint32_t it, uint32_t n, uint32_t c0, uint32_t buf) {  // thread 0 only
+        const uint32_t j = it / kNB, b = it % kNB;
+        const uint32_t cn = n - c0 < kCRound ? n - c0 : kCRound;
+        const uint32_t bytes = (uint32_t)((cn * sizeof(KEY) + 15) & ~(size_t)15);  // within cap_g (multiple of 4 keys)
+        const KEY *run = reinterpret_cast<const KEY *>(args.buckets[j]) + (size_t)b * args.cap_g[j] + c0;
+        mbar_expect_tx(&s_bar[buf], bytes);
+        tma_bulk_g2s(s_stage0 + (size_t)buf * kCRound, run, bytes, &s_bar[buf]);
+    };
+    uint32_t it = blockIdx.x;
+    uint32_t n = item_n(it), n_next = item_n(it + gridDim.x);
+    uint32_t buf = 0, phase0 = 0, phase1 = 0;
+    __syncthreads();  // barriers initialised
+    if (threadIdx.x == 0 && n) issue(it, n, 0, 0);
+    for (; it < nitems; it += gridDim.x, n = n_next, n_next = item_n(it + gridDim.x)) {
+        // (n_next for the item after the next one is loaded at the loop increment, a whole item ahead of its use)
+        const uint32_t j = it / kNB, b = it % kNB;
+        if (n == 0) {  // empty bucket: nothing in flight for it; start the next item's copy
+            __syncthreads();
+            if (threadIdx.x == 0 && n_next) issue(it + gridDim.x, n_next, 0, buf);
+            continue;
         }
-        if (threadIdx.x == 0) s_special = 0;
+        const uint32_t rn = (n + kCRound - 1) / kCRound;  // counting rounds (1 for ordinary genomes)
+        const bool MULTI = rn > 1;
+        uint32_t lg = 32 - __clz(2 * (rn > 1 ? kCRound : n) - 1);
+        lg = lg < 8 ? 8 : (lg > 13 ? 13 : lg);  // table: 2 x keys rounded up to a power of two, 256 .. kCTab slots
+        const uint32_t ts = 1u << lg, tmask = ts - 1;
         bool full = false;
-        uint32_t nloc = 0;  // candidates remembered by this thread
-        uint16_t *seg = s_seg + threadIdx.x * kCSeg;
-        for (uint32_t c = 0; c < nchunk; c++) {
-            const uint32_t c0 = c * kCRound, cn = n - c0 < kCRound ? n - c0 : kCRound;
-            __syncthreads();  // table cleared / previous chunk drained: the stage may be overwritten
-            if (threadIdx.x == 0) {
-                const uint32_t bytes = (uint32_t)((cn * sizeof(KEY) + 15) & ~(size_t)15);  // within cap_g (multiple of 4 keys)
-                mbar_expect_tx(&s_bar, bytes);
-                tma_bulk_g2s(s_stage, run + c0, bytes, &s_bar);
-            }
-            mbar_wait(&s_bar, phase);
-            phase ^= 1u;
-            // ---- per-lane queue: hold one key, probe once per trip
-            uint32_t i = threadIdx.x, s = 0, probes = 0;
-            KEY w = 0;
-            bool have = false;
-            for (;;) {
-                if (!have) {
-                    if (i >= cn) break;
-                    w = s_stage[i];
-                    i += kCThreads;
+        for (uint32_t r = 0; r < rn; r++) {
+            uint32_t ncand = 0;  // candidates remembered by this warp (uniform)
+            for (uint32_t c = 0; c < rn; c++) {
+                const uint32_t c0 = c * kCRound, cn = n - c0 < kCRound ? n - c0 : kCRound;
+                const bool last_load = r + 1 == rn && c + 1 == rn;
+                __syncthreads();  // previous chunk drained / previous round or item flushed
+                if (threadIdx.x == 0) {  // the NEXT copy flies while this chunk is counted
+                    if (!last_load) {
+                        const uint32_t c2 = c + 1 == rn ? 0 : c + 1;
+                        issue(it, n, c2 * kCRound, buf ^ 1u);
+                    } else if (n_next) {
+                        issue(it + gridDim.x, n_next, 0, buf ^ 1u);
+                    }
+                }
+                if (c == 0) {
+                    const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u), z4 = make_uint4(0, 0, 0, 0);
+                    uint4 *k4 = reinterpret_cast<uint4 *>(s_key);
+                    for (uint32_t s = threadIdx.x; s < ts * sizeof(KEY) / 16; s += kCThreads) k4[s] = e4;
+                    uint4 *d4 = reinterpret_cast<uint4 *>(s_dup);
+                    for (uint32_t s = threadIdx.x; s < kCDup / 4; s += kCThreads) d4[s] = z4;
+                    if (threadIdx.x == 0) s_special = 0;
+                }
+                // one thread polls the mbarrier; the others sleep in the hardware barrier
+                if (threadIdx.x == 0) mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
+                if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+                __syncthreads();
+                const KEY *s_stage = s_stage0 + (size_t)buf * kCRound;
+                buf ^= 1u;
+                // ---- phase A: straight-line, four keys per trip (independent loads and atomics); the
+                // outcomes are pooled per WARP with ballots: parked keys by stage index, light keys that
+                // were new at their home slot by slot (candidates from their first occurrence on)
+                uint32_t npark = 0;  // uniform in the warp
+                constexpr int kU = 4;
+                for (uint32_t i0 = threadIdx.x; i0 - lane < cn; i0 += kU * kCThreads) {  // warp-uniform trip count
+                    KEY w[kU], old[kU];
+                    uint32_t sl[kU];
+                    bool on[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        const uint32_t i = i0 + u * kCThreads;
+                        on[u] = i < cn;
+                        w[u] = s_stage[on[u] ? i : 0];
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        const uint32_t hw = sizeof(KEY) == 8 ? (uint32_t)(((uint64_t)w[u] * 0x9E3779B97F4A7C15ULL) >> 32)
+                                                             : (uint32_t)w[u] * 0x9E3779B1u;
+                        sl[u] = hw >> (32 - lg);
+                        if (MULTI) on[u] = on[u] && ((hw >> 4) & 0xFFFFu) % rn == r;  // another round's key
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; u++)  // (a no-op for the one word that collides with the sentinel)
+                        old[u] = on[u] ? smem_cas(&s_key[sl[u]], KeyTraits<KEY>::kEmpty, w[u]) : (KEY)0;
+#pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        const bool isnew = on[u] && old[u] == KeyTraits<KEY>::kEmpty && w[u] != KeyTraits<KEY>::kEmpty;
+                        const bool park = on[u] && !isnew;
+                        const bool cand = isnew && (w[u] & KeyTraits<KEY>::kFlag);
+                        const uint32_t bp = __ballot_sync(0xffffffffu, park), bc = __ballot_sync(0xffffffffu, cand);
+                        if (park) wpark[npark + __popc(bp & lt)] = (uint16_t)(i0 + u * kCThreads);
+                        npark += __popc(bp);
+                        const uint32_t at = ncand + __popc(bc & lt);
+                        if (cand && at < kCCand) wcand[at] = (uint16_t)sl[u];
+                        ncand += __popc(bc);
+                    }
+                }
+                // ---- phase B: the warp's parked keys probe on (or count one more occurrence), 32 per trip
+                for (uint32_t t0 = 0; t0 < npark; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    const bool act = t < npark;
+                    const KEY w = s_stage[act ? wpark[t] : 0];
+                    const bool flagged = (w & KeyTraits<KEY>::kFlag) != 0;
                     const uint32_t hw = sizeof(KEY) == 8 ? (uint32_t)(((uint64_t)w * 0x9E3779B97F4A7C15ULL) >> 32)
                                                          : (uint32_t)w * 0x9E3779B1u;
-                    if (rn > 1 && ((hw >> 4) & 0xFFFFu) % rn != r) continue;  // another round's key
-                    if (w == KeyTraits<KEY>::kEmpty) {  // the one word that collides with the sentinel
+                    uint32_t s = hw >> (32 - lg);
+                    bool cand = false;
+                    if (act && w == KeyTraits<KEY>::kEmpty) {
                         atomicAdd(&s_special, 1u);
-                        continue;
+                    } else if (act) {
+                        for (uint32_t probes = 0;; probes++) {
+                            const KEY old = smem_cas(&s_key[s], KeyTraits<KEY>::kEmpty, w);
+                            if (old == w) {  // one more occurrence: the first of them makes a heavy key a candidate
+                                const uint32_t before = dup_bump(s_dup, s);
+                                full |= before == 0xFFFFFFFFu;
+                                cand = before == 0 && !flagged;
+                                break;
+                            }
+                            if (old == KeyTraits<KEY>::kEmpty) {  // first occurrence after all
+                                cand = flagged;
+                                break;
+                            }
+                            if (probes > ts) {  // table full: more distinct keys than a round holds
+                                full = true;
+                                break;
+                            }
+                            s = (s + 1) & tmask;
+                        }
                     }
-                    s = hw >> (32 - lg);
-                    probes = 0;
+                    const uint32_t bc = __ballot_sync(0xffffffffu, cand);
+                    const uint32_t at = ncand + __popc(bc & lt);
+                    if (cand && at < kCCand) wcand[at] = (uint16_t)s;
+                    ncand += __popc(bc);
                 }
-                const KEY old = smem_cas(&s_key[s], KeyTraits<KEY>::kEmpty, w);
-                const bool isnew = old == KeyTraits<KEY>::kEmpty, isdup = old == w;
-                const bool flagged = (w & KeyTraits<KEY>::kFlag) != 0;
-                bool emit = isnew && flagged;  // light: a candidate from its first occurrence on
-                if (isdup) {  // one more occurrence: the first of them makes a heavy key a candidate
-                    const uint32_t shv = (s & 1u) * 16u;
-                    const uint32_t before = (atomicAdd(&s_cnt[s >> 1], 1u << shv) >> shv) & 0xFFFFu;
-                    emit = before == 0 && !flagged;
+            }
+            if (ncand > kCCand) {  // more candidates than a warp remembers: general path
+                full = true;
+                ncand = kCCand;
+            }
+            __syncthreads();  // the occurrence counts are final
+            // ---- candidates -> (k-mer, weight) -> points of ProbMinHash3a -> 128-bit slot minimum.  The
+            // exact f64 replay and the two global round trips of the compare-and-swap are hidden by the
+            // other resident CTAs; nothing is written but the slots that actually improve.
+            const uint32_t nspecial = s_special;
+            const double T = bound[j].T;
+            ulonglong2 *slot2 = args.slot2[j];
+            // the warp's candidates, 32 per trip, plus (warp 0) the word that collides with the sentinel:
+            // light by construction
+            const uint32_t nmine = ncand + ((warp == 0 && nspecial) ? 1u : 0u);
+            for (uint32_t t = lane; t < nmine; t += 32) {
+                KEY w;
+                uint32_t extra;
+                if (t < ncand) {
+                    const uint32_t s = wcand[t];
+                    w = s_key[s];
+                    extra = dup_lookup(s_dup, s);
+                } else {
+                    w = KeyTraits<KEY>::kEmpty;
+                    extra = nspecial - 1;
                 }
-                if (emit) {
-                    if (nloc < kCSeg) seg[nloc] = (uint16_t)s;
-                    else full = true;  // more candidates than a thread remembers: general path
-                    nloc++;
-                }
-                have = !(isnew || isdup);
-                s = (s + 1) & tmask;
-                if (have && ++probes > ts) {  // table full: more distinct keys than a round holds
-                    full = true;
-                    have = false;
-                }
+                const KT d = bunmix<KT>((KT)(((KT)b << pc.keybits) | (KT)(w & keymask)), pc);
+                pmh_points<KT>(d, 1u + extra, T, sc, [&](double h, uint32_t k) {
+                    slot_min128(&slot2[k], (unsigned long long)__double_as_longlong(h), (unsigned long long)d);
+                });
             }
         }
         if (full) atomicOr(&overflow[j], 2u);
-        if (nloc > kCSeg) nloc = kCSeg;
-        // ---- block-wide exclusive prefix of nloc -> dense list of slots in the (now free) stage
-        uint32_t incl = nloc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += up;
-        }
-        __syncthreads();  // every thread is done with the stage (and with the table)
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        uint32_t pre = 0, nl = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < kCThreads / 32; w2++) {
-            const uint32_t v = s_wsum[w2];
-            if ((uint32_t)w2 < warp) pre += v;
-            nl += v;
-        }
-        pre += incl - nloc;
-        for (uint32_t t = 0; t < nloc; t++) s_dense[pre + t] = seg[t];
-        const uint32_t nspecial = s_special;
-        const uint32_t nout = nl + (nspecial ? 1u : 0u);
-        if (threadIdx.x == 0) s_base = nout ? atomicAdd(job.list_n, nout) : 0u;
-        __syncthreads();
-        // ---- the remembered slots leave as (k-mer, weight) candidates
-        const uint32_t gbase = s_base;
-        for (uint32_t t = threadIdx.x; t < nout; t += kCThreads) {
-            KEY w;
-            uint32_t extra;
-            if (t < nl) {
-                const uint32_t s = s_dense[t];
-                w = s_key[s];
-                extra = (s_cnt[s >> 1] >> ((s & 1u) * 16u)) & 0xFFFFu;
-            } else {
-                w = KeyTraits<KEY>::kEmpty;  // light by construction (all bits set)
-                extra = nspecial - 1;
-            }
-            const KT u = (KT)(((KT)b << pc.keybits) | (KT)(w & keymask));
-            ListEntry e;
-            e.kmer = (uint64_t)bunmix<KT>(u, pc);
-            e.slot = 1u + extra;  // kind 2: the weight itself
-            e.kind = 2;
-            if (gbase + t < job.list_cap) job.list[gbase + t] = e;
-            else atomicOr(&overflow[j], 1u);
-        }
+    }
+}
+
+// ---- finalize of the partition path.  (The slot update itself happens inside k2p_count: every
+// candidate replays the exact f64 arithmetic of ProbMinHash3a::hashset against the static bound and
+// lowers the 128-bit slot objects (h, k-mer) with a compare-and-swap loop: the lexicographic minimum
+// is the reference's result with this repository's tie rule -- identical h: smaller k-mer -- in any
+// order of arrival.)
+template <typename SigT>
+__global__ void __launch_bounds__(256)
+k3p_finalize128(const ProbJob *__restrict__ jobs, uint32_t njobs, const ProbBound *__restrict__ bound,
+                const FileResult *__restrict__ res, SketchConsts sc, SigT *__restrict__ sig_out,
+                uint64_t *__restrict__ nb_bases_out, uint32_t *__restrict__ retry) {
+    const uint32_t j = blockIdx.y;
+    if (j >= njobs) return;
+    const ProbJob job = jobs[j];
+    const unsigned long long Tb = (unsigned long long)__double_as_longlong(bound[j].T);
+    const FileResult fr = res[job.file];
+    const bool has_kmers = fr.nsym >= sc.k && fr.status == 0;
+    bool over = false;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < sc.m; k += gridDim.x * blockDim.x) {
+        // exact iff every slot's minimum is strictly below the bound (no skipped point can win or tie)
+        const ulonglong2 s = job.slot2[k];
+        over |= !(s.x < Tb);
+        sig_out[(size_t)job.file * sc.m + k] = (s.y == ~0ull) ? (SigT)0 : (SigT)s.y;
+    }
+    if (__syncthreads_or(over && has_kmers) && threadIdx.x == 0) atomicOr(&retry[job.file], 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (fr.status) atomicOr(&retry[job.file], fr.status << 8);
+        if (nb_bases_out) nb_bases_out[job.file] = fr.nbases;
+        *job.prev_n = 0;  // no extra-occurrence counters on this path
     }
 }
 

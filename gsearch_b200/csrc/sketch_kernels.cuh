@@ -70,6 +70,7 @@ struct ProbJob {
     uint32_t *cursor;    // [kNB] keys appended to each bucket
     uint32_t cap_g;      // capacity of one bucket array
     uint32_t newpath;    // 1: this job runs the partition path (no extra-occurrence counters to clear)
+    ulonglong2 *slot2;   // [m] partition path: (ordered bits of min h, winning k-mer) as ONE 128-bit object
 };
 
 struct ProbBound {  // written by k_prob_reset

@@ -52,6 +52,19 @@ class Hnsw:
         _lib.check(_lib.lib().gsb_index_insert_batch_dev(self._h, C.c_void_p(d_sigs_ptr),
                                                          C.c_void_p(ids.ctypes.data), len(ids)))
 
+    def insert_sharded(self, comm, sigs_or_ptr, ids):
+        """parallel_insert over the GPUs of `comm` (gsb_index_insert_batch_sharded): every rank calls
+        it with the same signatures (numpy array, or a raw device pointer to the all-gathered matrix)
+        and ids; every replica ends with the graph one GPU builds with the same wave_max"""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        if isinstance(sigs_or_ptr, np.ndarray):
+            keep = np.ascontiguousarray(sigs_or_ptr, dtype=self.dtype)
+            ptr = keep.ctypes.data
+        else:
+            ptr = int(sigs_or_ptr)
+        _lib.check(_lib.lib().gsb_index_insert_batch_sharded(self._h, comm._h, C.c_void_p(ptr),
+                                                             C.c_void_p(ids.ctypes.data), len(ids)))
+
     def set_wave_max(self, wave_max):
         _lib.check(_lib.lib().gsb_index_set_wave_max(self._h, int(wave_max)))
 

@@ -59,6 +59,14 @@ class Sketcher:
         _lib.check(_lib.lib().gsb_sketch_fasta_batch(self._h, _ptr(buf), _ptr(offsets), n, _ptr(sig), _ptr(nb)))
         return sig, nb
 
+    def sketch_buffer_to_device(self, buf, offsets, d_sig_ptr, d_nb_ptr=0):
+        """host FASTA buffers in, signatures (n x S) written at the raw DEVICE pointer d_sig_ptr -- e.g.
+        this rank's slice of the matrix that is all-gathered before HNSW insertion"""
+        n = len(offsets) - 1
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _lib.check(_lib.lib().gsb_sketch_fasta_batch_to_dev(self._h, _ptr(buf), _ptr(offsets), n,
+                                                            C.c_void_p(d_sig_ptr), C.c_void_p(d_nb_ptr)))
+
     def sketch_pointers(self, bytes_ptr, offsets, n, sig_ptr, nb_ptr=0):
         """Raw HOST pointers (e.g. torch pinned tensors): the e2e path of bench.py."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)

@@ -144,6 +144,11 @@ GSB_API int gsb_sketch_fasta_batch_dev(gsb_sketcher *h, const uint8_t *d_bytes,
                                        const uint64_t *h_offsets, uint32_t n, void *d_sig_out,
                                        uint64_t *d_nb_bases_out, void *stream);
 
+/* host FASTA in (as gsb_sketch_fasta_batch), signatures and encoded lengths out to DEVICE memory:
+ * e.g. straight into this rank's slice of the signature matrix that is all-gathered next        */
+GSB_API int gsb_sketch_fasta_batch_to_dev(gsb_sketcher *h, const uint8_t *bytes,
+                                          const uint64_t *offsets, uint32_t n, void *d_sig_out,
+                                          uint64_t *d_nb_bases_out /* may be NULL */);
 /* number of kernel launches issued by this handle so far (bench bookkeeping) */
 GSB_API uint64_t gsb_sketcher_launch_count(const gsb_sketcher *h);
 /* number of genomes whose early-stop bound had to be widened and re-run so far */
@@ -171,6 +176,16 @@ GSB_API void gsb_sketcher_kernel_times(const gsb_sketcher *h, double *ms_out /*[
 /*   Hnsw::<Sig,DistHamming>::new (src/dna/dnasketch.rs:139) and directly at  */
 /*   src/bin/bindash.rs:94-95:  count(a[i] != b[i]) as f32 / len as f32.      */
 /* ------------------------------------------------------------------------- */
+
+/* Scalar, signature-compatible with anndists' DistCFFI / DistCFnPtr<T> plug point [U]
+ * (`extern "C" fn(*const T, *const T, len: u64) -> f32`, SURVEY 8b "distance surface"): what
+ * Distance::eval(va, vb) computes for one pair.  One pair per call on device 0 (GSB_DEVICE
+ * overrides): a convenience for drop-in wiring, latency bound -- hot paths use the batched forms
+ * below or the index.  On error the result is NaN and gsb_last_error() holds the reason.        */
+GSB_API float gsb_dist_hamming_u16(const uint16_t *a, const uint16_t *b, unsigned long long len);
+GSB_API float gsb_dist_hamming_u32(const uint32_t *a, const uint32_t *b, unsigned long long len);
+GSB_API float gsb_dist_hamming_u64(const uint64_t *a, const uint64_t *b, unsigned long long len);
+GSB_API float gsb_dist_hamming_f32(const float *a, const float *b, unsigned long long len);
 
 /* Batched: one query signature against n candidate signatures (row-major n x S).
  * elem = gsb_sig_type.  out[i] = hamming(q, cands[i]).  Host pointers.           */
@@ -261,6 +276,54 @@ GSB_API int gsb_index_set_wave_max(gsb_index *idx, uint32_t wave_max);
  * this library's own layout; hnswio byte compatibility is not claimed         */
 GSB_API int gsb_index_dump(const gsb_index *idx, const char *dir, const char *basename);
 GSB_API int gsb_index_load(gsb_index *idx, const char *dir, const char *basename);
+
+/* ------------------------------------------------------------------------- */
+/* device / pinned-host buffers for hosts without a CUDA binding of their own  */
+/* ------------------------------------------------------------------------- */
+GSB_API int gsb_device_malloc(int device, uint64_t bytes, void **out);
+GSB_API void gsb_device_free(int device, void *p);
+GSB_API int gsb_memcpy_h2d(int device, void *d_dst, const void *src, uint64_t bytes);
+GSB_API int gsb_memcpy_d2h(int device, void *dst, const void *d_src, uint64_t bytes);
+GSB_API int gsb_host_alloc_pinned(uint64_t bytes, void **out);
+GSB_API void gsb_host_free_pinned(void *p);
+
+/* ------------------------------------------------------------------------- */
+/* multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch                 */
+/*   The reference is one process (src/dna/dnasketch.rs:421-435: sketch every  */
+/*   file, then insert all signatures).  Here genomes shard by rank, finished   */
+/*   signatures are exchanged with one all-gather, and HNSW insertion is        */
+/*   sharded by point inside every wave.  NCCL is loaded at run time (dlopen);  */
+/*   single-GPU consumers never need it.                                        */
+/* ------------------------------------------------------------------------- */
+#define GSB_COMM_ID_BYTES 128
+typedef struct gsb_comm gsb_comm;
+/* rank 0 draws the id and ships it to the other ranks (pipe, file, MPI, torch.distributed ...) */
+GSB_API int gsb_comm_unique_id(uint8_t *id_out /* GSB_COMM_ID_BYTES */);
+/* collective: every rank calls it with the same id and nranks */
+GSB_API int gsb_comm_create(const uint8_t *id, int nranks, int rank, int device, gsb_comm **out);
+GSB_API void gsb_comm_destroy(gsb_comm *c);
+GSB_API int gsb_comm_rank(const gsb_comm *c);
+GSB_API int gsb_comm_size(const gsb_comm *c);
+/* all-gather of `bytes_per_rank` device bytes per rank into d_recv (nranks * bytes_per_rank, rank r at
+ * offset r * bytes_per_rank).  In place when d_send == d_recv + rank * bytes_per_rank: the sketcher
+ * (gsb_sketch_fasta_batch_dev) can write its signatures straight into its slice of the replicated
+ * matrix.  stream NULL: the communicator's own stream, synchronised before returning.         */
+GSB_API int gsb_comm_all_gather(gsb_comm *c, const void *d_send, void *d_recv, uint64_t bytes_per_rank,
+                                void *stream);
+GSB_API int gsb_comm_broadcast(gsb_comm *c, void *d_buf, uint64_t bytes, int root, void *stream);
+/* all-gather of row-sharded results into GLOBAL unit order.  Unit i (genome or query) lives on rank
+ * i mod nranks as that rank's local row i / nranks; d_local holds rows_per_rank rows of row_bytes,
+ * d_tmp nranks * rows_per_rank rows, d_out n_total rows: row i = unit i on every rank.            */
+GSB_API int gsb_comm_all_gather_rows(gsb_comm *c, const void *d_local, uint64_t rows_per_rank,
+                                     uint64_t row_bytes, uint64_t n_total, void *d_tmp, void *d_out,
+                                     void *stream);
+/* parallel_insert over the GPUs of `comm`: EVERY rank calls it with the same signatures (host or
+ * device pointer; normally the all-gathered matrix), ids and index parameters.  Inside each wave a
+ * rank searches / selects for its slice of the points (all the distance evaluations), the selections
+ * are all-gathered and every rank applies the same link updates: all replicas end bit-identical to
+ * the graph gsb_index_insert_batch builds on one GPU with the same wave_max.                  */
+GSB_API int gsb_index_insert_batch_sharded(gsb_index *idx, gsb_comm *comm, const void *sigs,
+                                           const uint64_t *ids, uint64_t n);
 
 #ifdef __cplusplus
 }

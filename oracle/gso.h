@@ -59,6 +59,7 @@ uint64_t gso_uniform_usize(gso_xoshiro *r, uint64_t m); /* Uniform::<usize>::new
 typedef struct { double lambda, c1, c2, c3; } gso_exp01;
 void gso_exp01_init(gso_exp01 *e, double lambda);
 double gso_exp01_sample(const gso_exp01 *e, gso_xoshiro *r);
+double gso_expm1_spec(double z); /* the frozen expm1 of the sampler's rejection branch, 0 <= z <= ln 2 */
 
 /* ---------------- fasta.c : needletail-like parse + encode ------------------ */
 /* One encoded sequence per kept record (seq mode) or one per file (block mode).

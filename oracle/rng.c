@@ -82,6 +82,18 @@ void gso_exp01_init(gso_exp01 *e, double lambda) {
     e->c3 = (1.0 - exp(-lambda)) / lambda;
 }
 
+/* expm1(z) for 0 <= z <= ln 2, as this repository FREEZES it: the degree-24 Taylor polynomial in
+ * Horner form, every step one correctly rounded IEEE operation (no contraction).  The reference
+ * calls the platform libm (Rust f64::exp_m1), whose last bit is not specified; the restatement and
+ * the CUDA kernel (common.cuh expm1_spec) must agree with EACH OTHER bit for bit, so both evaluate
+ * this.  It is within 2 ulp of libm on the whole range and only decides the last test of the
+ * rejection branch below.                                                                    */
+double gso_expm1_spec(double z) {
+    double r = 1.0;
+    for (int k = 24; k >= 2; k--) r = 1.0 + (z / (double)k) * r;
+    return z * r;
+}
+
 /* ExpRestricted01::sample */
 double gso_exp01_sample(const gso_exp01 *e, gso_xoshiro *r) {
     double x = e->c1 * gso_uniform_f64(r);
@@ -96,6 +108,6 @@ double gso_exp01_sample(const gso_exp01 *e, gso_xoshiro *r) {
         }
         if (x <= e->c3 * (1.0 - y)) return x;
         if (e->c1 * y <= 1.0 - x) return x;
-        if (y * e->c1 * e->lambda <= expm1(e->lambda * (1.0 - x))) return x;
+        if (y * e->c1 * e->lambda <= gso_expm1_spec(e->lambda * (1.0 - x))) return x;
     }
 }

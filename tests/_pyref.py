@@ -24,6 +24,14 @@ def rotl(x, k):
     return ((x << k) | (x >> (64 - k))) & M64
 
 
+def expm1_spec(z):
+    """the frozen expm1 of the sampler's rejection branch (oracle/rng.c gso_expm1_spec)"""
+    r = 1.0
+    for k in range(24, 1, -1):
+        r = 1.0 + (z / float(k)) * r
+    return z * r
+
+
 class Xoshiro:
     def __init__(self, seed=None, state=None):
         if state is not None:
@@ -86,7 +94,7 @@ class Exp01:
                 return x
             if self.c1 * y <= 1.0 - x:
                 return x
-            if y * self.c1 * self.lam <= math.expm1(self.lam * (1.0 - x)):
+            if y * self.c1 * self.lam <= expm1_spec(self.lam * (1.0 - x)):
                 return x
 
 

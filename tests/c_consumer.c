@@ -53,6 +53,9 @@ int main(void) {
     float d[N * N];
     if (gsb_hamming_matrix(sig, N, sig, N, S, GSB_SIG_U64, d, 0)) return 1;
     if (d[0 * N + 1] != 0.0f || d[0 * N + 2] < 0.9f) return 1; /* same sequence: distance 0 */
+    /* the scalar Distance::eval-shaped export (DistCFnPtr<u64>) gives the same bits, one pair per call */
+    float (*eval64)(const uint64_t *, const uint64_t *, unsigned long long) = gsb_dist_hamming_u64;
+    if (eval64(sig, sig + 2 * S, S) != d[0 * N + 2] || eval64(sig, sig + S, S) != 0.0f) return 1;
     gsb_index_params ip = {8, 1000, 16, 32, 1.0, GSB_SIG_U64, S, 1, 0, 0x5EED};
     gsb_index *idx = NULL;
     if (gsb_index_create(&ip, 0, &idx)) return 1;

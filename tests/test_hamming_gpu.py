@@ -50,3 +50,20 @@ def test_symmetry_and_triangle_at_scale():
     d = g.DistHamming().matrix(x, x)
     assert (d == d.T).all() and (np.diag(d) == 0).all()
     assert (d[0][:, None] + d <= 1e-6 + 2.0).all()
+
+
+@pytest.mark.parametrize("dtype,fn", [(np.uint16, "gsb_dist_hamming_u16"), (np.uint32, "gsb_dist_hamming_u32"),
+                                      (np.uint64, "gsb_dist_hamming_u64"), (np.float32, "gsb_dist_hamming_f32")])
+def test_scalar_distcfnptr_exports(oracle, dtype, fn):
+    """`extern "C" fn(*const T, *const T, len: u64) -> f32` (anndists DistCFFI shape): same
+    bits as the oracle's DistHamming::eval, one pair per call; errors come back as NaN"""
+    import ctypes as C
+    from gsearch_b200 import _lib
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 50, 12000).astype(dtype)
+    b = np.where(rng.random(12000) < 0.6, a, rng.integers(0, 50, 12000).astype(dtype)).astype(dtype)
+    f = getattr(_lib.lib(), fn)
+    got = f(C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), len(a))
+    assert np.float32(got).tobytes() == np.float32(oracle.hamming(a, b)).tobytes()
+    assert f(C.c_void_p(a.ctypes.data), C.c_void_p(a.ctypes.data), len(a)) == 0.0
+    assert np.isnan(f(C.c_void_p(0), C.c_void_p(b.ctypes.data), 5))

@@ -373,3 +373,20 @@ def test_fasta_parser_fuzz_against_python():
                 assert got == R.parse_fasta(data, data_t, block), (data, data_t, block)
 
     check()
+
+
+def test_expm1_spec_is_the_same_function_in_c_and_python_and_close_to_libm(oracle):
+    """the sampler's rejection branch evaluates a FROZEN expm1 (degree-24 Horner polynomial, one
+    rounded operation per step) so that the C oracle, the Python restatement and the CUDA kernel
+    agree bit for bit; it must stay within 2 ulp of libm on [0, ln 2]"""
+    import ctypes
+    import math
+    import _pyref as P
+    L = oracle.L()
+    L.gso_expm1_spec.restype = ctypes.c_double
+    L.gso_expm1_spec.argtypes = [ctypes.c_double]
+    rng = np.random.default_rng(8)
+    for z in list(rng.random(20000) * math.log(2.0)) + [0.0, 1e-300, 5.6e-5, math.log(2.0)]:
+        a = L.gso_expm1_spec(float(z))
+        assert a == P.expm1_spec(float(z))
+        assert abs(a - math.expm1(z)) <= 2 * math.ulp(math.expm1(z)) if z > 0 else a == 0.0

@@ -85,6 +85,16 @@ def test_prob_partition_large_k_uses_64_bit_keys(oracle):
     sk.close()
 
 
+@pytest.mark.parametrize("S", [2, 3, 7])
+def test_prob_tiny_sketch_sizes_take_the_rejection_branch(oracle, S):
+    """lambda = ln(m / (m - 1)) is large for a tiny m, so c1 = expm1(lambda) / lambda is well above 1
+    and about a third of the first draws enter the rejection loop of ExpRestricted01 -- the only
+    place expm1 is evaluated (by the frozen gso_expm1_spec on both sides, not by two libms)"""
+    files = [g.synth.dna_genome(90 + i, 60_000) for i in range(3)]
+    assert_same(*run_both(oracle, files, 21, S))
+    assert_same(*run_both(oracle, files, 16, S))
+
+
 def test_prob_heavy_repeats(oracle):
     rng = np.random.default_rng(1)
     unit = rand_seq(rng, 300)
