@@ -600,10 +600,43 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
         dist.broadcast(d_q_all, 0)
     torch.cuda.synchronize()
     idx = g.Hnsw(g.HnswParams(max_nb_conn=a.nbng, ef=a.ef), S, np.uint64, device=local)
+    comm = None
+    if world > 1:
+        # HNSW construction sharded over the GPUs (gsb_index_insert_batch_sharded): inside every
+        # insertion wave a rank searches / selects for its slice of the points, the selections are
+        # all-gathered (NCCL behind the C ABI) and every rank applies the same link updates
+        uid_t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid_t.copy_(torch.frombuffer(bytearray(g.comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid_t, 0)
+        comm = g.comm.Comm(bytes(uid_t.cpu().numpy().tobytes()), world, rank, local)
+        idx.set_wave_max(min(512, 296 * world))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    idx.insert_device(d_db.data_ptr(), np.arange(n, dtype=np.uint64))
+    if comm is not None:
+        idx.insert_sharded(comm, d_db.data_ptr(), np.arange(n, dtype=np.uint64))
+    else:
+        idx.insert_device(d_db.data_ptr(), np.arange(n, dtype=np.uint64))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
+    build_parity = None
+    if world > 1:
+        tb = torch.tensor([t_build], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        t_build = float(tb.item())
+        # every replica must hold the same graph: compare a checksum of the exported adjacency
+        import hashlib
+        gr = idx.export_graph()
+        hsh = hashlib.sha256(gr["nbr_index"].tobytes() + gr["nbr_offsets"].tobytes() + gr["levels"].tobytes()).digest()
+        hv = torch.tensor([int.from_bytes(hsh[:7], "little")], dtype=torch.int64, device=dev)
+        lo, hi = hv.clone(), hv.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert int(lo.item()) == int(hi.item()), "sharded insertion left different graphs on different GPUs"
+        build_parity = {"replica_graph_checksums_equal": True, "links": int(len(gr["nbr_index"]))}
+        del gr
     # this rank's queries: j mod world == rank (src/dna/dnarequest.rs:353: one query = one task)
     mine = torch.arange(rank, nq, world, device=dev)
     d_q = d_q_all[mine].contiguous()
@@ -723,7 +756,12 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
     head = recs[a.ef_search[0]]
     head["clocks"] = clk
     head["build"] = {"genomes_per_s_inserted": n / t_build, "seconds": t_build, "kernel": "k8_hnsw_insert_select",
-                     "ef_construction": a.ef, "replicated_on_every_gpu": world > 1, "datagen_seconds": t_gen}
+                     "ef_construction": a.ef, "datagen_seconds": t_gen,
+                     "sharding": ("gsb_index_insert_batch_sharded: phase A of every wave split over the GPUs, "
+                                  "selections all-gathered, wave_max %d" % min(512, 296 * world)) if world > 1
+                     else "single GPU, wave_max 296"}
+    if build_parity:
+        head["build"]["multi_gpu_parity"] = build_parity
     head["recall_at_knbn_on_8_queries"] = hits / (nchk * a.knbn)
     if parity:
         head["multi_gpu_parity"] = parity

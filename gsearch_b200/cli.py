@@ -6,9 +6,10 @@ layout, so a database is served by the binary that built it.  Host s
 JSON / text; sketching, HNSW construction and search all run in libgsearch_b200.so on the GPU.
 
   gsearch [--pio N] [--nbthreads N] tohnsw -d DIR -k K -s S -n NBNG [--ef EF]
-          [--scale_modify_f F] --algo prob|super|optdens [--aa] [--block]
+          [--scale_modify_f F] --algo prob|super|super2|optdens|revoptdens [--aa] [--block]
   gsearch add -b DBDIR -n NEWDIR
   gsearch request -b DBDIR -r QUERYDIR -n NBANSWERS
+  gsearch bindash -q QUERY_LIST -r REFERENCE_LIST [-k 16] [-s 2048] [-d 0|1] [-o OUT]   (src/bin/bindash.rs)
 
 Outputs, as in the reference: tohnsw writes hnswdump.hnsw.graph, hnswdump.hnsw.data, seqdict.json,
 parameters.json and processing_state.json into the CURRENT directory (src/dna/dnasketch.rs:152-156),
@@ -360,6 +361,40 @@ def cmd_request(a):
     print(f"request: {len(files)} queries answered in gsearch.neighbors.txt")
 
 
+def cmd_bindash(a):
+    """bindash-rs (src/bin/bindash.rs): OptDens / RevOptDens sketches of two genome lists and ALL
+    query x reference distances.  Sketches stay on the device; the distance matrix is one tiled
+    Hamming kernel (K6) instead of |Q| x |R| DistHamming::eval calls (bindash.rs:93-164); the ANI-style
+    transformation 1 - (2J / (1 + J))^(1/k) and the text output are the reference's (:92-99, :101-164).
+    Unlike the reference's k <= 14 branch (bindash.rs:349-354) k-mers are always canonical here."""
+    import ctypes as C
+    import gsearch_b200 as g
+    from . import _lib
+    from .comm import DeviceBuffer
+    read_list = lambda p: [ln.strip() for ln in open(p) if ln.strip()]
+    qfiles, rfiles = read_list(a.query_list), read_list(a.reference_list)
+    p = {"kmer": a.kmer_size, "sketch": a.sketch_size, "algo": "revoptdens" if a.densification == 1 else "optdens",
+         "aa": False, "block": False}
+    q = DeviceSignatures(g, qfiles, p, a.pio, nbthreads=a.threads or a.nbthreads)
+    r = DeviceSignatures(g, rfiles, p, a.pio, nbthreads=a.threads or a.nbthreads) if rfiles != qfiles else q
+    nq, nr = len(qfiles), len(rfiles)
+    d_out = DeviceBuffer(max(1, nq * nr) * 4)
+    _lib.check(_lib.lib().gsb_hamming_matrix_dev(C.c_void_p(q.d_sig.ptr), nq, C.c_void_p(r.d_sig.ptr), nr,
+                                                 a.sketch_size, g.SIG_F32, C.c_void_p(d_out.ptr), C.c_void_p(0)))
+    ham = d_out.download(np.float32, nq * nr).reshape(nq, nr)   # (the copy synchronises with the kernel)
+    j = np.float32(1.0) - ham
+    frac = (np.float32(2.0) * j) / (np.float32(1.0) + j)
+    dist = 1.0 - np.power(frac, np.float32(1.0 / a.kmer_size), dtype=np.float32).astype(np.float64)
+    out = open(a.output, "w") if a.output else sys.stdout
+    out.write("Query\tReference\tDistance\n")
+    for i, qp in enumerate(qfiles):
+        for k, rp in enumerate(rfiles):
+            d = 0.0 if os.path.basename(qp) == os.path.basename(rp) else dist[i, k]
+            out.write(f"{qp}\t{rp}\t{d:.6f}\n")
+    if a.output:
+        out.close()
+
+
 def build_parser():
     ap = argparse.ArgumentParser(prog="gsearch", description="GSearch sketch-and-search path on B200")
     ap.add_argument("--pio", type=int, default=64, help="files read and sketched together")
@@ -388,6 +423,15 @@ def build_parser():
     r.add_argument("-n", "--nbanswers", type=int, required=True)
     r.add_argument("-r", "--query", required=True)
     r.set_defaults(fn=cmd_request)
+    b = sub.add_parser("bindash", help="all-pairs OptDens / RevOptDens distances (src/bin/bindash.rs)")
+    b.add_argument("-q", "--query_list", required=True)
+    b.add_argument("-r", "--reference_list", required=True)
+    b.add_argument("-k", "--kmer_size", type=int, default=16)
+    b.add_argument("-s", "--sketch_size", type=int, default=2048)
+    b.add_argument("-d", "--densification", type=int, default=0, choices=[0, 1])
+    b.add_argument("-t", "--threads", type=int, default=0)
+    b.add_argument("-o", "--output", default=None)
+    b.set_defaults(fn=cmd_bindash)
     return ap
 
 

@@ -144,12 +144,13 @@ struct gsb_sketcher {
     SketchConsts sc;
     cudaStream_t stream = nullptr;
     DevBuf d_files, d_tile_prefix, d_tc4, d_ttrans, d_tnrec, d_tstate, d_tbase, d_trecbase, d_res,
-        d_packed, d_bounds, d_misc, d_retry, d_jobs, d_chunk_prefix, d_bound, d_overflow, d_bins;
+        d_packed, d_bounds, d_misc, d_retry, d_jobs, d_chunk_prefix, d_bound, d_overflow, d_bins, d_fqflag;
     PinBuf h_files, h_tile_prefix, h_jobs, h_chunk_prefix, h_retry, h_overflow;
     ProbSlot slot[kMaxSlots];
     DevBuf d_bytes, d_sig, d_nb;
     uint64_t launches = 0, retries = 0, fallbacks = 0;
     int prob_path = 0;  // 0 = partition path with filter fallback, 1 = filter path only
+    size_t dens_pass_files = 0;  // files of the current run_dens pass (RevOptDens scratch offset)
     std::vector<uint32_t> pending_fallback;  // files flagged by the partition path, waiting for the filter path
     std::vector<double> pending_fallback_t;
     // optional per-kernel-family timing (bench.py's roofline): CUDA events around launches
@@ -216,7 +217,7 @@ void collect_spans(gsb_sketcher *h) {  // call after the stream has been synchro
 }  // namespace
 
 static int sig_type_of(const gsb_sketch_params &p) {
-    if (p.algo == GSB_ALGO_PROB3A) {
+    if (p.algo == GSB_ALGO_PROB3A || p.algo == GSB_ALGO_SUPER2) {  // SuperHash2Sketch<Kmer, u32 | u64, Fx>: dnasketch.rs:575-599
         if (p.data_t == GSB_DATA_DNA) return (p.kmer_size <= 14 || p.kmer_size == 16) ? GSB_SIG_U32 : GSB_SIG_U64;
         return p.kmer_size <= 6 ? GSB_SIG_U32 : GSB_SIG_U64;
     }
@@ -243,9 +244,14 @@ extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, 
         set_error("sketch_size %u out of range 2..65535", p.sketch_size);
         return GSB_ERR_INVALID_ARG;
     }
-    if (p.algo != GSB_ALGO_PROB3A && p.algo != GSB_ALGO_OPTDENS && p.algo != GSB_ALGO_SUPER) {
-        set_error("algo %u is not built on the device path yet (prob, optdens, super are)", p.algo);
-        return p.algo <= GSB_ALGO_HLL ? GSB_ERR_UNSUPPORTED : GSB_ERR_INVALID_ARG;
+    if (p.algo == GSB_ALGO_HLL) {
+        set_error("--algo hll (HyperLogLogSketch<Kmer, u16> over probminhash's SetSketcher, src/dna/dnasketch.rs:541-574) "
+                  "is not built on the device path: prob, super, super2, optdens and revoptdens are");
+        return GSB_ERR_UNSUPPORTED;
+    }
+    if (p.algo > GSB_ALGO_HLL) {
+        set_error("unknown algo %u", p.algo);
+        return GSB_ERR_INVALID_ARG;
     }
     int rc = check_device(device);
     if (rc) return rc;
@@ -292,7 +298,7 @@ extern "C" void gsb_sketcher_destroy(gsb_sketcher *h) {
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&h->d_files, &h->d_tile_prefix, &h->d_tc4, &h->d_ttrans, &h->d_tnrec, &h->d_tstate,
                       &h->d_tbase, &h->d_trecbase, &h->d_res, &h->d_packed, &h->d_bounds, &h->d_misc,
-                      &h->d_retry, &h->d_jobs, &h->d_chunk_prefix, &h->d_bound, &h->d_overflow, &h->d_bins,
+                      &h->d_retry, &h->d_jobs, &h->d_chunk_prefix, &h->d_bound, &h->d_overflow, &h->d_bins, &h->d_fqflag,
                       &h->d_bytes, &h->d_sig, &h->d_nb};
     for (DevBuf *b : bufs) b->release();
     for (auto &s : h->slot) {
@@ -371,12 +377,13 @@ void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t
         Timed ts_(h, CAT_K1_SUMMARY, st);
         k1a_tile_summary<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
             d_bytes, total, files, tprefix, nf, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(),
-            h->d_tnrec.as<uint16_t>(), tile0);
+            h->d_tnrec.as<uint16_t>(), tile0, h->d_fqflag.as<uint32_t>() + f0);
     }
     k1b_resolve<<<(nf * 32 + 127) / 128, 128, 0, st>>>(
         files, nf, d_bytes, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>(),
         h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(), h->d_trecbase.as<uint32_t>(), res,
-        h->d_misc.as<uint32_t>(), bd_cap, want_bounds ? 1 : 0, (DATA_T == 1 && SEQ_SEP) ? 1 : 0);
+        h->d_misc.as<uint32_t>(), bd_cap, want_bounds ? 1 : 0, (DATA_T == 1 && SEQ_SEP) ? 1 : 0,
+        h->d_fqflag.as<uint32_t>() + f0);
     k1c_pack<DATA_T, SEQ_SEP><<<ntiles, kK1Threads, 0, st>>>(
         d_bytes, total, files, tprefix, nf, h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(),
         h->d_trecbase.as<uint32_t>(), res, DATA_T == 0 ? h->d_packed.as<uint32_t>() : nullptr,
@@ -502,11 +509,7 @@ void launch_part_group(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t 
                 ca.slot2[i] = pj.slot2;
                 ca.cap_g[i] = pj.cap_g;
             }
-            // GSB_COUNT_R > 0: persistent CTAs (R per SM) that prefetch the next bucket's run; 0 (default,
-            // measured faster): one CTA per (genome, bucket), the hardware scheduler does the balancing
-            const int cr = env_int("GSB_COUNT_R", 0, 0, 8);
-            const uint32_t cgrid = cr ? std::min<uint32_t>(njobs * kNB, (uint32_t)(h->nsm * cr)) : njobs * kNB;
-            k2p_count<KT, KEY><<<cgrid, kCThreads, csm, st>>>(ca, njobs, bound, h->sc, pc, ovf);
+            k2p_count<KT, KEY><<<dim3(kNB, njobs), kCThreads, csm, st>>>(ca, njobs, bound, h->sc, pc, ovf);
         }
     }
     Timed t3_(h, CAT_K3, st);
@@ -557,17 +560,37 @@ void launch_dens(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunk
                  bool want_bounds, void *d_sig, uint64_t *d_nb, cudaStream_t st) {
     const DensJob *jobs = h->d_jobs.as<DensJob>() + joff;
     const FileResult *res = h->d_res.as<FileResult>();
+    const bool super2 = h->p.algo == GSB_ALGO_SUPER2;
     if (nchunks) {
         Timed t_(h, CAT_K2_MARK, st);
         const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * 4));
-        k2_optdens<Src, KT><<<grid, kK2Threads, 0, st>>>(
-            jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
-            dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-            want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
+        if (super2)
+            k2_super2<Src, KT><<<grid, kK2Threads, 0, st>>>(
+                jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+                dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
+        else
+            k2_optdens<Src, KT><<<grid, kK2Threads, 0, st>>>(
+                jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+                dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
     }
     Timed t3_(h, CAT_K3, st);
-    k3_optdens_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (float *)d_sig, d_nb,
-                                               h->d_retry.as<uint32_t>(), h->p.algo == GSB_ALGO_SUPER ? 1 : 0);
+    if (super2) {
+        if (h->elem == 8)
+            k3_super2_finalize<uint64_t><<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (uint64_t *)d_sig, d_nb,
+                                                                h->d_retry.as<uint32_t>());
+        else
+            k3_super2_finalize<uint32_t><<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (uint32_t *)d_sig, d_nb,
+                                                                h->d_retry.as<uint32_t>());
+    } else {
+        // RevOptDens: per-file scratch for the round winners sits behind the bins of the whole pass
+        uint32_t *rev_win = h->p.algo == GSB_ALGO_REVOPTDENS ? h->d_bins.as<uint32_t>() + h->dens_pass_files * (size_t)h->sc.m +
+                                                                   (size_t)joff * h->sc.m
+                                                             : nullptr;
+        k3_optdens_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (float *)d_sig, d_nb,
+                                                   h->d_retry.as<uint32_t>(), h->p.algo == GSB_ALGO_SUPER ? 1 : 0, rev_win);
+    }
     h->launches += nchunks ? 2 : 1;
 }
 
@@ -729,13 +752,26 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     return GSB_OK;
 }
 
-// SuperMinHash cold path: files whose k-mers do not reach every slot at the first level
+// SuperMinHash / SuperMinHash2 cold path: files whose k-mers do not reach every slot at the first level
 template <class Src, typename KT>
 void launch_super_seq(gsb_sketcher *h, uint32_t nlist, bool dna, bool want_bounds, void *d_sig, cudaStream_t st) {
-    k_super_sequential<Src, KT><<<(nlist + 31) / 32, 32, 0, st>>>(
-        h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(),
-        dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
-        want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, (float *)d_sig, h->d_bins.as<uint32_t>());
+    const uint32_t *packed_dna = dna ? h->d_packed.as<uint32_t>() : nullptr;
+    const uint8_t *packed_aa = dna ? nullptr : h->d_packed.as<uint8_t>();
+    const uint32_t *bounds = want_bounds ? h->d_bounds.as<uint32_t>() : nullptr;
+    if (h->p.algo == GSB_ALGO_SUPER2) {
+        if (h->elem == 8)
+            k_super2_sequential<Src, KT, uint64_t><<<(nlist + 31) / 32, 32, 0, st>>>(
+                h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(), packed_dna,
+                packed_aa, bounds, h->sc, (uint64_t *)d_sig, h->d_bins.as<uint8_t>());
+        else
+            k_super2_sequential<Src, KT, uint32_t><<<(nlist + 31) / 32, 32, 0, st>>>(
+                h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(), packed_dna,
+                packed_aa, bounds, h->sc, (uint32_t *)d_sig, h->d_bins.as<uint8_t>());
+    } else {
+        k_super_sequential<Src, KT><<<(nlist + 31) / 32, 32, 0, st>>>(
+            h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(), packed_dna, packed_aa,
+            bounds, h->sc, (float *)d_sig, h->d_bins.as<uint32_t>());
+    }
     h->launches += 1;
 }
 
@@ -746,7 +782,7 @@ int run_super_sequential(gsb_sketcher *h, const std::vector<uint32_t> &list, voi
     int rc;
     if ((rc = h->h_jobs.ensure((size_t)nl * 4))) return rc;
     if ((rc = h->d_jobs.ensure((size_t)nl * 4))) return rc;
-    if ((rc = h->d_bins.ensure((size_t)nl * 3 * h->sc.m * 4))) return rc;
+    if ((rc = h->d_bins.ensure((size_t)nl * h->sc.m * (h->p.algo == GSB_ALGO_SUPER2 ? 28 : 12) + 64))) return rc;
     memcpy(h->h_jobs.p, list.data(), (size_t)nl * 4);
     GSB_CUDA_TRY(pull_small(h->d_jobs.p, h->h_jobs.p, (size_t)nl * 4, st));
     if (dna) {
@@ -774,7 +810,11 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     if ((rc = h->d_jobs.ensure((size_t)n * sizeof(DensJob)))) return rc;
     if ((rc = h->h_chunk_prefix.ensure((size_t)ngroups * (grp + 1) * 4))) return rc;
     if ((rc = h->d_chunk_prefix.ensure((size_t)ngroups * (grp + 1) * 4))) return rc;
-    if ((rc = h->d_bins.ensure((size_t)n * h->sc.m * 4))) return rc;
+    const bool super2 = h->p.algo == GSB_ALGO_SUPER2;
+    // per file: m f32 bins (+ m round winners for RevOptDens), or m 128-bit (r, hash) slots for SuperMinHash2
+    const size_t per_file = super2 ? (size_t)h->sc.m * 16 : (size_t)h->sc.m * 4 * (h->p.algo == GSB_ALGO_REVOPTDENS ? 2 : 1);
+    if ((rc = h->d_bins.ensure((size_t)n * per_file + 64))) return rc;
+    h->dens_pass_files = n;
     DensJob *hj = h->h_jobs.as<DensJob>();
     uint32_t *hcp = h->h_chunk_prefix.as<uint32_t>();
     std::vector<uint32_t> group_chunks(ngroups);
@@ -787,7 +827,8 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 const uint32_t f = todo[i];
                 const size_t len = h_offsets[f + 1] - h_offsets[f];
                 hj[i].file = f;
-                hj[i].bins = h->d_bins.as<uint32_t>() + (size_t)i * h->sc.m;
+                hj[i].bins = super2 ? reinterpret_cast<uint32_t *>(h->d_bins.as<ulonglong2>() + (size_t)i * h->sc.m)
+                                    : h->d_bins.as<uint32_t>() + (size_t)i * h->sc.m;
                 hj[i].tmult = tmult[i];
                 acc += (len + kChunk - 1) / kChunk;
             }
@@ -800,7 +841,8 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     }
     GSB_CUDA_TRY(pull_small(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), st));
     GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (grp + 1) * 4, st));
-    k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
+    if (super2) k_super2_reset<<<592, 256, 0, st>>>(h->d_bins.as<ulonglong2>(), (size_t)n * h->sc.m);
+    else k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
     h->launches += 1;
     GSB_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
     for (auto gs : h->gstream) GSB_CUDA_TRY(cudaStreamWaitEvent(gs, h->ev_fork, 0));
@@ -926,11 +968,13 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
     if ((rc = h->d_misc.ensure(256))) return rc;
     if ((rc = h->d_retry.ensure((size_t)n * 4))) return rc;
     if ((rc = h->h_retry.ensure((size_t)n * 4))) return rc;
+    if ((rc = h->d_fqflag.ensure((size_t)n * 4))) return rc;
 
     GSB_CUDA_TRY(pull_small(h->d_files.p, hf, (size_t)n * sizeof(FileDesc), st));
     GSB_CUDA_TRY(pull_small(h->d_tile_prefix.p, htp, (size_t)(n + 1) * 4, st));
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
     GSB_CUDA_TRY(cudaMemsetAsync(h->d_retry.p, 0, (size_t)n * 4, st));
+    GSB_CUDA_TRY(cudaMemsetAsync(h->d_fqflag.p, 0, (size_t)n * 4, st));
     if (dna) GSB_CUDA_TRY(cudaMemsetAsync(h->d_packed.p, 0, packed_bytes, st));
     K1Plan kp;
     kp.d_bytes = d_bytes;
@@ -972,6 +1016,16 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
             if (status == 5) {
                 set_error("file %u starts with neither '>' nor '@' (not FASTA / FASTQ)", h->file_base + f);
                 return GSB_ERR_BAD_INPUT;
+            }
+            if (status == 6) {
+                set_error("file %u: malformed FASTQ record (a line that should start with '@' or '+' does not, or "
+                          "the last record is truncated)", h->file_base + f);
+                return GSB_ERR_BAD_INPUT;
+            }
+            if (status == 9) {
+                set_error("file %u: FASTQ text contains \"capsid\": the reference drops records by id "
+                          "(src/dna/dnafiles.rs:67), which the FASTQ device path does not implement", h->file_base + f);
+                return GSB_ERR_UNSUPPORTED;
             }
             if (status == 8) {
                 set_error("file %u: record-boundary pool exhausted", h->file_base + f);

@@ -19,7 +19,13 @@
 //                      four possible incoming states;
 //   k1b_resolve      : one warp per file walks its tiles, resolves states, prefix-sums counts;
 //   k1c_pack         : per tile again (bytes now come from L2), compacts and writes.
-// Parser state s = in_header | dropped<<1.  Every byte is a function {0..3}->{0..3}:
+// FASTQ (first byte '@'; needletail reads four-line records only [U]) runs through the same three
+// kernels with another 4-state machine: s = line number mod 4, '\n' is s -> s+1, a byte is emitted
+// iff it is in the alphabet and s == 1 (the sequence line), a record starts at the file's first
+// byte and at every newline that leads to s == 0.  Lines that must start with '@' / '+' are
+// checked (status 6).  A FASTQ file whose text contains "capsid" is refused (status 9): the
+// reference would drop such records, this path has no state bit left for it.
+// FASTA parser state s = in_header | dropped<<1.  Every byte is a function {0..3}->{0..3}:
 //   '>' at a line start : s -> 1          (new record: in header, not dropped)
 //   '\n'                : s -> s & 2      (header ends)
 //   'c' of "capsid"     : s -> s|2 if s&1 (record id contains "capsid": dropped)
@@ -65,6 +71,16 @@ __device__ __forceinline__ uint32_t fn_zero_lanes(uint32_t f) {
     return (z & 1u) | ((z >> 2) & 1u) << 8 | ((z >> 4) & 1u) << 16 | ((z >> 6) & 1u) << 24;
 }
 
+// byte lane s of the result = 1 iff f(s) == 1
+__device__ __forceinline__ uint32_t fn_one_lanes(uint32_t f) {
+    const uint32_t z = (f & ~(f >> 1)) & 0x55u;
+    return (z & 1u) | ((z >> 2) & 1u) << 8 | ((z >> 4) & 1u) << 16 | ((z >> 6) & 1u) << 24;
+}
+// every image + 1 mod 4 (FASTQ: a newline)
+__device__ __forceinline__ uint32_t fn_rot1(uint32_t f) {
+    const uint32_t lo = f & 0x55u, hi = (f >> 1) & 0x55u;
+    return (lo ^ 0x55u) | ((hi ^ lo) << 1);
+}
 // residues "ACDEFGHIKLMNPQRSTVWY" -> 1..20 without a table: bit (c - 'A') of the mask says valid,
 // the rank of that bit is the code (the alphabet string is in alphabetical order)
 constexpr uint32_t kAAMask = 0x16fbdfdu;
@@ -231,6 +247,32 @@ __device__ __forceinline__ void fold16(const uint8_t *p /* own 16 bytes; p[-1], 
     }
 }
 
+// FASTQ twin of fold16: bytes [lo, hi) of the chunk are inside the file.  `nl` = newlines seen (the
+// tile-level record count follows from it and the incoming state), `capsid` = the text occurs.
+template <int DATA_T, bool SEQ_SEP>
+__device__ __forceinline__ void fold16_fastq(const uint8_t *p, const uint8_t *aa_lut, int lo, int hi, bool file_start,
+                                             uint32_t &f, uint32_t &cnt4, uint32_t &nl, bool &capsid) {
+    f = kFnIdent;
+    cnt4 = 0;
+    nl = 0;
+    capsid = false;
+    uint32_t inc4 = fn_one_lanes(f);
+    if (DATA_T == 1 && SEQ_SEP && file_start) cnt4 += 1u;  // separator of the first record (incoming state 0)
+#pragma unroll 1
+    for (int i = lo; i < hi; i++) {
+        const uint32_t c = p[i];
+        if (c == '\n') {
+            f = fn_rot1(f);
+            nl++;
+            inc4 = fn_one_lanes(f);
+            if (DATA_T == 1 && SEQ_SEP) cnt4 += fn_zero_lanes(f);  // a record starts: separator symbol
+        } else {
+            if (c == 'c' && is_capsid(p + i)) capsid = true;
+            if (sym_code<DATA_T>(c, aa_lut) >= 0) cnt4 += inc4;
+        }
+    }
+}
+
 // block-wide exclusive scan of state functions (composition) -> returns F_excl for this
 // thread and the block total in *total
 __device__ __forceinline__ uint32_t block_scan_fn(uint32_t f, uint32_t *warp_tot /* 8 */,
@@ -324,7 +366,7 @@ __global__ void __launch_bounds__(kK1Threads)
 k1a_tile_summary(const uint8_t *__restrict__ bytes, uint64_t total,
                  const FileDesc *__restrict__ files, const uint32_t *__restrict__ tile_prefix,
                  uint32_t nfiles, uint64_t *__restrict__ t_counts4, uint8_t *__restrict__ t_trans,
-                 uint16_t *__restrict__ t_nrec, uint32_t tile0) {
+                 uint16_t *__restrict__ t_nrec, uint32_t tile0, uint32_t *__restrict__ fq_flags /* per file of the range */) {
     __shared__ __align__(16) uint8_t sm[kTile + 32];
     __shared__ uint8_t aa_lut[256];
     __shared__ uint32_t wtot[kK1Threads / 32];
@@ -341,7 +383,17 @@ k1a_tile_summary(const uint8_t *__restrict__ bytes, uint64_t total,
     uint32_t f, cnt4, nrec;
     Chunk16 ck;
     bool fast;
-    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec, ck, fast);
+    const bool fq = fd.end > fd.beg && bytes[fd.beg] == '@';  // uniform for the CTA
+    if (fq) {
+        const int64_t a0 = (int64_t)tbase + threadIdx.x * 16;
+        const int lo = (int)max((int64_t)0, (int64_t)fd.beg - a0), hi = (int)min((int64_t)16, (int64_t)fd.end - a0);
+        bool capsid;
+        fold16_fastq<DATA_T, SEQ_SEP>(p, aa_lut, lo, hi, a0 <= (int64_t)fd.beg && (int64_t)fd.beg < a0 + 16, f, cnt4,
+                                      nrec, capsid);
+        if (__syncthreads_or(capsid) && threadIdx.x == 0) atomicOr(fq_flags + fi, 1u);
+    } else {
+        fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec, ck, fast);
+    }
     uint32_t ftot;
     const uint32_t fex = block_scan_fn(f, wtot, &ftot);
     // this thread's symbol count for each possible tile-incoming state s0
@@ -386,11 +438,14 @@ __global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
                             const uint16_t *__restrict__ t_nrec, uint8_t *__restrict__ t_state,
                             uint32_t *__restrict__ t_base, uint32_t *__restrict__ t_recbase,
                             FileResult *__restrict__ res, uint32_t *__restrict__ bd_cursor,
-                            uint32_t bd_capacity, int want_boundaries, int sep_counts_as_symbol) {
+                            uint32_t bd_capacity, int want_boundaries, int sep_counts_as_symbol,
+                            const uint32_t *__restrict__ fq_flags) {
     const uint32_t fi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (fi >= nfiles) return;
     const uint32_t lane = lane_id();
     const FileDesc fd = files[fi];
+    const uint8_t first = fd.end > fd.beg ? bytes[fd.beg] : (uint8_t)'>';
+    const bool fq = first == '@';  // FASTQ: t_nrec holds the tile's newline count
     uint32_t s_carry = 0, base = 0, recbase = 0;
     for (uint32_t c0 = 0; c0 < fd.ntiles; c0 += 32) {
         const uint32_t i = c0 + lane;
@@ -409,7 +464,9 @@ __global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
         if (lane == 0) excl = kFnIdent;
         const uint32_t s_in = fn_apply(excl, s_carry);
         const uint32_t cnt = (uint32_t)((c4 >> (16 * s_in)) & 0xFFFFull);
-        uint32_t ci = cnt, ri = nr;
+        // FASTQ: a record starts at the file's first byte and at every newline that leads to line 0
+        const uint32_t nrr = fq ? (on ? ((s_in + nr) >> 2) + (i == 0 ? 1u : 0u) : 0u) : nr;
+        uint32_t ci = cnt, ri = nrr;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t u1 = __shfl_up_sync(0xffffffffu, ci, d);
@@ -422,7 +479,7 @@ __global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
         if (on) {
             t_state[T] = (uint8_t)s_in;
             t_base[T] = base + ci - cnt;
-            t_recbase[T] = recbase + ri - nr;
+            t_recbase[T] = recbase + ri - nrr;
         }
         s_carry = fn_apply(__shfl_sync(0xffffffffu, incl, 31), s_carry);
         base += __shfl_sync(0xffffffffu, ci, 31);
@@ -433,7 +490,7 @@ __global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
         r.nsym = base;
         r.nrec = recbase;
         r.nbases = sep_counts_as_symbol ? base - recbase : base;
-        r.status = (fd.end > fd.beg && bytes[fd.beg] != '>') ? 5u : 0u;
+        r.status = (first != '>' && first != '@') ? 5u : ((fq && fq_flags[fi]) ? 9u : 0u);
         r.bd_off = 0;
         r.pad_ = 0;
         if (want_boundaries) {
@@ -450,7 +507,7 @@ __global__ void __launch_bounds__(kK1Threads)
 k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__restrict__ files,
          const uint32_t *__restrict__ tile_prefix, uint32_t nfiles,
          const uint8_t *__restrict__ t_state, const uint32_t *__restrict__ t_base,
-         const uint32_t *__restrict__ t_recbase, const FileResult *__restrict__ res,
+         const uint32_t *__restrict__ t_recbase, FileResult *__restrict__ res,
          uint32_t *__restrict__ out_dna, uint8_t *__restrict__ out_aa,
          uint32_t *__restrict__ boundaries /* DNA seq mode, else null */, uint32_t tile0) {
     __shared__ __align__(16) uint8_t sm[kTile + 32];
@@ -470,11 +527,21 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
     const uint8_t *p = sm + 16 + threadIdx.x * 16;
     uint32_t f, cnt4, nrec;
     Chunk16 ck;
-    bool fast;
-    fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec, ck, fast);
+    bool fast = false;
+    const bool fq = bytes[fd.beg] == '@';  // uniform for the CTA (the file is not empty: it has tiles)
+    const int64_t a0 = (int64_t)tbase + threadIdx.x * 16;
+    const int lo = (int)max((int64_t)0, (int64_t)fd.beg - a0), hi = (int)min((int64_t)16, (int64_t)fd.end - a0);
+    const bool has_start = a0 <= (int64_t)fd.beg && (int64_t)fd.beg < a0 + 16;
+    if (fq) {
+        bool capsid;
+        fold16_fastq<DATA_T, SEQ_SEP>(p, aa_lut, lo, hi, has_start, f, cnt4, nrec, capsid);
+    } else {
+        fold16<DATA_T, SEQ_SEP>(p, aa_lut, f, cnt4, nrec, ck, fast);
+    }
     const uint32_t fex = block_scan_fn(f, wtot, nullptr);
     const uint32_t s0 = t_state[tile];
     uint32_t s = fn_apply(fex, s0);
+    if (fq) nrec = ((s + nrec) >> 2) + (has_start ? 1u : 0u);  // record starts of this chunk, now that its state is known
     const uint32_t cnt = (cnt4 >> (8 * s)) & 0xFFu;
     uint32_t tile_tot;
     const uint32_t sc = block_scan_add(cnt | (nrec << 16), wtot, &tile_tot);
@@ -483,7 +550,40 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
     const uint32_t ntile = tile_tot & 0xFFFFu;
     const uint32_t pbase = t_base[tile];
     // concrete pass: emit symbols into the staging buffer
-    if (fast) {
+    if (fq) {
+        uint32_t bad = 0;
+#pragma unroll 1
+        for (int i = lo; i < hi; i++) {
+            const uint32_t c = p[i];
+            const int64_t a = a0 + i;
+            bool start = a == (int64_t)fd.beg;  // (line state 0 by construction)
+            if (c == '\n') {
+                s = (s + 1) & 3u;
+                const bool more = a + 1 < (int64_t)fd.end;
+                const uint32_t nb = more ? p[i + 1] : 0u;
+                if (s == 0) {
+                    start = true;  // a trailing terminator opens an empty record: harmless (no symbol follows)
+                    if (more && nb != '@' && nb != '\n' && nb != '\r') bad = 6;  // InvalidStart inside the file
+                } else if (s == 2) {
+                    // InvalidSeparator.  (Blank lines after the last record keep the line counter turning:
+                    // they emit nothing, so a terminator or the end of the file is let through here; a
+                    // record cut before its '+' line is then NOT diagnosed, unlike in the reference.)
+                    if (more && nb != '+' && nb != '\n' && nb != '\r') bad = 6;
+                }
+            } else if (s == 1) {
+                const int code = sym_code<DATA_T>(c, aa_lut);
+                if (code >= 0) stage[o++] = (uint8_t)code;
+            }
+            if (start) {
+                if (DATA_T == 1 && SEQ_SEP) stage[o++] = 0;
+                if (DATA_T == 0 && boundaries) {
+                    boundaries[fr.bd_off + t_recbase[tile] + ro] = pbase + o;
+                    ro++;
+                }
+            }
+        }
+        if (bad) atomicMax(&res[fi].status, bad);
+    } else if (fast) {
         // emitted = symbols before the first newline if s == 0, after it if (s & 2) == 0
         uint32_t emit = ck.sym;
         if (ck.nl) {

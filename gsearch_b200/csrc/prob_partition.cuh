@@ -261,29 +261,29 @@ k2p_partition(const ProbJob *__restrict__ jobs, const uint32_t *__restrict__ chu
     }
 }
 
-// ---- pass C: count.  Persistent CTAs over the (genome, bucket) items of a group.
+// ---- pass C: count + slot update.  grid = (kNB, njobs), kCThreads threads
 //
-// Every CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ...  The run of item k+1 is already on
-// its way into the other half of a double-buffered stage (TMA bulk copy, cp.async.bulk + mbarrier:
-// SASS UBLKCP; its length was read one item earlier still) while item k is counted, so no global
-// latency is exposed after the first item.  Counting itself:
-//   phase A  straight-line: every lane takes its keys four at a time, ONE atomicCAS each into a
-//            shared-memory table; a key that found its slot empty is counted, anything else (a second
-//            occurrence, or a different key in the slot: ~16 %) is parked in a pool of the WARP
-//            (ballot compaction, no atomic);
-//   phase B  drains the pool, 32 parked keys per trip: probe on, or count one more occurrence in a
-//            small side table keyed by the slot (repeats are rare: a counter per slot would triple
-//            the table's footprint and cost a resident CTA);
-//   emit     a key becomes a candidate exactly once -- at its first occurrence if it is light, at its
-//            second occurrence otherwise -- and only its slot is remembered, per warp; after ONE block
-//            barrier (the occurrence counts are final) the slots leave as (k-mer, weight) entries
-//            into the bucket's own region of the genome's candidate list: plain coalesced stores, no
-//            global atomic.  k3p_points128 consumes them.
+// The bucket's run is staged in shared memory by one TMA bulk copy per chunk of kCRound keys
+// (cp.async.bulk + mbarrier: SASS UBLKCP) while the table is cleared.  Phase A is straight-line:
+// every lane takes its keys four at a time, ONE atomicCAS each; a key that found its slot empty is
+// counted, anything else (a second occurrence or a different key in the slot: ~16 %) is parked in a
+// pool of the WARP (ballot compaction, no atomic).  Phase B drains the pool, 32 parked keys per trip
+// (probe on / bump the occurrence counter).  A key becomes a candidate exactly once -- at its first
+// occurrence if it is light, at its second occurrence otherwise -- and only its table slot is
+// remembered, again per warp.  After ONE block barrier (the occurrence counters are final) every
+// warp turns its candidates into (k-mer, weight), replays the exact f64 arithmetic of
+// ProbMinHash3a::hashset against the static bound and lowers the genome's 128-bit slot objects
+// (h, k-mer) with compare-and-swap: no candidate list, no second pass, no global cursor.  The two
+// global round trips of a compare-and-swap are hidden by the other resident CTAs.
+// Job parameters travel in the kernel arguments (constant bank): a CTA's first dependent global
+// load is its bucket cursor.  (Tried and measured slower on B200, same 5 Mbp workload: persistent
+// CTAs with a double-buffered stage that prefetch the next bucket, 300 us per group of 6 genomes
+// against 271; per-lane bit masks instead of warp pools, 413 us; a separate slot-update kernel over a
+// candidate list, 226 + 66 us.)
 constexpr int kCThreads = 256;
 constexpr uint32_t kCWarps = kCThreads / 32;
 constexpr uint32_t kCPark = kCRound / kCWarps;   // parked keys per warp and chunk (all of them, at worst)
 constexpr uint32_t kCCand = 256;                 // candidate slots per warp and round
-constexpr uint32_t kCDup = 512;                  // side table: distinct repeated keys per round (load <= 3/4)
 constexpr uint32_t kMaxGroupJobs = 8;            // genomes per group (kMaxSlots / 2)
 
 struct CountArgs {
@@ -295,32 +295,8 @@ struct CountArgs {
 
 template <typename KEY>
 constexpr size_t count_smem_bytes() {
-    return 2 * (size_t)kCRound * sizeof(KEY) + (size_t)kCTab * sizeof(KEY) + kCDup * 4 + kCWarps * kCPark * 2 +
+    return (size_t)kCRound * sizeof(KEY) + (size_t)kCTab * sizeof(KEY) + kCTab * 2 + kCWarps * kCPark * 2 +
            kCWarps * kCCand * 2;
-}
-
-// extra occurrences of the key in table slot `s` (0 if it never repeated)
-__device__ __forceinline__ uint32_t dup_lookup(const uint32_t *s_dup, uint32_t s) {
-    uint32_t h = (s * 0x9E3779B1u) >> 23;  // 9 bits
-    for (uint32_t p = 0; p < kCDup; p++) {
-        const uint32_t e = s_dup[h];
-        if (e == 0) return 0;
-        if ((e >> 16) == s + 1) return e & 0xFFFFu;
-        h = (h + 1) & (kCDup - 1);
-    }
-    return 0;
-}
-// one more occurrence of the key in slot `s`; returns the number of extra occurrences BEFORE this
-// one, or 0xFFFFFFFF if the side table is full
-__device__ __forceinline__ uint32_t dup_bump(uint32_t *s_dup, uint32_t s) {
-    uint32_t h = (s * 0x9E3779B1u) >> 23;
-    for (uint32_t p = 0; p < kCDup; p++) {
-        const uint32_t e = atomicCAS(&s_dup[h], 0u, ((s + 1) << 16) | 1u);
-        if (e == 0) return 0;
-        if ((e >> 16) == s + 1) return atomicAdd(&s_dup[h], 1u) & 0xFFFFu;
-        h = (h + 1) & (kCDup - 1);
-    }
-    return 0xFFFFFFFFu;
 }
 
 template <typename KT, typename KEY>
@@ -328,196 +304,164 @@ __global__ void __launch_bounds__(kCThreads, 3)
 k2p_count(CountArgs args, uint32_t njobs, const ProbBound *__restrict__ bound, SketchConsts sc, PartConsts pc,
           uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    KEY *s_stage0 = reinterpret_cast<KEY *>(s_raw);                       // [2][kCRound] double-buffered runs
-    KEY *s_key = s_stage0 + 2 * kCRound;                                  // [kCTab]
-    uint32_t *s_dup = reinterpret_cast<uint32_t *>(s_key + kCTab);        // [kCDup] (slot + 1) << 16 | extra occurrences
-    uint16_t *s_park = reinterpret_cast<uint16_t *>(s_dup + kCDup);       // [kCWarps][kCPark] parked stage indices
+    KEY *s_stage = reinterpret_cast<KEY *>(s_raw);                        // [kCRound] keys of the current chunk
+    KEY *s_key = s_stage + kCRound;                                       // [kCTab]
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_key + kCTab);        // [kCTab / 2] u16 pairs: extra occurrences
+    uint16_t *s_park = reinterpret_cast<uint16_t *>(s_cnt + kCTab / 2);   // [kCWarps][kCPark] parked stage indices
     uint16_t *s_cand = s_park + kCWarps * kCPark;                         // [kCWarps][kCCand] candidate slots
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_special;
+    const uint32_t j = blockIdx.y, b = blockIdx.x;
+    if (j >= njobs) return;
+    uint32_t n = __ldg(args.cursor[j] + b);
+    if (n == 0) return;
+    const double T = bound[j].T;  // needed after the counting: the load flies meanwhile
+    const uint32_t cap_g = args.cap_g[j];
+    if (n > cap_g) n = cap_g;  // the genome is flagged already (k2p_partition)
+    const KEY *run = reinterpret_cast<const KEY *>(args.buckets[j]) + (size_t)b * cap_g;
+    ulonglong2 *slot2 = args.slot2[j];
+    const uint32_t rn = (n + kCRound - 1) / kCRound;          // counting rounds (1 for ordinary genomes)
+    const uint32_t nchunk = rn;                               // stage loads per round
+    // table sized to the round: 2 x keys rounded up to a power of two, 256 .. kCTab slots
+    uint32_t lg = 32 - __clz(2 * (rn > 1 ? kCRound : n) - 1);
+    lg = lg < 8 ? 8 : (lg > 13 ? 13 : lg);
     static_assert(kCTab == 1u << 13, "table size");
     static_assert(kCRound % kCThreads == 0, "chunk size");
+    const uint32_t ts = 1u << lg, tmask = ts - 1;
     const KEY keymask = pc.keybits >= 8 * sizeof(KEY) ? (KEY)~(KEY)0 : (KEY)(((KEY)1 << pc.keybits) - 1);
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     uint16_t *wpark = s_park + warp * kCPark, *wcand = s_cand + warp * kCCand;
-    const uint32_t nitems = njobs * kNB;
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar, 1);
         fence_barrier_init();
     }
-    // item -> (genome, bucket): consecutive items are consecutive buckets of one genome
-    auto item_n = [&](uint32_t it) -> uint32_t {
-        if (it >= nitems) return 0u;
-        const uint32_t j = it / kNB, b = it % kNB;
-        const uint32_t n = __ldg(args.cursor[j] + b), cap = args.cap_g[j];
-        return n < cap ? n : cap;  // (an overfull bucket: the genome is flagged already, k2p_partition)
-    };
-    auto issue = [&](uint32_t it, uint32_t n, uint32_t c0, uint32_t buf) {  // thread 0 only
-        const uint32_t j = it / kNB, b = it % kNB;
-        const uint32_t cn = n - c0 < kCRound ? n - c0 : kCRound;
-        const uint32_t bytes = (uint32_t)((cn * sizeof(KEY) + 15) & ~(size_t)15);  // within cap_g (multiple of 4 keys)
-        const KEY *run = reinterpret_cast<const KEY *>(args.buckets[j]) + (size_t)b * args.cap_g[j] + c0;
-        mbar_expect_tx(&s_bar[buf], bytes);
-        tma_bulk_g2s(s_stage0 + (size_t)buf * kCRound, run, bytes, &s_bar[buf]);
-    };
-    uint32_t it = blockIdx.x;
-    uint32_t n = item_n(it), n_next = item_n(it + gridDim.x);
-    uint32_t buf = 0, phase0 = 0, phase1 = 0;
-    __syncthreads();  // barriers initialised
-    if (threadIdx.x == 0 && n) issue(it, n, 0, 0);
-    for (; it < nitems; it += gridDim.x, n = n_next, n_next = item_n(it + gridDim.x)) {
-        // (n_next for the item after the next one is loaded at the loop increment, a whole item ahead of its use)
-        const uint32_t j = it / kNB, b = it % kNB;
-        if (n == 0) {  // empty bucket: nothing in flight for it; start the next item's copy
+    uint32_t phase = 0;
+    bool full = false;
+    for (uint32_t r = 0; r < rn; r++) {
+        uint32_t ncand = 0;  // candidates remembered by this warp (uniform)
+        for (uint32_t c = 0; c < nchunk; c++) {
+            const uint32_t c0 = c * kCRound, cn = n - c0 < kCRound ? n - c0 : kCRound;
+            __syncthreads();  // previous chunk drained / previous round flushed (and the barrier is initialised)
+            if (threadIdx.x == 0) {  // the bulk copy of the chunk flies while the table is cleared
+                const uint32_t bytes = (uint32_t)((cn * sizeof(KEY) + 15) & ~(size_t)15);  // within cap_g (multiple of 4 keys)
+                mbar_expect_tx(&s_bar, bytes);
+                tma_bulk_g2s(s_stage, run + c0, bytes, &s_bar);
+            }
+            if (c == 0) {
+                const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u), z4 = make_uint4(0, 0, 0, 0);
+                uint4 *k4 = reinterpret_cast<uint4 *>(s_key);
+                for (uint32_t s = threadIdx.x; s < ts * sizeof(KEY) / 16; s += kCThreads) k4[s] = e4;
+                uint4 *c4 = reinterpret_cast<uint4 *>(s_cnt);
+                for (uint32_t s = threadIdx.x; s < ts / 8; s += kCThreads) c4[s] = z4;
+                if (threadIdx.x == 0) s_special = 0;
+            }
+            // one thread polls the mbarrier; the others sleep in the hardware barrier (a spin loop in
+            // every warp costs more issue slots than the counting itself)
+            if (threadIdx.x == 0) mbar_wait(&s_bar, phase);
+            phase ^= 1u;
             __syncthreads();
-            if (threadIdx.x == 0 && n_next) issue(it + gridDim.x, n_next, 0, buf);
-            continue;
-        }
-        const uint32_t rn = (n + kCRound - 1) / kCRound;  // counting rounds (1 for ordinary genomes)
-        const bool MULTI = rn > 1;
-        uint32_t lg = 32 - __clz(2 * (rn > 1 ? kCRound : n) - 1);
-        lg = lg < 8 ? 8 : (lg > 13 ? 13 : lg);  // table: 2 x keys rounded up to a power of two, 256 .. kCTab slots
-        const uint32_t ts = 1u << lg, tmask = ts - 1;
-        bool full = false;
-        for (uint32_t r = 0; r < rn; r++) {
-            uint32_t ncand = 0;  // candidates remembered by this warp (uniform)
-            for (uint32_t c = 0; c < rn; c++) {
-                const uint32_t c0 = c * kCRound, cn = n - c0 < kCRound ? n - c0 : kCRound;
-                const bool last_load = r + 1 == rn && c + 1 == rn;
-                __syncthreads();  // previous chunk drained / previous round or item flushed
-                if (threadIdx.x == 0) {  // the NEXT copy flies while this chunk is counted
-                    if (!last_load) {
-                        const uint32_t c2 = c + 1 == rn ? 0 : c + 1;
-                        issue(it, n, c2 * kCRound, buf ^ 1u);
-                    } else if (n_next) {
-                        issue(it + gridDim.x, n_next, 0, buf ^ 1u);
-                    }
+            // ---- phase A
+            uint32_t npark = 0;  // uniform in the warp
+            constexpr int kU = 4;
+            for (uint32_t i0 = threadIdx.x; i0 - lane < cn; i0 += kU * kCThreads) {  // warp-uniform trip count
+                KEY w[kU], old[kU];
+                uint32_t sl[kU];
+                bool on[kU];
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const uint32_t i = i0 + u * kCThreads;
+                    on[u] = i < cn;
+                    w[u] = s_stage[on[u] ? i : 0];
                 }
-                if (c == 0) {
-                    const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u), z4 = make_uint4(0, 0, 0, 0);
-                    uint4 *k4 = reinterpret_cast<uint4 *>(s_key);
-                    for (uint32_t s = threadIdx.x; s < ts * sizeof(KEY) / 16; s += kCThreads) k4[s] = e4;
-                    uint4 *d4 = reinterpret_cast<uint4 *>(s_dup);
-                    for (uint32_t s = threadIdx.x; s < kCDup / 4; s += kCThreads) d4[s] = z4;
-                    if (threadIdx.x == 0) s_special = 0;
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const uint32_t hw = sizeof(KEY) == 8 ? (uint32_t)(((uint64_t)w[u] * 0x9E3779B97F4A7C15ULL) >> 32)
+                                                         : (uint32_t)w[u] * 0x9E3779B1u;
+                    sl[u] = hw >> (32 - lg);
+                    if (rn > 1) on[u] = on[u] && ((hw >> 4) & 0xFFFFu) % rn == r;  // another round's key
                 }
-                // one thread polls the mbarrier; the others sleep in the hardware barrier
-                if (threadIdx.x == 0) mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
-                if (buf) phase1 ^= 1u; else phase0 ^= 1u;
-                __syncthreads();
-                const KEY *s_stage = s_stage0 + (size_t)buf * kCRound;
-                buf ^= 1u;
-                // ---- phase A: straight-line, four keys per trip (independent loads and atomics); the
-                // outcomes are pooled per WARP with ballots: parked keys by stage index, light keys that
-                // were new at their home slot by slot (candidates from their first occurrence on)
-                uint32_t npark = 0;  // uniform in the warp
-                constexpr int kU = 4;
-                for (uint32_t i0 = threadIdx.x; i0 - lane < cn; i0 += kU * kCThreads) {  // warp-uniform trip count
-                    KEY w[kU], old[kU];
-                    uint32_t sl[kU];
-                    bool on[kU];
 #pragma unroll
-                    for (int u = 0; u < kU; u++) {
-                        const uint32_t i = i0 + u * kCThreads;
-                        on[u] = i < cn;
-                        w[u] = s_stage[on[u] ? i : 0];
-                    }
+                for (int u = 0; u < kU; u++)  // (a no-op for the one word that collides with the sentinel)
+                    old[u] = on[u] ? smem_cas(&s_key[sl[u]], KeyTraits<KEY>::kEmpty, w[u]) : (KEY)0;
 #pragma unroll
-                    for (int u = 0; u < kU; u++) {
-                        const uint32_t hw = sizeof(KEY) == 8 ? (uint32_t)(((uint64_t)w[u] * 0x9E3779B97F4A7C15ULL) >> 32)
-                                                             : (uint32_t)w[u] * 0x9E3779B1u;
-                        sl[u] = hw >> (32 - lg);
-                        if (MULTI) on[u] = on[u] && ((hw >> 4) & 0xFFFFu) % rn == r;  // another round's key
-                    }
-#pragma unroll
-                    for (int u = 0; u < kU; u++)  // (a no-op for the one word that collides with the sentinel)
-                        old[u] = on[u] ? smem_cas(&s_key[sl[u]], KeyTraits<KEY>::kEmpty, w[u]) : (KEY)0;
-#pragma unroll
-                    for (int u = 0; u < kU; u++) {
-                        const bool isnew = on[u] && old[u] == KeyTraits<KEY>::kEmpty && w[u] != KeyTraits<KEY>::kEmpty;
-                        const bool park = on[u] && !isnew;
-                        const bool cand = isnew && (w[u] & KeyTraits<KEY>::kFlag);
-                        const uint32_t bp = __ballot_sync(0xffffffffu, park), bc = __ballot_sync(0xffffffffu, cand);
-                        if (park) wpark[npark + __popc(bp & lt)] = (uint16_t)(i0 + u * kCThreads);
-                        npark += __popc(bp);
-                        const uint32_t at = ncand + __popc(bc & lt);
-                        if (cand && at < kCCand) wcand[at] = (uint16_t)sl[u];
-                        ncand += __popc(bc);
-                    }
-                }
-                // ---- phase B: the warp's parked keys probe on (or count one more occurrence), 32 per trip
-                for (uint32_t t0 = 0; t0 < npark; t0 += 32) {
-                    const uint32_t t = t0 + lane;
-                    const bool act = t < npark;
-                    const KEY w = s_stage[act ? wpark[t] : 0];
-                    const bool flagged = (w & KeyTraits<KEY>::kFlag) != 0;
-                    const uint32_t hw = sizeof(KEY) == 8 ? (uint32_t)(((uint64_t)w * 0x9E3779B97F4A7C15ULL) >> 32)
-                                                         : (uint32_t)w * 0x9E3779B1u;
-                    uint32_t s = hw >> (32 - lg);
-                    bool cand = false;
-                    if (act && w == KeyTraits<KEY>::kEmpty) {
-                        atomicAdd(&s_special, 1u);
-                    } else if (act) {
-                        for (uint32_t probes = 0;; probes++) {
-                            const KEY old = smem_cas(&s_key[s], KeyTraits<KEY>::kEmpty, w);
-                            if (old == w) {  // one more occurrence: the first of them makes a heavy key a candidate
-                                const uint32_t before = dup_bump(s_dup, s);
-                                full |= before == 0xFFFFFFFFu;
-                                cand = before == 0 && !flagged;
-                                break;
-                            }
-                            if (old == KeyTraits<KEY>::kEmpty) {  // first occurrence after all
-                                cand = flagged;
-                                break;
-                            }
-                            if (probes > ts) {  // table full: more distinct keys than a round holds
-                                full = true;
-                                break;
-                            }
-                            s = (s + 1) & tmask;
-                        }
-                    }
-                    const uint32_t bc = __ballot_sync(0xffffffffu, cand);
+                for (int u = 0; u < kU; u++) {
+                    const bool special = w[u] == KeyTraits<KEY>::kEmpty;
+                    const bool isnew = on[u] && old[u] == KeyTraits<KEY>::kEmpty && !special;
+                    const bool park = on[u] && !isnew;
+                    const bool cand = isnew && (w[u] & KeyTraits<KEY>::kFlag);  // light: a candidate from its first occurrence on
+                    const uint32_t bp = __ballot_sync(0xffffffffu, park), bc = __ballot_sync(0xffffffffu, cand);
+                    if (park) wpark[npark + __popc(bp & lt)] = (uint16_t)(i0 + u * kCThreads);
+                    npark += __popc(bp);
                     const uint32_t at = ncand + __popc(bc & lt);
-                    if (cand && at < kCCand) wcand[at] = (uint16_t)s;
+                    if (cand && at < kCCand) wcand[at] = (uint16_t)sl[u];
                     ncand += __popc(bc);
                 }
             }
-            if (ncand > kCCand) {  // more candidates than a warp remembers: general path
-                full = true;
-                ncand = kCCand;
-            }
-            __syncthreads();  // the occurrence counts are final
-            // ---- candidates -> (k-mer, weight) -> points of ProbMinHash3a -> 128-bit slot minimum.  The
-            // exact f64 replay and the two global round trips of the compare-and-swap are hidden by the
-            // other resident CTAs; nothing is written but the slots that actually improve.
-            const uint32_t nspecial = s_special;
-            const double T = bound[j].T;
-            ulonglong2 *slot2 = args.slot2[j];
-            // the warp's candidates, 32 per trip, plus (warp 0) the word that collides with the sentinel:
-            // light by construction
-            const uint32_t nmine = ncand + ((warp == 0 && nspecial) ? 1u : 0u);
-            for (uint32_t t = lane; t < nmine; t += 32) {
-                KEY w;
-                uint32_t extra;
-                if (t < ncand) {
-                    const uint32_t s = wcand[t];
-                    w = s_key[s];
-                    extra = dup_lookup(s_dup, s);
-                } else {
-                    w = KeyTraits<KEY>::kEmpty;
-                    extra = nspecial - 1;
+            // ---- phase B: the warp's parked keys probe on (or count one more occurrence), 32 per trip
+            for (uint32_t t0 = 0; t0 < npark; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                const bool act = t < npark;
+                const KEY w = s_stage[act ? wpark[t] : 0];
+                const bool flagged = (w & KeyTraits<KEY>::kFlag) != 0;
+                const uint32_t hw = sizeof(KEY) == 8 ? (uint32_t)(((uint64_t)w * 0x9E3779B97F4A7C15ULL) >> 32)
+                                                     : (uint32_t)w * 0x9E3779B1u;
+                uint32_t s = hw >> (32 - lg);
+                bool cand = false;
+                if (act && w == KeyTraits<KEY>::kEmpty) {
+                    atomicAdd(&s_special, 1u);
+                } else if (act) {
+                    for (uint32_t probes = 0;; probes++) {
+                        const KEY old = smem_cas(&s_key[s], KeyTraits<KEY>::kEmpty, w);
+                        if (old == w) {  // one more occurrence: the first of them makes a heavy key a candidate
+                            const uint32_t shv = (s & 1u) * 16u;
+                            const uint32_t before = (atomicAdd(&s_cnt[s >> 1], 1u << shv) >> shv) & 0xFFFFu;
+                            cand = before == 0 && !flagged;
+                            break;
+                        }
+                        if (old == KeyTraits<KEY>::kEmpty) {  // first occurrence after all
+                            cand = flagged;
+                            break;
+                        }
+                        if (probes > ts) {  // table full: more distinct keys than a round holds
+                            full = true;
+                            break;
+                        }
+                        s = (s + 1) & tmask;
+                    }
                 }
-                const KT d = bunmix<KT>((KT)(((KT)b << pc.keybits) | (KT)(w & keymask)), pc);
-                pmh_points<KT>(d, 1u + extra, T, sc, [&](double h, uint32_t k) {
-                    slot_min128(&slot2[k], (unsigned long long)__double_as_longlong(h), (unsigned long long)d);
-                });
+                const uint32_t bc = __ballot_sync(0xffffffffu, cand);
+                const uint32_t at = ncand + __popc(bc & lt);
+                if (cand && at < kCCand) wcand[at] = (uint16_t)s;
+                ncand += __popc(bc);
             }
         }
-        if (full) atomicOr(&overflow[j], 2u);
+        if (ncand > kCCand) {  // more candidates than a warp remembers: general path
+            full = true;
+            ncand = kCCand;
+        }
+        __syncthreads();  // the occurrence counters are final
+        // ---- candidates -> (k-mer, weight) -> points -> 128-bit slot minimum
+        const uint32_t nspecial = s_special;
+        const uint32_t nmine = ncand + ((warp == 0 && nspecial) ? 1u : 0u);
+        for (uint32_t t = lane; t < nmine; t += 32) {
+            KEY w;
+            uint32_t extra;
+            if (t < ncand) {
+                const uint32_t s = wcand[t];
+                w = s_key[s];
+                extra = (s_cnt[s >> 1] >> ((s & 1u) * 16u)) & 0xFFFFu;
+            } else {
+                w = KeyTraits<KEY>::kEmpty;  // the word that collides with the sentinel: light by construction
+                extra = nspecial - 1;
+            }
+            const KT d = bunmix<KT>((KT)(((KT)b << pc.keybits) | (KT)(w & keymask)), pc);
+            pmh_points<KT>(d, 1u + extra, T, sc, [&](double h, uint32_t k) {
+                slot_min128(&slot2[k], (unsigned long long)__double_as_longlong(h), (unsigned long long)d);
+            });
+        }
     }
+    if (full) atomicOr(&overflow[j], 2u);
 }
 
 // ---- finalize of the partition path.  (The slot update itself happens inside k2p_count: every

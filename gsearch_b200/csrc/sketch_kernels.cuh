@@ -699,6 +699,13 @@ struct DensJob {
 
 constexpr uint32_t kDensLargeBits = 0x4F800000u;  // 4294967296.0f = F::from(u32::MAX)
 
+// RevOptDens: bin targeted by non-empty bin i in round a (oracle/sketch.c gso_revdens_target)
+__device__ __forceinline__ uint32_t revdens_target(uint32_t i, uint32_t a, uint32_t m) {
+    uint64_t z = (uint64_t)i * 0x9e3779b97f4a7c15ULL + (uint64_t)a * 0xd1b54a32d192ed03ULL + 0x2545f4914f6cdd1dULL;
+    z = sm64_mix(z);
+    return (uint32_t)__umul64hi(z, (uint64_t)m);
+}
+
 template <class Src, typename KT>
 __global__ void __launch_bounds__(kK2Threads)
 k2_optdens(const DensJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix,
@@ -751,7 +758,7 @@ __global__ void __launch_bounds__(256)
 k3_optdens_finalize(const DensJob *__restrict__ jobs, uint32_t njobs,
                     const FileResult *__restrict__ res, SketchConsts sc,
                     float *__restrict__ sig_out, uint64_t *__restrict__ nb_bases_out,
-                    uint32_t *__restrict__ retry, int super_mode) {
+                    uint32_t *__restrict__ retry, int super_mode, uint32_t *__restrict__ rev_win /* REVOPTDENS: [njobs][m] */) {
     const uint32_t j = blockIdx.x;
     if (j >= njobs) return;
     const DensJob job = jobs[j];
@@ -790,6 +797,38 @@ k3_optdens_finalize(const DensJob *__restrict__ jobs, uint32_t njobs,
         if (nb_bases_out) nb_bases_out[job.file] = fr.nbases;
     }
     float *out = sig_out + (size_t)job.file * sc.m;
+    if (rev_win && nempty != 0 && nempty != sc.m && !need_retry) {
+        // RevOptDens (SPEC: oracle/sketch.c gso_revoptdens): non-empty bins push their value into empty
+        // ones, round after round; in a round the lowest pushing bin wins an empty target
+        uint32_t *win = rev_win + (size_t)j * sc.m;
+        __shared__ uint32_t s_left;
+        for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
+            out[k] = __uint_as_float(job.bins[k]);
+            win[k] = 0xFFFFFFFFu;
+        }
+        if (threadIdx.x == 0) s_left = nempty;
+        __syncthreads();
+        for (uint32_t a = 0; s_left > 0; a++) {
+            for (uint32_t i = threadIdx.x; i < sc.m; i += blockDim.x) {
+                if (job.bins[i] == kDensLargeBits) continue;
+                const uint32_t t = revdens_target(i, a, sc.m);
+                if (__float_as_uint(out[t]) == kDensLargeBits) atomicMin(&win[t], i);
+            }
+            __syncthreads();
+            uint32_t filled = 0;
+            for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
+                const uint32_t w = win[k];
+                if (w != 0xFFFFFFFFu) {
+                    out[k] = __uint_as_float(job.bins[w]);
+                    win[k] = 0xFFFFFFFFu;
+                    filled++;
+                }
+            }
+            if (filled) atomicSub(&s_left, filled);
+            __syncthreads();
+        }
+        return;
+    }
     for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
         uint32_t b = job.bins[k];
         if (b == kDensLargeBits && nempty != sc.m && !need_retry && !super_mode) {
@@ -884,6 +923,176 @@ __global__ void k_super_sequential(const uint32_t *__restrict__ file_list, uint3
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ SuperMinHash2
+// probminhash SuperMinHash2 [U; oracle/sketch.c gso_superminhash2]: per slot the fx hash of the item
+// that gave the minimum.  Level-0 values (r < 1) beat every later level, so when each slot is reached
+// at level 0 the signature is, per slot, the hash of the item with the smallest first draw: ONE
+// 128-bit minimum (bits of r, hash) per slot, merged with compare-and-swap.  Otherwise (fewer k-mers
+// than ~ m ln m) the file takes the sequential restatement.
+__device__ __forceinline__ uint64_t fx_hash_of(uint64_t v, bool kt32) {
+    return kt32 ? (uint64_t)((uint32_t)v * 0x9e3779b9u) : v * kFxSeed64;
+}
+constexpr unsigned long long kSuper2Large = 0x41F0000000000000ull;  // 4294967296.0
+
+__global__ void k_super2_reset(ulonglong2 *slots, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        slots[i] = make_ulonglong2(kSuper2Large, ~0ull);
+}
+
+template <class Src, typename KT>
+__global__ void __launch_bounds__(kK2Threads)
+k2_super2(const DensJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
+          const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+          const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+          const uint32_t *__restrict__ boundaries, SketchConsts sc, uint32_t nchunks) {
+    for (uint32_t gchunk = blockIdx.x; gchunk < nchunks; gchunk += gridDim.x) {  // persistent CTAs
+        const uint32_t j = find_file(chunk_prefix, njobs, gchunk);
+        const DensJob job = jobs[j];
+        const FileResult fr = res[job.file];
+        if (fr.status != 0) continue;
+        const uint32_t cbase = (gchunk - chunk_prefix[j]) * kChunk;
+        if (cbase >= fr.nsym) continue;
+        const FileDesc fd = files[job.file];
+        SeqView sv;
+        sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
+        sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
+        sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
+        sv.nbounds = boundaries ? fr.nrec : 0;
+        sv.N = fr.nsym;
+        const uint32_t nk = fr.nsym >= sc.k ? fr.nsym - sc.k + 1 : 0;
+        const double T = nk ? job.tmult * ((double)sc.m / (double)nk) * sc.lnm8 : 2.0;
+        ulonglong2 *slots = reinterpret_cast<ulonglong2 *>(job.bins);
+        Src src;
+        src.init(sv, cbase + threadIdx.x * kRun, sc.k);
+        for (uint32_t i = 0; i < kRun; i++) {
+            KT val;
+            if (!src.step(i, val)) continue;
+            const uint64_t hv = fx_hash_of((uint64_t)val, sizeof(KT) == 4);
+            uint64_t s0;
+            const double r = u01_f64_from_bits(first_output(hv, s0));
+            if (!(r < T)) continue;
+            Xoshiro rng;
+            rng.seed(hv);
+            (void)rng.next();
+            const uint32_t k = uniform_usize(rng, sc.m, sc.zone);
+            slot_min128(&slots[k], (unsigned long long)__double_as_longlong(r), hv);
+        }
+    }
+}
+
+template <typename SigT>
+__global__ void __launch_bounds__(256)
+k3_super2_finalize(const DensJob *__restrict__ jobs, uint32_t njobs, const FileResult *__restrict__ res,
+                   SketchConsts sc, SigT *__restrict__ sig_out, uint64_t *__restrict__ nb_bases_out,
+                   uint32_t *__restrict__ retry) {
+    const uint32_t j = blockIdx.x;
+    if (j >= njobs) return;
+    const DensJob job = jobs[j];
+    const FileResult fr = res[job.file];
+    const ulonglong2 *slots = reinterpret_cast<const ulonglong2 *>(job.bins);
+    const uint32_t nk = fr.nsym >= sc.k ? fr.nsym - sc.k + 1 : 0;
+    const double T = nk ? job.tmult * ((double)sc.m / (double)nk) * sc.lnm8 : 2.0;
+    const bool bounded = T < 1.0;
+    const unsigned long long Tb = (unsigned long long)__double_as_longlong(bounded ? T : 1.0);
+    bool over = false, empty = false;
+    for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
+        const ulonglong2 s = slots[k];
+        empty |= s.y == ~0ull && s.x == kSuper2Large;
+        over |= !(s.x < Tb);  // an empty slot is "over" too
+        sig_out[(size_t)job.file * sc.m + k] = (SigT)s.y;
+    }
+    const bool any_over = __syncthreads_or(over), any_empty = __syncthreads_or(empty);
+    if (threadIdx.x == 0) {
+        const bool ok = fr.status == 0 && nk > 0;
+        // with a bound in force a slot at or above it may hide a smaller skipped draw: widen and re-run;
+        // without a bound (T >= 1) a slot that level 0 never reached needs the later levels: sequential
+        const bool need_retry = ok && bounded && any_over;
+        const bool need_seq = ok && !need_retry && any_empty;
+        retry[job.file] = (need_retry ? 1u : 0u) | (need_seq ? 2u : 0u) | (fr.status << 8);
+        if (nb_bases_out) nb_bases_out[job.file] = fr.nbases;
+    }
+}
+
+// cold path: the sequential algorithm, one thread per file; q/p/b/h/v live in global scratch
+template <class Src, typename KT, typename SigT>
+__global__ void k_super2_sequential(const uint32_t *__restrict__ file_list, uint32_t nlist,
+                                    const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+                                    const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+                                    const uint32_t *__restrict__ boundaries, SketchConsts sc,
+                                    SigT *__restrict__ sig_out, uint8_t *__restrict__ scratch) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nlist) return;
+    const uint32_t f = file_list[li];
+    const FileResult fr = res[f];
+    const FileDesc fd = files[f];
+    const uint32_t m = sc.m;
+    SigT *sig = sig_out + (size_t)f * m;
+    uint8_t *base = scratch + (size_t)li * m * 28;
+    double *h = reinterpret_cast<double *>(base);
+    uint64_t *v = reinterpret_cast<uint64_t *>(base + (size_t)m * 8);
+    uint32_t *q = reinterpret_cast<uint32_t *>(base + (size_t)m * 16), *p = q + m;
+    int32_t *b = reinterpret_cast<int32_t *>(p + m);
+    for (uint32_t i = 0; i < m; i++) {
+        h[i] = 4294967296.0;
+        v[i] = 0;
+        q[i] = 0xFFFFFFFFu;
+        p[i] = 0;
+        b[i] = 0;
+    }
+    b[m - 1] = (int32_t)m;
+    uint32_t a_upper = m - 1;
+    SeqView sv;
+    sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
+    sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
+    sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
+    sv.nbounds = boundaries ? fr.nrec : 0;
+    sv.N = fr.nsym;
+    for (uint32_t p0 = 0; p0 < fr.nsym; p0 += kRun) {
+        Src src;
+        src.init(sv, p0, sc.k);
+        for (uint32_t i = 0; i < kRun; i++) {
+            KT val;
+            if (!src.step(i, val)) continue;
+            const uint32_t irank = p0 + i;
+            const uint64_t hv = fx_hash_of((uint64_t)val, sizeof(KT) == 4);
+            Xoshiro rng;
+            rng.seed(hv);
+            uint32_t jj = 0;
+            while (jj <= a_upper) {
+                const double r = u01_f64_from_bits(rng.next());
+                const uint64_t range = (uint64_t)(m - jj);
+                const uint32_t k = jj + uniform_usize(rng, range, UINT64_MAX - ((UINT64_MAX - range + 1) % range));
+                if (q[jj] != irank) {
+                    q[jj] = irank;
+                    p[jj] = jj;
+                }
+                if (q[k] != irank) {
+                    q[k] = irank;
+                    p[k] = k;
+                }
+                const uint32_t t = p[jj];
+                p[jj] = p[k];
+                p[k] = t;
+                const double rpj = __dadd_rn(r, (double)jj);
+                const uint32_t slot = p[jj];
+                if (rpj < h[slot] || (rpj == h[slot] && hv < v[slot])) {
+                    const double old = h[slot];
+                    const uint32_t j2 = (old >= (double)(m - 1)) ? (m - 1) : (uint32_t)old;
+                    h[slot] = rpj;
+                    v[slot] = hv;
+                    if (jj < j2) {
+                        b[j2] -= 1;
+                        b[jj] += 1;
+                        while (b[a_upper] == 0) a_upper--;
+                    }
+                }
+                jj++;
+            }
+        }
+    }
+    for (uint32_t i = 0; i < m; i++) sig[i] = (SigT)v[i];
 }
 
 }  // namespace gsb

@@ -36,7 +36,7 @@ class SeqSketcherParams:
     def sig_type(self):
         """Sig type chosen by the reference dispatch tables (src/dna/dnasketch.rs:493-644,
         src/aa/aasketch.rs:449-552)."""
-        if self.algo == ALGO_PROB3A:
+        if self.algo in (ALGO_PROB3A, ALGO_SUPER2):  # SuperHash2Sketch<Kmer, u32 | u64, Fx>: dnasketch.rs:575-599
             if self.data_t == DATA_DNA:
                 return SIG_U32 if (self.kmer_size <= 14 or self.kmer_size == 16) else SIG_U64
             return SIG_U32 if self.kmer_size <= 6 else SIG_U64

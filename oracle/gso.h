@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 /* same numeric values as include/gsearch_b200.h */
-enum { GSO_ALGO_PROB3A = 0, GSO_ALGO_SUPER = 1, GSO_ALGO_OPTDENS = 2 };
+enum { GSO_ALGO_PROB3A = 0, GSO_ALGO_SUPER = 1, GSO_ALGO_OPTDENS = 2, GSO_ALGO_REVOPTDENS = 3, GSO_ALGO_SUPER2 = 4 };
 enum { GSO_DATA_DNA = 0, GSO_DATA_AA = 1 };
 enum { GSO_SIG_U32 = 0, GSO_SIG_U64 = 1, GSO_SIG_F32 = 2, GSO_SIG_U16 = 3 };
 enum { GSO_SPEC_NOHASH_IDENTITY = 1u << 0, GSO_SPEC_OPTDENS_F64_DRAW = 1u << 1 };
@@ -94,6 +94,11 @@ int gso_probminhash3a(const uint64_t *keys, const double *w, uint64_t nd, uint32
 /* OptDensMinHash::sketch over every occurrence + end_sketch : f32 sig[m] */
 int gso_optdens(const uint64_t *vals, uint64_t n, uint32_t m, uint32_t spec_flags,
                 float *sig_out);
+/* RevOptDensMinHash: OptDens bins, reverse densification (non-empty bins push into empty ones) */
+int gso_revoptdens(const uint64_t *vals, uint64_t n, uint32_t m, uint32_t spec_flags, float *sig_out);
+uint32_t gso_revdens_target(uint32_t i, uint32_t a, uint32_t m);
+/* SuperMinHash2: per slot the fx hash (32- or 64-bit) of the item that gave the minimum */
+int gso_superminhash2(const uint64_t *vals, uint64_t n, uint32_t m, int kt32, uint64_t *sig_out);
 /* SuperMinHash (f32) over distinct values in first-occurrence order */
 int gso_superminhash(const uint64_t *vals, uint64_t n, uint32_t m, float *sig_out);
 

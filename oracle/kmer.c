@@ -20,7 +20,7 @@
 #include <string.h>
 
 int gso_sig_type(const gso_sketch_params *p) {
-    if (p->algo == GSO_ALGO_PROB3A) {
+    if (p->algo == GSO_ALGO_PROB3A || p->algo == GSO_ALGO_SUPER2) { /* SuperHash2Sketch<Kmer, u32|u64, Fx>: dnasketch.rs:575-599 */
         if (p->data_t == GSO_DATA_DNA) {
             if (p->kmer_size <= 14 || p->kmer_size == 16) return GSO_SIG_U32;
             return GSO_SIG_U64;

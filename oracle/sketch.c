@@ -181,6 +181,52 @@ int gso_optdens(const uint64_t *vals, uint64_t n, uint32_t m, uint32_t spec_flag
     return 0;
 }
 
+/* RevOptDensMinHash (probminhash [U, low]; dispatch src/dna/dnasketch.rs:623-641): the same
+ * one-permutation bins as OptDens; only the densification differs -- non-empty bins PUSH their
+ * value into empty ones (Mai et al. 2020, "Densified MinHash in O(k log k)").  Frozen here as:
+ * rounds a = 0, 1, 2, ...; in a round every bin i that was non-empty BEFORE densification, in
+ * increasing i, targets bin j = target(i, a) and fills it if it is still empty; until no bin is
+ * empty.  target(i, a) = floor(mix(i, a) * m / 2^64) with the stateless 64-bit mix below, so that
+ * the restatement and the CUDA kernel (k3_optdens_finalize, REV mode) need no generator state. */
+uint32_t gso_revdens_target(uint32_t i, uint32_t a, uint32_t m) {
+    uint64_t z = (uint64_t)i * 0x9e3779b97f4a7c15ULL + (uint64_t)a * 0xd1b54a32d192ed03ULL + 0x2545f4914f6cdd1dULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    z ^= z >> 31;
+    return (uint32_t)(((__uint128_t)z * (__uint128_t)m) >> 64);
+}
+
+int gso_revoptdens(const uint64_t *vals, uint64_t n, uint32_t m, uint32_t spec_flags, float *sig_out) {
+    if (m < 1) return 1;
+    for (uint32_t k = 0; k < m; k++) sig_out[k] = OPTDENS_LARGE;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t hval = vals[i] * FX_SEED64;
+        gso_xoshiro rng;
+        gso_xoshiro_seed_from_u64(&rng, hval);
+        float r = (spec_flags & GSO_SPEC_OPTDENS_F64_DRAW) ? (float)gso_uniform_f64(&rng) : gso_uniform_f32(&rng);
+        uint32_t k = (uint32_t)gso_uniform_usize(&rng, m);
+        if (r <= sig_out[k]) sig_out[k] = r;
+    }
+    uint32_t nempty = 0;
+    for (uint32_t k = 0; k < m; k++) nempty += (sig_out[k] > 1.5f);
+    if (nempty == 0 || nempty == m) return 0;
+    uint8_t *orig = (uint8_t *)malloc(m);
+    if (!orig) return 4;
+    for (uint32_t k = 0; k < m; k++) orig[k] = !(sig_out[k] > 1.5f);
+    for (uint32_t a = 0; nempty > 0; a++) {
+        for (uint32_t i = 0; i < m && nempty > 0; i++) {
+            if (!orig[i]) continue;
+            const uint32_t j = gso_revdens_target(i, a, m);
+            if (sig_out[j] > 1.5f) {
+                sig_out[j] = sig_out[i];
+                nempty--;
+            }
+        }
+    }
+    free(orig);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------- */
 /* SuperMinHash                                                               */
 /* ------------------------------------------------------------------------- */
@@ -244,6 +290,79 @@ int gso_superminhash(const uint64_t *vals, uint64_t n, uint32_t m, float *sig_ou
     return 0;
 }
 
+/* SuperMinHash2 (probminhash superminhasher2 [U, low-medium]; dispatch src/dna/dnasketch.rs:575-599
+ * with the hasher chosen by the CALLER: FxHasher32 for 32-bit k-mers, FxHasher64 for 64-bit ones):
+ * Ertl's SuperMinHash whose signature holds, per slot, the HASH of the item that gave the minimum
+ * (so signatures compare by equality: DistHamming on u32 / u64).  Frozen here as: per item
+ * hval = fx(item) (fx32: (u32)item * 0x9e3779b9 ; fx64: item * 0x517cc1b727220a95), generator seeded
+ * by hval; level j draws r = Uniform<f64>[0,1) and k = j + Uniform<usize>[0, m-j), lazy Fisher-Yates
+ * swap, value r + j lands in slot p[j]; the slot keeps the smallest value and the hval of its item
+ * (identical values: the smaller hval -- probability 2^-52, the reference is order dependent there). */
+int gso_superminhash2(const uint64_t *vals, uint64_t n, uint32_t m, int kt32, uint64_t *sig_out) {
+    if (m < 1) return 1;
+    int64_t *q = (int64_t *)malloc(m * sizeof(int64_t));
+    uint32_t *p = (uint32_t *)malloc(m * sizeof(uint32_t));
+    int64_t *b = (int64_t *)malloc(m * sizeof(int64_t));
+    double *h = (double *)malloc(m * sizeof(double));
+    if (!q || !p || !b || !h) {
+        free(q);
+        free(p);
+        free(b);
+        free(h);
+        return 4;
+    }
+    for (uint32_t i = 0; i < m; i++) {
+        sig_out[i] = 0;
+        h[i] = 4294967296.0;
+        q[i] = -1;
+        p[i] = 0;
+        b[i] = 0;
+    }
+    b[m - 1] = m;
+    uint32_t a_upper = m - 1;
+    for (uint64_t it = 0; it < n; it++) {
+        const uint64_t hval = kt32 ? (uint64_t)((uint32_t)vals[it] * 0x9e3779b9u) : vals[it] * FX_SEED64;
+        gso_xoshiro rng;
+        gso_xoshiro_seed_from_u64(&rng, hval);
+        const int64_t irank = (int64_t)it;
+        uint32_t j = 0;
+        while (j <= a_upper) {
+            const double r = gso_uniform_f64(&rng);
+            const uint32_t k = j + (uint32_t)gso_uniform_usize(&rng, (uint64_t)(m - j));
+            if (q[j] != irank) {
+                q[j] = irank;
+                p[j] = j;
+            }
+            if (q[k] != irank) {
+                q[k] = irank;
+                p[k] = k;
+            }
+            const uint32_t t = p[j];
+            p[j] = p[k];
+            p[k] = t;
+            const double rpj = r + (double)j;
+            const uint32_t slot = p[j];
+            if (rpj < h[slot] || (rpj == h[slot] && hval < sig_out[slot])) {
+                const double old = h[slot];
+                const uint32_t j2 = (old >= (double)(m - 1)) ? (m - 1) : (uint32_t)old;
+                h[slot] = rpj;
+                sig_out[slot] = hval;
+                if (j < j2) {
+                    b[j2] -= 1;
+                    b[j] += 1;
+                    while (b[a_upper] == 0) a_upper--;
+                }
+            }
+            j++;
+        }
+    }
+    free(q);
+    free(p);
+    free(b);
+    free(h);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------- */
 /* per-file driver                                                            */
 /* ------------------------------------------------------------------------- */
@@ -280,6 +399,21 @@ static int sketch_one(const gso_sketch_params *p, const uint8_t *bytes, uint64_t
         rc = gso_optdens(vals, n, m, p->spec_flags, (float *)sig);
     } else if (p->algo == GSO_ALGO_SUPER) {
         rc = gso_superminhash(vals, n, m, (float *)sig);
+    } else if (p->algo == GSO_ALGO_REVOPTDENS) {
+        rc = gso_revoptdens(vals, n, m, p->spec_flags, (float *)sig);
+    } else if (p->algo == GSO_ALGO_SUPER2) {
+        const int kt32 = gso_sig_type(p) == GSO_SIG_U32;
+        uint64_t *tmp = (uint64_t *)malloc((size_t)m * sizeof(uint64_t));
+        if (!tmp) {
+            free(vals);
+            return 4;
+        }
+        rc = gso_superminhash2(vals, n, m, kt32, tmp);
+        if (kt32)
+            for (uint32_t i = 0; i < m; i++) ((uint32_t *)sig)[i] = (uint32_t)tmp[i];
+        else
+            memcpy(sig, tmp, (size_t)m * sizeof(uint64_t));
+        free(tmp);
     } else {
         rc = 6;
     }

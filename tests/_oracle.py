@@ -179,6 +179,20 @@ def optdens(vals, m, spec_flags=0):
     return sig
 
 
+def revoptdens(vals, m, spec_flags=0):
+    vals = np.ascontiguousarray(vals, dtype=np.uint64)
+    sig = np.zeros(m, dtype=np.float32)
+    assert L().gso_revoptdens(_p(vals), len(vals), m, spec_flags, _p(sig)) == 0
+    return sig
+
+
+def superminhash2(vals, m, kt32):
+    vals = np.ascontiguousarray(vals, dtype=np.uint64)
+    sig = np.zeros(m, dtype=np.uint64)
+    assert L().gso_superminhash2(_p(vals), len(vals), m, 1 if kt32 else 0, _p(sig)) == 0
+    return sig
+
+
 def superminhash(vals, m):
     vals = np.ascontiguousarray(vals, dtype=np.uint64)
     sig = np.zeros(m, dtype=np.float32)

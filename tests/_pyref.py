@@ -102,6 +102,18 @@ def parse_fasta(data: bytes, data_t=0, block=False):
     """-> list of code lists.  Line-based: a line starting with '>' opens a record."""
     if not data:
         return [[]] if block else []
+    if data[:1] == b"@":
+        # FASTQ as needletail reads it: four lines per record, the sequence on ONE line
+        lines = data.split(b"\n")
+        while lines and lines[-1].strip(b"\r") == b"":
+            lines.pop()  # trailing terminators
+        recs = []
+        for r in range(0, len(lines), 4):
+            quad = [ln[:-1] if ln.endswith(b"\r") else ln for ln in lines[r:r + 4]]
+            assert quad[0][:1] == b"@" and len(quad[0]) > 1, "InvalidStart"
+            assert len(quad) >= 3 and quad[2][:1] == b"+", "InvalidSeparator"
+            recs.append([quad[0][1:], [quad[1]]])
+        return _encode_records(recs, data_t, block)
     assert data[:1] == b">", "not FASTA"
     recs = []
     cur = None
@@ -111,6 +123,10 @@ def parse_fasta(data: bytes, data_t=0, block=False):
             recs.append(cur)
         else:
             cur[1].append(line)
+    return _encode_records(recs, data_t, block)
+
+
+def _encode_records(recs, data_t, block):
     out = []
     blk = []
     for hdr, lines in recs:
@@ -233,6 +249,58 @@ def superminhash_definition(vals, m):
             if val < sig[perm[j]]:
                 sig[perm[j]] = val
     return np.array(sig, dtype=np.float32)
+
+
+def superminhash2_definition(vals, m, kt32):
+    """SuperMinHash2 as a plain definition (no early stop, no lazy permutation): per slot the fx hash
+    of the item with the smallest r_j + j that landed there (identical values: the smaller hash)"""
+    best = [(float("inf"), 0)] * m
+    for v in set(vals):
+        hv = ((v & 0xFFFFFFFF) * 0x9E3779B9) & 0xFFFFFFFF if kt32 else (v * 0x517CC1B727220A95) & M64
+        rng = Xoshiro(hv)
+        perm = list(range(m))
+        for j in range(m):
+            r = rng.f64()
+            k = j + rng.usize(m - j)
+            perm[j], perm[k] = perm[k], perm[j]
+            cand = (r + float(j), hv)
+            if cand < best[perm[j]]:
+                best[perm[j]] = cand
+    return [b[1] for b in best]
+
+
+def revdens_target(i, a, m):
+    z = (i * 0x9E3779B97F4A7C15 + a * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    z ^= z >> 31
+    return (z * m) >> 64
+
+
+def revoptdens_definition(vals, m):
+    """OptDens bins, then reverse densification: round a, every originally non-empty bin i in
+    increasing order pushes its value into bin target(i, a) if that bin is still empty"""
+    import numpy as np
+    large = np.float32(4294967296.0)
+    sk = [large] * m
+    for v in set(vals):
+        rng = Xoshiro((v * 0x517CC1B727220A95) & M64)
+        r = np.float32(rng.f32())
+        k = rng.usize(m)
+        if r <= sk[k]:
+            sk[k] = r
+    orig = [s <= 1.5 for s in sk]
+    left = m - sum(orig)
+    a = 0
+    while 0 < left < m:
+        for i in range(m):
+            if orig[i] and left:
+                j = revdens_target(i, a, m)
+                if sk[j] > 1.5:
+                    sk[j] = sk[i]
+                    left -= 1
+        a += 1
+    return np.array(sk, dtype=np.float32)
 
 
 def hamming(a, b):

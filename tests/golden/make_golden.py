@@ -26,7 +26,24 @@ CASES = {
     # SuperMinHash: the first file is small (sequential cold path on the device), the second reaches
     # every slot at the first level (bin-min fast path)
     "super_dna_k21_s256": (lambda: [g.synth.dna_genome(7, 1500), g.synth.dna_genome(8, 40000)], 21, 256, 1, 0, False),
+    # round 2: RevOptDens (first file: empty bins -> reverse densification), SuperMinHash2 (u64 and u32
+    # hashes; first file: sequential cold path), FASTQ input
+    "revoptdens_dna_k21_s256": (lambda: [g.synth.dna_genome(9, 200), g.synth.dna_genome(10, 30000)], 21, 256, 3, 0, False),
+    "super2_dna_k21_s256": (lambda: [g.synth.dna_genome(11, 1500), g.synth.dna_genome(12, 40000)], 21, 256, 4, 0, False),
+    "super2_dna_k14_s128": (lambda: [g.synth.dna_genome(13, 900), g.synth.dna_genome(14, 25000)], 14, 128, 4, 0, True),
+    "prob_fastq_k16_s256": (lambda: [fastq_of(g.synth.dna_genome(15, 20000, 3)), g.synth.dna_genome(16, 20000)], 16, 256, 0, 0, False),
 }
+ROUND2 = ["revoptdens_dna_k21_s256", "super2_dna_k21_s256", "super2_dna_k14_s128", "prob_fastq_k16_s256"]
+
+
+def fastq_of(fasta_bytes):
+    """the records of a FASTA file as four-line FASTQ records"""
+    out = []
+    for rec in fasta_bytes.split(b">")[1:]:
+        head, _, body = rec.partition(b"\n")
+        seq = body.replace(b"\n", b"")
+        out.append(b"@" + head + b"\n" + seq + b"\n+\n" + b"I" * len(seq) + b"\n")
+    return b"".join(out)
 
 
 def wave_graph_fixture():
@@ -48,6 +65,16 @@ def wave_graph_fixture():
 
 
 def main(only=None):
+    if only == "round2":   # fixtures added in round 2: leaves the committed ones untouched
+        for name in ROUND2:
+            mk, k, S, algo, data_t, block = CASES[name]
+            files = mk()
+            sig, nb = O.sketch_files(files, k, S, algo, data_t, block)
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), sig=sig, nb=nb,
+                                meta=np.array([k, S, algo, data_t, int(block), len(files)]),
+                                sha=np.array([hash_bytes(f) for f in files], dtype=np.uint64))
+            print(name, sig.shape, sig.dtype, nb.tolist())
+        return
     if only == "new":   # fixtures added after the first set: leaves the committed ones untouched
         name = "super_dna_k21_s256"
         mk, k, S, algo, data_t, block = CASES[name]

@@ -117,3 +117,31 @@ def test_tohnsw_request_aa_optdens(tmp_path, monkeypatch):
     txt = open(work / "gsearch.neighbors.txt").read()
     assert txt.count("query_id:") >= 1 and "ignored" not in txt
     assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(db / "p007.faa") in txt
+
+
+@pytest.mark.gpu
+def test_bindash_all_pairs(tmp_path, oracle):
+    """`gsearch bindash` (src/bin/bindash.rs): all query x reference distances from OptDens / RevOptDens
+    sketches; rows `Query<TAB>Reference<TAB>Distance` with 1 - (2J/(1+J))^(1/k), 0 for equal basenames"""
+    files = []
+    for i in range(5):
+        pth = tmp_path / f"g{i}.fna"
+        pth.write_bytes(g.synth.dna_genome(16 + i, 40_000))
+        files.append(str(pth))
+    ql, rl, out = tmp_path / "q.txt", tmp_path / "r.txt", tmp_path / "out.tsv"
+    ql.write_text("\n".join(files[:2]) + "\n")
+    rl.write_text("\n".join(files) + "\n")
+    for dens, algo in ((0, g.ALGO_OPTDENS), (1, g.ALGO_REVOPTDENS)):
+        cli.main(f"bindash -q {ql} -r {rl} -k 16 -s 1024 -d {dens} -o {out}".split())
+        rows = open(out).read().splitlines()
+        assert rows[0] == "Query\tReference\tDistance" and len(rows) == 1 + 2 * 5
+        sig, _ = oracle.sketch_files([open(f, "rb").read() for f in files], 16, 1024, algo)
+        for row in rows[1:]:
+            qp, rp, d = row.split("\t")
+            i, k = files.index(qp), files.index(rp)
+            if i == k:
+                assert float(d) == 0.0
+                continue
+            j = np.float32(1.0) - np.float32(oracle.hamming(sig[i], sig[k]))
+            want = 1.0 - float(np.power((np.float32(2.0) * j) / (np.float32(1.0) + j), np.float32(1.0 / 16), dtype=np.float32))
+            assert abs(float(d) - want) < 1e-6

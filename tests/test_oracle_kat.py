@@ -375,6 +375,37 @@ def test_fasta_parser_fuzz_against_python():
     check()
 
 
+def test_fastq_parser_fuzz_against_python():
+    """FASTQ (needletail: four-line records, first byte '@'): well-formed files with hostile line
+    CONTENT (CR, lower case, N, '@' / '+' / '>' inside sequence and quality lines, "capsid" ids, empty
+    sequences, missing final terminator) -- the C oracle and the Python restatement must agree"""
+    from hypothesis import given, settings, strategies as st
+
+    word = st.lists(st.sampled_from([b"A", b"C", b"G", b"T", b"N", b"acgt", b"@", b"+", b">", b" ", b"MKV", b"*",
+                                     b"ACGTACGTAC", b"capsid", b"c"]), min_size=0, max_size=12).map(b"".join)
+    rec = st.tuples(word, word, word, word, st.sampled_from([b"\n", b"\r\n"]))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(rec, min_size=1, max_size=8), st.sampled_from([b"", b"\n", b"\n\n", b"\r\n"]), st.booleans())
+    def check(recs, tail, cut_last):
+        parts = []
+        for hid, seq, plus, qual, eol in recs:
+            parts.append(b"@r" + hid.replace(b"\n", b"") + eol + seq + eol + b"+" + plus + eol + qual + eol)
+        data = b"".join(parts)
+        if cut_last:
+            data = data.rstrip(b"\r\n")      # the last line may lack its terminator
+        data += tail
+        for data_t in (0, 1):
+            for block in (False, True):
+                got = [list(map(int, s)) for s in O.parse_fasta(data, data_t, block)]
+                assert got == R.parse_fasta(data, data_t, block), (data, data_t, block)
+
+    check()
+    for bad in (b"@r\nACGT\nX\nIIII\n", b"@r\nACGT\n+\nIIII\nACGT\n", b"@r\nACGT\n"):
+        with pytest.raises(RuntimeError):
+            O.parse_fasta(bad, 0, False)
+
+
 def test_expm1_spec_is_the_same_function_in_c_and_python_and_close_to_libm(oracle):
     """the sampler's rejection branch evaluates a FROZEN expm1 (degree-24 Horner polynomial, one
     rounded operation per step) so that the C oracle, the Python restatement and the CUDA kernel
@@ -390,3 +421,28 @@ def test_expm1_spec_is_the_same_function_in_c_and_python_and_close_to_libm(oracl
         a = L.gso_expm1_spec(float(z))
         assert a == P.expm1_spec(float(z))
         assert abs(a - math.expm1(z)) <= 2 * math.ulp(math.expm1(z)) if z > 0 else a == 0.0
+
+
+def test_superminhash2_and_revoptdens_equal_their_definitions(oracle):
+    """SuperMinHash2 (per slot the fx hash of the winning item) and RevOptDens (reverse densification)
+    as the oracle implements them -- early stop, lazy permutation, in-place rounds -- against the plain
+    Python definitions; repeated items are idempotent; RevOptDens without empty bins IS OptDens"""
+    import _pyref as P
+    rng = np.random.default_rng(21)
+    for n, m, kt32 in [(5, 8, True), (40, 16, False), (300, 32, True), (3, 64, False), (2000, 24, False)]:
+        vals = rng.integers(1, 2**31 if kt32 else 2**40, n).astype(np.uint64)
+        vals = np.concatenate([vals, vals[: n // 2]])
+        got = oracle.superminhash2(vals, m, kt32)
+        assert got.tolist() == P.superminhash2_definition([int(v) for v in vals], m, kt32), (n, m, kt32)
+        got = oracle.revoptdens(vals, m)
+        want = P.revoptdens_definition([int(v) for v in vals], m)
+        assert got.tobytes() == want.tobytes(), (n, m)
+        if n >= 300:  # every bin filled: nothing to densify
+            assert got.tobytes() == oracle.optdens(vals, m).tobytes()
+        assert (got <= 1.0).all()
+    # Jaccard by equality: two sets sharing half of their items
+    a = rng.integers(1, 2**40, 4000).astype(np.uint64)
+    b = np.concatenate([a[:2000], rng.integers(1, 2**40, 2000).astype(np.uint64)])
+    sa, sb = oracle.superminhash2(a, 2048, False), oracle.superminhash2(b, 2048, False)
+    j = 2000 / 6000
+    assert abs((sa == sb).mean() - j) < 4 * np.sqrt(j * (1 - j) / 2048)
