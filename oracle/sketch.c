@@ -297,7 +297,9 @@ int gso_superminhash(const uint64_t *vals, uint64_t n, uint32_t m, float *sig_ou
  * hval = fx(item) (fx32: (u32)item * 0x9e3779b9 ; fx64: item * 0x517cc1b727220a95), generator seeded
  * by hval; level j draws r = Uniform<f64>[0,1) and k = j + Uniform<usize>[0, m-j), lazy Fisher-Yates
  * swap, value r + j lands in slot p[j]; the slot keeps the smallest value and the hval of its item
- * (identical values: the smaller hval -- probability 2^-52, the reference is order dependent there). */
+ * (identical values: the smaller hval -- probability 2^-52, the reference is order dependent there).
+ * A slot no item reached (empty input only: every item visits all m slots at worst) holds the
+ * signature type's maximum, as the other order-free minima here do. */
 int gso_superminhash2(const uint64_t *vals, uint64_t n, uint32_t m, int kt32, uint64_t *sig_out) {
     if (m < 1) return 1;
     int64_t *q = (int64_t *)malloc(m * sizeof(int64_t));
@@ -312,7 +314,7 @@ int gso_superminhash2(const uint64_t *vals, uint64_t n, uint32_t m, int kt32, ui
         return 4;
     }
     for (uint32_t i = 0; i < m; i++) {
-        sig_out[i] = 0;
+        sig_out[i] = kt32 ? 0xFFFFFFFFull : ~0ull;
         h[i] = 4294967296.0;
         q[i] = -1;
         p[i] = 0;

@@ -254,7 +254,7 @@ def superminhash_definition(vals, m):
 def superminhash2_definition(vals, m, kt32):
     """SuperMinHash2 as a plain definition (no early stop, no lazy permutation): per slot the fx hash
     of the item with the smallest r_j + j that landed there (identical values: the smaller hash)"""
-    best = [(float("inf"), 0)] * m
+    best = [(float("inf"), 0xFFFFFFFF if kt32 else M64)] * m
     for v in set(vals):
         hv = ((v & 0xFFFFFFFF) * 0x9E3779B9) & 0xFFFFFFFF if kt32 else (v * 0x517CC1B727220A95) & M64
         rng = Xoshiro(hv)
