@@ -411,16 +411,41 @@ static int launch_search(gsb_index *idx, const SearchBufs &sb, uint32_t nq, uint
     // updates, neighbour gathering) -- measured 12.8 k against 9.6 k queries/s with the row staged
     // and one CTA per SM (GSB_K7_STAGED=1 restores that).  The row is read through L1/L2 instead.
     const int staged = (((row + 127) & ~(size_t)127) <= kSmemMax && getenv("GSB_K7_STAGED")) ? 1 : 0;
-    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
-    const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
-    size_t smem = row128 + (ret_in_smem ? ret_bytes : 0);
-    // visited bitmap in shared memory when it fits beside the row and the result heap
+    // Default: the candidate rows stream through a TMA ring (hnsw_device.cuh, eval_list_ring); it needs
+    // 16-byte rows and pays off from a few KB per row.  The shared memory of a CTA is then budgeted for
+    // three CTAs per SM: ring, the top of the result heap (the rest lives in the workspace, like the
+    // candidate heap), the visited bitmap if it still fits.
+    // The ring pays off when the result heap is too large to leave room for three CTAs' worth of
+    // register-load streaming (measured at S = 18000 x u64: ef_search 5000 +15 %, ef_search 1600 -17 %).
+    const bool want_ring = getenv("GSB_K7_RING") ? atoi(getenv("GSB_K7_RING")) != 0 : ef + 2 > 2048;
+    const int ring = (!staged && want_ring && (row & 15) == 0 && row >= 4096 && (((uintptr_t)sb.queries) & 15) == 0) ? 1 : 0;
+    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : (ring ? (size_t)kRingBytes : 0);
     const size_t bm_bytes = ((idx->n + 31) / 32) * 4;
-    const uint32_t bm_words = (smem + bm_bytes <= kSmemMax && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
-    smem += (size_t)bm_words * 4;
-    GSB_CUDA_TRY(cudaFuncSetAttribute(k7_hnsw_search<ELEM, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kSmemMax));
-    const uint32_t nctas = std::min<uint32_t>(nq, (uint32_t)idx->nsm * (staged ? 1u : 3u));
+    uint32_t ret_cs, bm_words;
+    size_t smem;
+    if (ring) {
+        // dynamic bytes of one of three CTAs per SM: (228 KB / 3 - 1 KB reserved) - 15.5 KB static
+        constexpr size_t kBudget = 233472 / 3 - 1024 - 15744 - 128;
+        smem = row128;
+        bm_words = (smem + bm_bytes + 512 * sizeof(HItem) <= kBudget && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
+        smem += (size_t)bm_words * 4;
+        ret_cs = (uint32_t)std::min<size_t>((size_t)ef + 2, (kBudget - smem) / sizeof(HItem));
+        smem += (size_t)ret_cs * sizeof(HItem);
+    } else {
+        const int ret_in_smem = row128 + ret_bytes <= kSmemMax ? 1 : 0;
+        ret_cs = ret_in_smem ? ef + 2 : 0;
+        smem = row128 + (ret_in_smem ? ret_bytes : 0);
+        // visited bitmap in shared memory when it fits beside the row and the result heap
+        bm_words = (smem + bm_bytes <= kSmemMax && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
+        smem += (size_t)bm_words * 4;
+    }
+    auto kern = ring ? k7_hnsw_search<ELEM, F32, true> : k7_hnsw_search<ELEM, F32, false>;
+    GSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    // (A grid sized so that every CTA gets the same number of queries -- 334 CTAs for 1000 queries --
+    // was measured slower than the full 444: the chains are latency bound, more of them in flight win.)
+    const uint32_t max_ctas = (uint32_t)idx->nsm * (staged ? 1u : 3u);
+    uint32_t nctas = std::min<uint32_t>(max_ctas, nq);
+    if (const char *e = getenv("GSB_K7_CTAS")) nctas = std::max(1, std::min<int>(atoi(e), (int)max_ctas));
     int rc;
     if ((rc = ensure_workspace(idx, nctas, idx->n, ef))) return rc;
     if ((rc = idx->d_counter.ensure(256))) return rc;
@@ -429,8 +454,8 @@ static int launch_search(gsb_index *idx, const SearchBufs &sb, uint32_t nq, uint
     so.out = sb.out;
     so.counts = sb.counts;
     so.nb_eval = sb.nb_eval;
-    k7_hnsw_search<ELEM, F32><<<nctas, kSearchThreads, smem, st>>>(
-        graph_view(idx), sb.queries, nq, knbn, ef, ret_in_smem, bm_words, staged,
+    kern<<<nctas, kSearchThreads, smem, st>>>(
+        graph_view(idx), sb.queries, nq, knbn, ef, ret_cs, bm_words, staged,
         idx->d_ws.as<uint8_t>(), idx->wl, so, idx->d_counter.as<uint32_t>());
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB_OK;

@@ -138,7 +138,8 @@ struct HeapT {
         }
     }
 };
-constexpr uint32_t kCandSmem = 2048;  // entries of the candidate heap kept in shared memory
+constexpr uint32_t kCandSmem = 2048;  // entries of the candidate heap kept in shared memory (K8)
+constexpr uint32_t kCandSmemK7 = 1024;  // K7: three CTAs per SM, the row ring takes the room
 
 struct GraphView {
     const uint8_t *sigs;        // n x S x elem
@@ -209,7 +210,7 @@ struct HnswShared {
     uint32_t done, node, flag, work, next;
     float fval;
     HeapT<true> cand;   // owned by thread 0
-    HeapT<false> ret;
+    HeapT<true> ret;    // first `cs` entries in shared memory, the rest in the CTA's workspace
 };
 
 // distances of the staged row to the nE rows E[i] -> D[i].  One warp per row when there are
@@ -294,6 +295,93 @@ __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView
     if (threadIdx.x < nE) D[threadIdx.x] = __fdiv_rn((float)acc[threadIdx.x], fS);
 }
 
+// ---- K7: candidate rows AND the matching query pieces through a TMA ring
+// A search chain evaluates one or two rows per expansion (ef_search = 5000: 1.45 on average), so
+// its bandwidth is the bytes it keeps in flight, and the query (144 KB at S = 18000 x u64) does not
+// fit in shared memory three times per SM: it is re-read from L2 beside every row.  Measured on the
+// B200 with this access pattern (scripts/ubench_rowstream.cu, profiles/r2_ubench_rowstream.log):
+//   rows alone, TMA or register loads                              7.0 - 7.4 TB/s
+//   rows by TMA + query by register loads (LDG, L2 hits)           3.4 TB/s   <- round 1 / first ring
+//   rows + query both by TMA, default L2 policy, 444 CTAs          3.8 TB/s   (64 MB of queries thrash L2)
+//   rows (evict-first) + query (evict-last) both by TMA, 444 CTAs  7.0 TB/s of rows
+// So ONE thread streams, per job, kRingChunk bytes of a row and the same piece of the query as two
+// bulk copies (cp.async.bulk + mbarrier: SASS UBLKCP) onto one transaction barrier; the 256 threads
+// compare the two pieces out of shared memory.  No register loads, no LSU slots, and the L2 policies
+// keep the queries resident under the stream of rows.  full[s]: both copies landed; empty[s]: the
+// eight warps are done with the slot.
+constexpr uint32_t kRingSlots = 3;
+constexpr uint32_t kRingChunk = 8192;   // 2 x 16 bytes of the row per thread and job
+constexpr uint32_t kRingBytes = kRingSlots * 2 * kRingChunk;
+struct RowRing {
+    uint8_t *buf;             // kRingSlots x [row piece | query piece], 128-byte aligned
+    uint64_t *full, *empty;   // [kRingSlots] each
+    uint32_t slot, par;       // next job's slot and the parity of its use (uniform in the CTA)
+    uint64_t pol_rows, pol_query;
+};
+
+template <int ELEM, bool F32>
+__device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g, const uint32_t *E, uint32_t nE,
+                                            float *D, uint32_t *acc, RowRing &ring) {
+    if (nE == 0) return;
+    RowRing rr = ring;  // (the caller's copy lives in local memory: this is a real call)
+    const uint32_t row = g.S * ELEM;
+    const uint32_t nch = (row + kRingChunk - 1) / kRingChunk;
+    const uint32_t J = nE * nch;
+    const uint32_t t = threadIdx.x;
+    for (uint32_t i = t; i < nE; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    uint32_t pr = 0, pc = 0, pj = 0, pslot = rr.slot;  // producer (thread 0): next job to issue
+    auto issue = [&]() {
+        const uint32_t off = pc * kRingChunk;
+        const uint32_t bytes = row - off < kRingChunk ? row - off : kRingChunk;
+        uint8_t *dst = rr.buf + pslot * (2 * kRingChunk);
+        mbar_expect_tx(&rr.full[pslot], 2 * bytes);
+        tma_bulk_g2s_hint(dst, g.sigs + (size_t)E[pr] * row + off, bytes, &rr.full[pslot], rr.pol_rows);
+        tma_bulk_g2s_hint(dst + kRingChunk, q + off, bytes, &rr.full[pslot], rr.pol_query);
+        if (++pslot == kRingSlots) pslot = 0;
+        if (++pc == nch) {
+            pc = 0;
+            pr++;
+        }
+        pj++;
+    };
+    if (t == 0)
+        while (pj < J && pj < kRingSlots) issue();
+    uint32_t r = 0, c = 0, cnt = 0;
+    for (uint32_t j = 0; j < J; j++) {
+        const uint32_t off = c * kRingChunk;
+        const uint32_t nv = (row - off < kRingChunk ? row - off : kRingChunk) / 16;
+        mbar_wait(&rr.full[rr.slot], rr.par);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(rr.buf + rr.slot * (2 * kRingChunk));
+        const uint4 *sq = s4 + kRingChunk / 16;
+        if (t < nv) cnt += diff16<ELEM, F32>(sq[t], s4[t]);
+        if (t + 256 < nv) cnt += diff16<ELEM, F32>(sq[t + 256], s4[t + 256]);
+        if (++c == nch) {  // the row is complete (uniform)
+            c = 0;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            if (lane_id() == 0 && cnt) atomicAdd(&acc[r], cnt);
+            cnt = 0;
+            r++;
+        }
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&rr.empty[rr.slot]);
+        if (t == 0 && pj < J) {  // refill this slot as soon as the eight warps have released it
+            mbar_wait(&rr.empty[rr.slot], rr.par);
+            issue();
+        }
+        if (++rr.slot == kRingSlots) {
+            rr.slot = 0;
+            rr.par ^= 1u;
+        }
+    }
+    ring.slot = rr.slot;
+    ring.par = rr.par;
+    __syncthreads();
+    const float fS = (float)g.S;
+    for (uint32_t i = t; i < nE; i += blockDim.x) D[i] = __fdiv_rn((float)acc[i], fS);
+}
+
 // stage one signature row in shared memory (TMA bulk copy when alignment allows) and return where
 // the row now is; all threads must have finished reading the previous content (caller
 // synchronises before).  A row that does not fit in shared memory (S up to 65535 is legal) stays
@@ -317,10 +405,10 @@ __device__ __forceinline__ const uint8_t *stage_row(uint8_t *smem, const uint8_t
 
 // hnsw_rs search_layer: best-first search on one layer from `ep` (distance d_ep known), result in
 // sh.ret (max-heap of at most ef), candidates in sh.cand; `vis` is reset here.
-template <int ELEM, bool F32>
+template <int ELEM, bool F32, bool RING = false>
 __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint32_t ep, float d_ep,
                                  uint32_t ef, uint32_t layer, HnswShared &sh, Visit &vis,
-                                 unsigned long long &neval) {
+                                 unsigned long long &neval, RowRing *rr) {
     vis.begin();
     __syncthreads();
     // thread 0 owns the heaps: pop the next candidate (or decide to stop) and publish it
@@ -330,7 +418,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
             sh.done = 1;
         } else {
             const HItem c = sh.cand.pop();
-            if (-c.d > sh.ret.a[0].d) sh.done = 1;
+            if (-c.d > sh.ret.at(0).d) sh.done = 1;
             sh.node = c.p;
             sh.next = sh.cand.n ? sh.cand.at(0).p : 0xFFFFFFFFu;  // the likely next pop
         }
@@ -346,9 +434,15 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
     }
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t cap = layer == 0 ? 2 * g.M : g.M;  // list capacity: entries beyond the count are stale but readable
+#ifdef GSB_K7_PROF
+    long long pt_g = 0, pt_e = 0, pt_h = 0, pt_n = 0, pt_rows = 0, pt0;
+#endif
     for (;;) {
         __syncthreads();
         if (sh.done) break;
+#ifdef GSB_K7_PROF
+        pt0 = clock64();
+#endif
         if (threadIdx.x < 32 && sh.next != 0xFFFFFFFFu) prefetch_list(g, sh.next, layer);
         // gather the unvisited neighbours of the popped node in list order; the count and the
         // entries are loaded together (one L2 round trip instead of two dependent ones)
@@ -376,21 +470,38 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
             if (base + blockDim.x >= len) break;  // nothing valid beyond the count
         }
         __syncthreads();
-        eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
+#ifdef GSB_K7_PROF
+        pt_g += clock64() - pt0; pt0 = clock64();
+#endif
+        if (RING) eval_list_ring<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc, *rr);
+        else eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
         __syncthreads();
+#ifdef GSB_K7_PROF
+        pt_e += clock64() - pt0; pt0 = clock64(); pt_n++; pt_rows += tot;
+#endif
         if (threadIdx.x == 0) {
             neval += tot;
             for (uint32_t i = 0; i < tot; i++) {
                 const float ed = sh.D[i];
-                if (ed < sh.ret.a[0].d || sh.ret.n < ef) {
+                if (ed < sh.ret.at(0).d || sh.ret.n < ef) {
                     sh.cand.push(-ed, sh.E[i]);
                     sh.ret.push(ed, sh.E[i]);
                     if (sh.ret.n > ef) (void)sh.ret.pop();
                 }
             }
             pop_next();
+#ifdef GSB_K7_PROF
+            pt_h += clock64() - pt0;
+#endif
         }
     }
+#ifdef GSB_K7_PROF
+    uint32_t smid_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+    if (threadIdx.x == 0 && blockIdx.x % 37 == 0 && ef > 1)
+        printf("k7prof cta %u sm %u: expansions %lld rows %lld  cycles/expansion: gather %lld eval %lld heap %lld\n", blockIdx.x, smid_,
+               pt_n, pt_rows, pt_g / (pt_n ? pt_n : 1), pt_e / (pt_n ? pt_n : 1), pt_h / (pt_n ? pt_n : 1));
+#endif
     __syncthreads();
 }
 
@@ -404,35 +515,51 @@ struct WsLayout {
     size_t off_newc;   // uint32_t[newc_cap] (insert: candidate extension)
 };
 
-// smem: [row: row bytes rounded to 128][ret heap: (ef+2) items if ret_in_smem]
-template <int ELEM, bool F32>
+// smem: [row: row bytes rounded to 128 (staged)] or [row ring (ring)] [ret heap: first ret_cs items]
+// [visited bitmap: bm_words]
+template <int ELEM, bool F32, bool RING>
 __global__ void __launch_bounds__(kSearchThreads, 3)
 k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, uint32_t knbn, uint32_t ef,
-               int ret_in_smem, uint32_t bm_words, int staged, uint8_t *__restrict__ ws, WsLayout wl,
+               uint32_t ret_cs, uint32_t bm_words, int staged, uint8_t *__restrict__ ws, WsLayout wl,
                SearchOut so, uint32_t *__restrict__ qcounter) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t ring_bar[2 * kRingSlots];
     __shared__ HnswShared sh;
-    __shared__ __align__(8) HItem cand_sm[kCandSmem];
+    __shared__ __align__(8) HItem cand_sm[kCandSmemK7];
     __shared__ uint32_t s_q;
     const size_t row = (size_t)g.S * ELEM;
-    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : 0;
+    const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : (RING ? (size_t)kRingBytes : 0);
     uint8_t *my = ws + (size_t)blockIdx.x * wl.stride;
     uint32_t *stamps = reinterpret_cast<uint32_t *>(my + wl.off_stamp);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+        for (uint32_t s = 0; s < kRingSlots; s++) {
+            mbar_init(&ring_bar[s], 1);
+            mbar_init(&ring_bar[kRingSlots + s], kSearchThreads / 32);
+        }
         fence_barrier_init();
         sh.cand.a = cand_sm;
         sh.cand.g = reinterpret_cast<HItem *>(my + wl.off_cand);
-        sh.cand.cs = kCandSmem;
-        sh.ret.a = ret_in_smem ? reinterpret_cast<HItem *>(smem + row128) : reinterpret_cast<HItem *>(my + wl.off_ret);
+        sh.cand.cs = kCandSmemK7;
+        sh.ret.a = reinterpret_cast<HItem *>(smem + row128);
+        sh.ret.g = reinterpret_cast<HItem *>(my + wl.off_ret);
+        sh.ret.cs = ret_cs;
     }
     __syncthreads();
     uint32_t phase = 0;
+    RowRing rring;
+    rring.buf = smem;
+    rring.full = ring_bar;
+    rring.empty = ring_bar + kRingSlots;
+    rring.slot = 0;
+    rring.par = 0;
+    rring.pol_rows = l2_evict_first_policy();
+    rring.pol_query = l2_evict_last_policy();
+    RowRing *rr = &rring;
     Visit vis;
     vis.nwords = bm_words;
-    vis.bits = bm_words ? reinterpret_cast<uint32_t *>(smem + row128 + (ret_in_smem ? ((size_t)ef + 2) * sizeof(HItem) : 0))
-                        : nullptr;
+    vis.bits = bm_words ? reinterpret_cast<uint32_t *>(smem + row128 + (size_t)ret_cs * sizeof(HItem)) : nullptr;
     vis.stamps = stamps;
     vis.stamp = *reinterpret_cast<uint32_t *>(my + wl.off_ctr);
     for (;;) {
@@ -440,12 +567,16 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
         __syncthreads();
         const uint32_t q = s_q;
         if (q >= nq) break;
+#ifdef GSB_K7_PROF
+        const long long qt0 = clock64();
+#endif
         const uint8_t *cur = stage_row(smem, queries + (size_t)q * row, row, &bar, phase, staged);
         unsigned long long neval = 0;
         uint32_t pivot = g.entry;
         if (threadIdx.x == 0) sh.E[0] = pivot;
         __syncthreads();
-        eval_list<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc);
+        if (RING) eval_list_ring<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc, *rr);
+        else eval_list<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc);
         __syncthreads();
         float dist_to_entry = sh.D[0];
         neval += 1;
@@ -457,7 +588,8 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldg(&lst[i]);
             __syncthreads();
-            eval_list<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc);
+            if (RING) eval_list_ring<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc, *rr);
+            else eval_list<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc);
             __syncthreads();
             neval += len;
             // every thread scans the same shared arrays: uniform result, no broadcast needed
@@ -471,16 +603,40 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             pivot = newp;
         }
         // ---- search_layer(q, pivot, ef, 0)
-        search_layer_dev<ELEM, F32>(g, cur, pivot, dist_to_entry, ef, 0, sh, vis, neval);
+        search_layer_dev<ELEM, F32, RING>(g, cur, pivot, dist_to_entry, ef, 0, sh, vis, neval, rr);
+#ifdef GSB_K7_PROF
+        const long long qt1 = clock64();
+#endif
+        // BinaryHeap::into_sorted_vec is a serial chain of ef sift-downs: run it on a contiguous
+        // shared-memory copy of the heap (the row ring is idle now) instead of the hybrid one
+        HItem *flat = nullptr;
+        const uint32_t nret = sh.ret.n;
+        if (RING && (size_t)nret * sizeof(HItem) <= kRingBytes) {
+            flat = reinterpret_cast<HItem *>(smem);
+            for (uint32_t i = threadIdx.x; i < nret; i += blockDim.x) flat[i] = sh.ret.at(i);
+            __syncthreads();
+        } else if (sh.ret.cs >= nret) {
+            flat = sh.ret.a;
+        }
         if (threadIdx.x == 0) {
-            sh.ret.into_sorted();
+            HeapT<false> fl;
+            fl.a = flat;
+            fl.n = nret;
+            if (flat) fl.into_sorted();
+            else sh.ret.into_sorted();
+#ifdef GSB_K7_PROF
+            if (blockIdx.x % 37 == 0)
+                printf("k7prof cta %u query %u: search %lld cycles, into_sorted %lld cycles\n", blockIdx.x, q, qt1 - qt0,
+                       clock64() - qt1);
+#endif
             uint32_t last = knbn < ef ? knbn : ef;
-            if (sh.ret.n < last) last = sh.ret.n;
+            if (nret < last) last = nret;
             for (uint32_t i = 0; i < last; i++) {
-                const uint32_t p = sh.ret.a[i].p;
+                const HItem it = flat ? flat[i] : sh.ret.at(i);
+                const uint32_t p = it.p;
                 gsb_neighbour nbq;
                 nbq.d_id = g.ids[p];
-                nbq.distance = sh.ret.a[i].d;
+                nbq.distance = it.d;
                 nbq.layer = g.levels[p];
                 nbq.pad_[0] = nbq.pad_[1] = nbq.pad_[2] = 0;
                 nbq.rank = (int32_t)g.ranks[p];
@@ -489,6 +645,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             so.counts[q] = last;
             if (so.nb_eval) so.nb_eval[q] = neval;
         }
+        if (RING) fence_proxy_async();  // the ring was written with ordinary stores: order them before the next bulk copies
         __syncthreads();
     }
     if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(my + wl.off_ctr) = vis.stamp;
@@ -538,7 +695,9 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
         sh.cand.a = cand_sm;
         sh.cand.g = reinterpret_cast<HItem *>(my + wl.off_cand);
         sh.cand.cs = kCandSmem;
-        sh.ret.a = ret_in_smem ? reinterpret_cast<HItem *>(smem + row128) : reinterpret_cast<HItem *>(my + wl.off_ret);
+        sh.ret.a = reinterpret_cast<HItem *>(smem + row128);
+        sh.ret.g = reinterpret_cast<HItem *>(my + wl.off_ret);
+        sh.ret.cs = ret_in_smem ? 0xFFFFFFFFu : 0u;
     }
     __syncthreads();
     uint32_t phase = 0;
@@ -571,7 +730,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
         float d_ep = sh.D[0];
         // ---- greedy descent through the layers above the point's level: search_layer(ef = 1)
         for (int l = (int)lmax; l >= (int)level + 1; l--) {
-            search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, 1, (uint32_t)l, sh, vis, neval);
+            search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, 1, (uint32_t)l, sh, vis, neval, nullptr);
             if (threadIdx.x == 0) {
                 s_ep = ep;
                 s_dep = d_ep;
@@ -589,7 +748,7 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
         }
         const int top = (int)(level < lmax ? level : lmax);
         for (int l = top; l >= 0; l--) {
-            search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval);
+            search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval, nullptr);
             // ---- earlier points of this wave, in order, as if search_layer had met them last
             {
                 uint32_t tot = 0;
@@ -613,14 +772,14 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                 if (threadIdx.x == 0) {
                     for (uint32_t i = 0; i < tot; i++) {
                         const float ed = sh.D[i];
-                        if (ed < sh.ret.a[0].d || sh.ret.n < wv.ef_c) {
+                        if (ed < sh.ret.at(0).d || sh.ret.n < wv.ef_c) {
                             sh.ret.push(ed, sh.E[i]);
                             if (sh.ret.n > wv.ef_c) (void)sh.ret.pop();
                         }
                     }
                     // from_positive_binaryheap_to_negative_binary_heap: push in underlying-vec order
                     sh.cand.n = 0;
-                    for (uint32_t i = 0; i < sh.ret.n; i++) sh.cand.push(-sh.ret.a[i].d, sh.ret.a[i].p);
+                    for (uint32_t i = 0; i < sh.ret.n; i++) sh.cand.push(-sh.ret.at(i).d, sh.ret.at(i).p);
                 }
                 __syncthreads();
             }

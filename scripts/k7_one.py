@@ -1,0 +1,14 @@
+"""one K7 launch at BASELINE configs[2] (for ncu): EF env = ef_search"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import gsearch_b200 as g
+from gsearch_b200.comm import DeviceBuffer
+S, n, nq = 18000, int(os.environ.get("DB", "50000")), 1000
+db = g.synth.signatures(n, S)
+q, _ = g.synth.queries(nq, db)
+d_db = DeviceBuffer(db.nbytes); d_db.upload(db)
+idx = g.Hnsw(g.HnswParams(max_nb_conn=128, ef=1600), S, np.uint64)
+idx.insert_device(d_db.ptr, np.arange(n, dtype=np.uint64))
+o, c, ne = idx.search_raw(q, 50, int(os.environ.get("EF", "5000")))
+print("evals/q", ne.mean())
