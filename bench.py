@@ -283,6 +283,14 @@ def measured_traffic(key):
     return None
 
 
+def k7_traffic(a, ef, world):
+    """ncu DRAM bytes of one K7 launch, if the committed capture is of this very configuration"""
+    t = measured_traffic("k7_hnsw_search_ef%d" % ef)
+    if t and world == 1 and t.get("queries") == a.queries and t.get("db_signatures") == a.db:
+        return t["dram_bytes_per_launch"]
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -719,7 +727,7 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
                     "note": "gsb_index_search_batch: host queries in, host neighbours out"},
             "gpu_launches": calls,
             "roofline": {"kernel": "k7_hnsw_search", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": k7_traffic(a, ef, world), "peak_source": peak_src,
                          "algorithmic_bytes_per_query": bytes_step / nq,
                          "mean_evaluations_per_query": float(tot_ev.item()) / nq,
                          "avg_launch_ms": 1e3 * dt / calls},

@@ -21,8 +21,9 @@
 //       atomics per k-mer instead of 1, and coalesced run writes instead of random L2 traffic.
 //   k2p_count      one CTA per (genome, bucket): the ~2 400 keys of a bucket go through a
 //       shared-memory hash table (atomicCAS on the key, atomicAdd on a duplicate counter): exact
-//       multiplicities with no global atomic per k-mer.  Only keys that are repeated or light
-//       leave the CTA, as (k-mer, weight) candidates for the unchanged exact replay (k3_prob_*).
+//       multiplicities with no global atomic per k-mer.  Only keys that are repeated or light are
+//       candidates; the CTA replays their exact f64 point sequence on the spot and lowers the
+//       genome's 128-bit slot objects (h, k-mer) with compare-and-swap (k3p_finalize128 reads them).
 //
 // Exactness: u -> (bucket, key) is a bijection of the 2k-bit (5k-bit) k-mer value, so equal keys in
 // a bucket are equal k-mers; every occurrence lands in exactly one bucket run (shared-memory region,

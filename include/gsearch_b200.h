@@ -48,7 +48,7 @@ typedef enum {
     GSB_ERR_NO_DEVICE = 2,     /* no usable CUDA device: the library has no CPU path */
     GSB_ERR_CUDA = 3,          /* a CUDA runtime call failed                         */
     GSB_ERR_OOM = 4,           /* host or device allocation failed                   */
-    GSB_ERR_BAD_INPUT = 5,     /* malformed FASTA (reference: exit(1), dnafiles.rs:54)*/
+    GSB_ERR_BAD_INPUT = 5,     /* malformed FASTA / FASTQ (reference: exit(1), dnafiles.rs:54)*/
     GSB_ERR_UNSUPPORTED = 6,   /* valid in the reference, not (yet) built here       */
     GSB_ERR_IO = 7,            /* file dump / reload failed                          */
     GSB_ERR_CAPACITY = 8       /* index capacity or genome-length limit exceeded     */
@@ -71,9 +71,9 @@ typedef enum {
     GSB_ALGO_PROB3A = 0,     /* --algo prob     ProbMinHash3a, Sig = k-mer value   */
     GSB_ALGO_SUPER = 1,      /* --algo super    SuperMinHash,  Sig = f32            */
     GSB_ALGO_OPTDENS = 2,    /* --algo optdens  OptDensMinHash, Sig = f32           */
-    GSB_ALGO_REVOPTDENS = 3, /* --algo revoptdens                                   */
-    GSB_ALGO_SUPER2 = 4,     /* --algo super2                                       */
-    GSB_ALGO_HLL = 5         /* --algo hll                                          */
+    GSB_ALGO_REVOPTDENS = 3, /* --algo revoptdens  RevOptDensMinHash, Sig = f32      */
+    GSB_ALGO_SUPER2 = 4,     /* --algo super2   SuperMinHash2, Sig = item hash u32/u64 */
+    GSB_ALGO_HLL = 5         /* --algo hll      not built: GSB_ERR_UNSUPPORTED       */
 } gsb_algo;
 
 typedef enum { GSB_DATA_DNA = 0, GSB_DATA_AA = 1 } gsb_data_t;
@@ -123,7 +123,9 @@ GSB_API int gsb_sketcher_sig_type(const gsb_sketcher *h);
 GSB_API uint32_t gsb_sketcher_elem_size(const gsb_sketcher *h);
 
 /*
- * Sketch n FASTA "files" (already decompressed bytes) -> n signatures.
+ * Sketch n FASTA / FASTQ "files" (already decompressed bytes) -> n signatures.  The first
+ * byte of a file picks the format like needletail's parse_fastx_file (src/dna/dnafiles.rs:52):
+ * '>' FASTA, '@' four-line FASTQ; anything else is GSB_ERR_BAD_INPUT.
  *   bytes      concatenation of the n files
  *   offsets    n+1 byte offsets into `bytes` (file i = [offsets[i], offsets[i+1]))
  *   sig_out    n * sketch_size * elem_size bytes, row i = signature of file i
