@@ -6,7 +6,7 @@ layout, so a database is served by the binary that built it.  Host s
 JSON / text; sketching, HNSW construction and search all run in libgsearch_b200.so on the GPU.
 
   gsearch [--pio N] [--nbthreads N] tohnsw -d DIR -k K -s S -n NBNG [--ef EF]
-          [--scale_modify_f F] --algo prob|super|super2|optdens|revoptdens [--aa] [--block]
+          [--scale_modify_f F] --algo prob|super|super2|optdens|revoptdens|hll [--aa] [--block]
   gsearch add -b DBDIR -n NEWDIR
   gsearch request -b DBDIR -r QUERYDIR -n NBANSWERS
   gsearch bindash -q QUERY_LIST -r REFERENCE_LIST [-k 16] [-s 2048] [-d 0|1] [-o OUT]   (src/bin/bindash.rs)

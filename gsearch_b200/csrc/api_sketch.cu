@@ -221,6 +221,7 @@ static int sig_type_of(const gsb_sketch_params &p) {
         if (p.data_t == GSB_DATA_DNA) return (p.kmer_size <= 14 || p.kmer_size == 16) ? GSB_SIG_U32 : GSB_SIG_U64;
         return p.kmer_size <= 6 ? GSB_SIG_U32 : GSB_SIG_U64;
     }
+    if (p.algo == GSB_ALGO_HLL) return GSB_SIG_U16;  // HyperLogLogSketch<Kmer, u16>: dnasketch.rs:541-573
     return GSB_SIG_F32;
 }
 
@@ -244,11 +245,6 @@ extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, 
         set_error("sketch_size %u out of range 2..65535", p.sketch_size);
         return GSB_ERR_INVALID_ARG;
     }
-    if (p.algo == GSB_ALGO_HLL) {
-        set_error("--algo hll (HyperLogLogSketch<Kmer, u16> over probminhash's SetSketcher, src/dna/dnasketch.rs:541-574) "
-                  "is not built on the device path: prob, super, super2, optdens and revoptdens are");
-        return GSB_ERR_UNSUPPORTED;
-    }
     if (p.algo > GSB_ALGO_HLL) {
         set_error("unknown algo %u", p.algo);
         return GSB_ERR_INVALID_ARG;
@@ -260,7 +256,7 @@ extern "C" int gsb_sketcher_create(const gsb_sketch_params *params, int device, 
     h->p = p;
     h->device = device;
     h->sig_type = sig_type_of(p);
-    h->elem = h->sig_type == GSB_SIG_U64 ? 8 : 4;
+    h->elem = h->sig_type == GSB_SIG_U64 ? 8 : (h->sig_type == GSB_SIG_U16 ? 2 : 4);
     h->kt32 = p.data_t == GSB_DATA_DNA ? (p.kmer_size <= 14 || p.kmer_size == 16) : (p.kmer_size <= 6);
     SketchConsts &sc = h->sc;
     sc.k = p.kmer_size;
@@ -561,10 +557,16 @@ void launch_dens(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunk
     const DensJob *jobs = h->d_jobs.as<DensJob>() + joff;
     const FileResult *res = h->d_res.as<FileResult>();
     const bool super2 = h->p.algo == GSB_ALGO_SUPER2;
+    const bool hll = h->p.algo == GSB_ALGO_HLL;
     if (nchunks) {
         Timed t_(h, CAT_K2_MARK, st);
         const uint32_t grid = std::min<uint32_t>(nchunks, (uint32_t)(h->nsm * 4));
-        if (super2)
+        if (hll)
+            k2_hll<Src, KT><<<grid, kK2Threads, 0, st>>>(
+                jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
+                dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
+                want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
+        else if (super2)
             k2_super2<Src, KT><<<grid, kK2Threads, 0, st>>>(
                 jobs, h->d_chunk_prefix.as<uint32_t>() + cpoff, njobs, h->d_files.as<FileDesc>(), res,
                 dna ? h->d_packed.as<uint32_t>() : nullptr, dna ? nullptr : h->d_packed.as<uint8_t>(),
@@ -576,7 +578,9 @@ void launch_dens(gsb_sketcher *h, uint32_t joff, uint32_t njobs, uint32_t nchunk
                 want_bounds ? h->d_bounds.as<uint32_t>() : nullptr, h->sc, nchunks);
     }
     Timed t3_(h, CAT_K3, st);
-    if (super2) {
+    if (hll) {
+        k3_hll_finalize<<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (uint16_t *)d_sig, d_nb, h->d_retry.as<uint32_t>());
+    } else if (super2) {
         if (h->elem == 8)
             k3_super2_finalize<uint64_t><<<njobs, 256, 0, st>>>(jobs, njobs, res, h->sc, (uint64_t *)d_sig, d_nb,
                                                                 h->d_retry.as<uint32_t>());
@@ -758,7 +762,11 @@ void launch_super_seq(gsb_sketcher *h, uint32_t nlist, bool dna, bool want_bound
     const uint32_t *packed_dna = dna ? h->d_packed.as<uint32_t>() : nullptr;
     const uint8_t *packed_aa = dna ? nullptr : h->d_packed.as<uint8_t>();
     const uint32_t *bounds = want_bounds ? h->d_bounds.as<uint32_t>() : nullptr;
-    if (h->p.algo == GSB_ALGO_SUPER2) {
+    if (h->p.algo == GSB_ALGO_HLL) {
+        k_hll_sequential<Src, KT><<<(nlist + 31) / 32, 32, 0, st>>>(
+            h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(), packed_dna, packed_aa,
+            bounds, h->sc, (uint16_t *)d_sig, h->d_bins.as<uint32_t>());
+    } else if (h->p.algo == GSB_ALGO_SUPER2) {
         if (h->elem == 8)
             k_super2_sequential<Src, KT, uint64_t><<<(nlist + 31) / 32, 32, 0, st>>>(
                 h->d_jobs.as<uint32_t>(), nlist, h->d_files.as<FileDesc>(), h->d_res.as<FileResult>(), packed_dna,
@@ -841,7 +849,8 @@ int run_dens(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
     }
     GSB_CUDA_TRY(pull_small(h->d_jobs.p, hj, (size_t)n * sizeof(DensJob), st));
     GSB_CUDA_TRY(pull_small(h->d_chunk_prefix.p, hcp, (size_t)ngroups * (grp + 1) * 4, st));
-    if (super2) k_super2_reset<<<592, 256, 0, st>>>(h->d_bins.as<ulonglong2>(), (size_t)n * h->sc.m);
+    if (h->p.algo == GSB_ALGO_HLL) GSB_CUDA_TRY(cudaMemsetAsync(h->d_bins.p, 0, (size_t)n * h->sc.m * 4, st));  // registers start at 0
+    else if (super2) k_super2_reset<<<592, 256, 0, st>>>(h->d_bins.as<ulonglong2>(), (size_t)n * h->sc.m);
     else k_dens_reset<<<592, 256, 0, st>>>(h->d_bins.as<uint32_t>(), (size_t)n * h->sc.m);
     h->launches += 1;
     GSB_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
@@ -1048,7 +1057,7 @@ static int sketch_batch_dev_locked(gsb_sketcher *h, const uint8_t *d_bytes, cons
             }
             if (hr[f] & 1u) {
                 next.push_back(f);
-                next_t.push_back(prob ? tmult[i] * 8.0 : 1e30);
+                next_t.push_back((prob || h->p.algo == GSB_ALGO_HLL) ? tmult[i] * 8.0 : 1e30);
             }
             if (hr[f] & 2u) seq_files.push_back(f);
         }

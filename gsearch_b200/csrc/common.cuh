@@ -87,6 +87,35 @@ __device__ __forceinline__ double expm1_spec(double z) {
     return __dmul_rn(z, r);
 }
 
+// ln(x), normal x > 0, as the SPEC freezes it (oracle/rng.c gso_ln_spec): same reduction, same
+// coefficients, same order of correctly rounded operations -- identical bits on the host and here
+// (SetSketch takes floor(1 - log_b x): a last-bit difference between two libms flips it).
+__device__ __forceinline__ double ln_spec(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    int e = (int)((bits >> 52) & 0x7FFull) - 1023;
+    double m = __longlong_as_double((long long)((bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+    if (m > 1.4142135623730951) {
+        m = __dmul_rn(m, 0.5);
+        e += 1;
+    }
+    const double f = __dadd_rn(m, -1.0);
+    const double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+    const double z = __dmul_rn(s, s);
+    const double w = __dmul_rn(z, z);
+    const double t1 = __dmul_rn(w, __dadd_rn(Lg2, __dmul_rn(w, __dadd_rn(Lg4, __dmul_rn(w, Lg6)))));
+    const double t2 = __dmul_rn(z, __dadd_rn(Lg1, __dmul_rn(w, __dadd_rn(Lg3, __dmul_rn(w, __dadd_rn(Lg5, __dmul_rn(w, Lg7)))))));
+    const double R = __dadd_rn(t2, t1);
+    const double hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
+    const double dk = (double)e;
+    // dk*ln2_hi - ((hfsq - (s*(hfsq+R) + dk*ln2_lo)) - f)
+    const double a = __dadd_rn(__dmul_rn(s, __dadd_rn(hfsq, R)), __dmul_rn(dk, ln2_lo));
+    return __dadd_rn(__dmul_rn(dk, ln2_hi), -__dadd_rn(__dadd_rn(hfsq, -a), -f));
+}
+
 // ExpRestricted01::sample, entered after the first uniform has been drawn (u0)
 __device__ __forceinline__ double exp01_sample_from(const Exp01 &e, double u0, Xoshiro &rng) {
     double x = __dmul_rn(e.c1, u0);

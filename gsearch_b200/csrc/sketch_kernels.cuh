@@ -1095,4 +1095,219 @@ __global__ void k_super2_sequential(const uint32_t *__restrict__ file_list, uint
     for (uint32_t i = 0; i < m; i++) sig[i] = (SigT)v[i];
 }
 
+// ====================================================================== SetSketch ("--algo hll")
+// HyperLogLogSketch<Kmer, u16> = probminhash SetSketcher [U] (dispatch src/dna/dnasketch.rs:541-573);
+// SPEC: oracle/sketch.c gso_setsketch.  Order-free definition: register i = max over the k-mers and
+// their points of k = clamp(floor(1 - log_b x_j), 0, 65535) for the point the k-mer's lazy
+// Fisher-Yates permutation sends to i.  Like the other sketchers the scan uses a STATIC bound:
+// points with x > X_hi = (1/a)/m * T cannot raise a register that ends at or above k(X_hi) -- checked
+// by the finalize kernel, else the genome is re-run with a larger bound -- so all but ~6 % of the
+// k-mers are dismissed by an integer compare on their first draw.
+constexpr double kHllB = 1.001, kHllInvA = 1.0 / 20.0;
+constexpr uint32_t kHllMaxSteps = 16;         // points of one k-mer below the bound that the scan follows
+constexpr uint32_t kHllOverflow = 0xFFFFFFFFu;  // register 0 holds this: the genome needs the sequential path
+constexpr double kHllSeqT = 0.25;             // bound (in unit-exponential scale) from which a file goes sequential
+
+__device__ __forceinline__ uint32_t hll_k_of(double x, double lnb) {
+    if (!(x > 0.0)) return 65535u;
+    const double z = __dadd_rn(1.0, -__ddiv_rn(ln_spec(x), lnb));
+    const double kf = floor(z);
+    return kf < 0.0 ? 0u : (kf > 65535.0 ? 65535u : (uint32_t)kf);
+}
+
+__device__ __forceinline__ double hll_T(const DensJob &job, const FileResult &fr, const SketchConsts &sc) {
+    const uint32_t nk = fr.nsym >= sc.k ? fr.nsym - sc.k + 1 : 0;
+    return nk ? job.tmult * ((double)sc.m / (double)nk) * sc.lnm8 : 2.0;
+}
+
+template <class Src, typename KT>
+__global__ void __launch_bounds__(kK2Threads)
+k2_hll(const DensJob *__restrict__ jobs, const uint32_t *__restrict__ chunk_prefix, uint32_t njobs,
+       const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+       const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+       const uint32_t *__restrict__ boundaries, SketchConsts sc, uint32_t nchunks) {
+  const double lnb = ln_spec(kHllB);
+  for (uint32_t gchunk = blockIdx.x; gchunk < nchunks; gchunk += gridDim.x) {  // persistent CTAs
+    const uint32_t j = find_file(chunk_prefix, njobs, gchunk);
+    const DensJob job = jobs[j];
+    const FileResult fr = res[job.file];
+    if (fr.status != 0) continue;
+    const uint32_t chunk = gchunk - chunk_prefix[j];
+    const uint32_t cbase = chunk * kChunk;
+    if (cbase >= fr.nsym) continue;
+    const double T = hll_T(job, fr, sc);
+    if (!(T < kHllSeqT)) continue;  // small input: the sequential kernel does the whole file
+    const FileDesc fd = files[job.file];
+    SeqView sv;
+    sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
+    sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
+    sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
+    sv.nbounds = boundaries ? fr.nrec : 0;
+    sv.N = fr.nsym;
+    const double x_hi = __dmul_rn(__ddiv_rn(kHllInvA, (double)sc.m), T);
+    // first draw E = -ln(1 - U) >= 1.001 T  <=>  U >= 1 - exp(-1.001 T): dismissed without the logarithm
+    const double uthr = 1.0 - exp(-1.001 * T);
+    const uint64_t thr52 = (uint64_t)(uthr * 4503599627370496.0) + 2;
+    const uint32_t p0 = cbase + threadIdx.x * kRun;
+    Src src;
+    src.init(sv, p0, sc.k);
+    for (uint32_t i = 0; i < kRun; i++) {
+        KT val;
+        if (!src.step(i, val)) continue;
+        const uint64_t seed = (uint64_t)val * kFxSeed64;
+        uint64_t s0;
+        const uint64_t out1 = first_output(seed, s0);
+        if ((out1 >> 12) >= thr52) continue;
+        Xoshiro rng;
+        rng.seed(seed);
+        double x = 0.0;
+        uint32_t mapk[kHllMaxSteps], mapv[kHllMaxSteps], nmap = 0;
+        for (uint32_t jj = 0; jj < sc.m; jj++) {
+            const double e = -ln_spec(__dadd_rn(1.0, -u01_f64_from_bits(rng.next())));
+            x = __dadd_rn(x, __dmul_rn(__ddiv_rn(kHllInvA, (double)(sc.m - jj)), e));
+            if (x > x_hi) break;
+            const uint32_t kk = hll_k_of(x, lnb);
+            if (kk == 0) break;
+            if (jj == kHllMaxSteps) {  // more points below the bound than the scan follows
+                atomicMax(&job.bins[0], kHllOverflow);
+                break;
+            }
+            const uint64_t range = (uint64_t)(sc.m - jj);
+            const uint32_t r = jj + uniform_usize(rng, range, UINT64_MAX - ((UINT64_MAX - range + 1) % range));
+            // lazy Fisher-Yates: position jj is never read again, so only the entries written at r > jj live on
+            uint32_t a = jj, b = r;
+            for (uint32_t q = 0; q < nmap; q++) {
+                if (mapk[q] == jj) a = mapv[q];
+                if (mapk[q] == r) b = mapv[q];
+            }
+            uint32_t reg = a;
+            if (r != jj) {
+                reg = b;
+                uint32_t q = 0;
+                while (q < nmap && mapk[q] != r) q++;
+                mapk[q] = r;
+                mapv[q] = a;
+                if (q == nmap) nmap++;
+            }
+            atomicMax(&job.bins[reg], kk);
+        }
+    }
+  }
+}
+
+// per genome: check the bound, write the u16 registers
+__global__ void __launch_bounds__(256)
+k3_hll_finalize(const DensJob *__restrict__ jobs, uint32_t njobs, const FileResult *__restrict__ res,
+                SketchConsts sc, uint16_t *__restrict__ sig_out, uint64_t *__restrict__ nb_bases_out,
+                uint32_t *__restrict__ retry) {
+    const uint32_t j = blockIdx.x;
+    if (j >= njobs) return;
+    const DensJob job = jobs[j];
+    const FileResult fr = res[job.file];
+    __shared__ uint32_t smin[256], smax[256];
+    const double T = hll_T(job, fr, sc);
+    const bool bounded = T < kHllSeqT;
+    const uint32_t nk = fr.nsym >= sc.k ? fr.nsym - sc.k + 1 : 0;
+    uint32_t mn = 0xFFFFFFFFu, mx = 0;
+    for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) {
+        const uint32_t b = job.bins[k];
+        mn = b < mn ? b : mn;
+        mx = b > mx ? b : mx;
+    }
+    smin[threadIdx.x] = mn;
+    smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int d = 128; d >= 1; d >>= 1) {
+        if (threadIdx.x < d) {
+            if (smin[threadIdx.x + d] < smin[threadIdx.x]) smin[threadIdx.x] = smin[threadIdx.x + d];
+            if (smax[threadIdx.x + d] > smax[threadIdx.x]) smax[threadIdx.x] = smax[threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    const bool ok_status = fr.status == 0;
+    const bool overflow = smax[0] == kHllOverflow;
+    // every register must have ended at or above k(X_hi): then no dismissed point could have raised one
+    const double x_hi = __dmul_rn(__ddiv_rn(kHllInvA, (double)sc.m), T);
+    const uint32_t k_hi = bounded ? hll_k_of(x_hi, ln_spec(kHllB)) : 0u;
+    const bool need_seq = ok_status && nk > 0 && (!bounded || overflow);
+    const bool need_retry = ok_status && nk > 0 && bounded && !overflow && smin[0] < k_hi;
+    if (threadIdx.x == 0) {
+        retry[job.file] = (need_retry ? 1u : 0u) | (need_seq ? 2u : 0u) | (fr.status << 8);
+        if (nb_bases_out) nb_bases_out[job.file] = fr.nbases;
+    }
+    uint16_t *out = sig_out + (size_t)job.file * sc.m;
+    for (uint32_t k = threadIdx.x; k < sc.m; k += blockDim.x) out[k] = (uint16_t)job.bins[k];
+}
+
+// cold path (small inputs): the sequential algorithm of the SPEC, one thread per file; q/p in scratch
+template <class Src, typename KT>
+__global__ void k_hll_sequential(const uint32_t *__restrict__ file_list, uint32_t nlist,
+                                 const FileDesc *__restrict__ files, const FileResult *__restrict__ res,
+                                 const uint32_t *__restrict__ packed_dna, const uint8_t *__restrict__ packed_aa,
+                                 const uint32_t *__restrict__ boundaries, SketchConsts sc,
+                                 uint16_t *__restrict__ sig_out, uint32_t *__restrict__ scratch) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nlist) return;
+    const uint32_t f = file_list[li];
+    const FileResult fr = res[f];
+    const FileDesc fd = files[f];
+    const uint32_t m = sc.m;
+    uint16_t *sig = sig_out + (size_t)f * m;
+    uint32_t *q = scratch + (size_t)li * m * 2, *p = q + m;
+    for (uint32_t i = 0; i < m; i++) {
+        sig[i] = 0;
+        q[i] = 0xFFFFFFFFu;
+        p[i] = 0;
+    }
+    const double lnb = ln_spec(kHllB);
+    uint32_t k_low = 0;
+    unsigned long long nbmin = 0;
+    SeqView sv;
+    sv.dna = packed_dna ? packed_dna + fd.out_off : nullptr;
+    sv.aa = packed_aa ? packed_aa + fd.out_off : nullptr;
+    sv.bounds = boundaries ? boundaries + fr.bd_off : nullptr;
+    sv.nbounds = boundaries ? fr.nrec : 0;
+    sv.N = fr.nsym;
+    for (uint32_t p0 = 0; p0 < fr.nsym; p0 += kRun) {
+        Src src;
+        src.init(sv, p0, sc.k);
+        for (uint32_t i = 0; i < kRun; i++) {
+            KT val;
+            if (!src.step(i, val)) continue;
+            const uint32_t irank = p0 + i;
+            Xoshiro rng;
+            rng.seed((uint64_t)val * kFxSeed64);
+            double x = 0.0;
+            for (uint32_t jj = 0; jj < m; jj++) {
+                const double e = -ln_spec(__dadd_rn(1.0, -u01_f64_from_bits(rng.next())));
+                x = __dadd_rn(x, __dmul_rn(__ddiv_rn(kHllInvA, (double)(m - jj)), e));
+                const uint32_t kk = hll_k_of(x, lnb);
+                if (kk <= k_low) break;
+                const uint64_t range = (uint64_t)(m - jj);
+                const uint32_t r = jj + uniform_usize(rng, range, UINT64_MAX - ((UINT64_MAX - range + 1) % range));
+                if (q[jj] != irank) {
+                    q[jj] = irank;
+                    p[jj] = jj;
+                }
+                if (q[r] != irank) {
+                    q[r] = irank;
+                    p[r] = r;
+                }
+                const uint32_t t = p[jj];
+                p[jj] = p[r];
+                p[r] = t;
+                const uint32_t reg = p[jj];
+                if (kk > sig[reg]) {
+                    sig[reg] = (uint16_t)kk;
+                    if (++nbmin % m == 0) {
+                        uint32_t mn = 65535;
+                        for (uint32_t t2 = 0; t2 < m; t2++) mn = sig[t2] < mn ? sig[t2] : mn;
+                        k_low = mn;
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace gsb

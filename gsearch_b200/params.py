@@ -40,6 +40,8 @@ class SeqSketcherParams:
             if self.data_t == DATA_DNA:
                 return SIG_U32 if (self.kmer_size <= 14 or self.kmer_size == 16) else SIG_U64
             return SIG_U32 if self.kmer_size <= 6 else SIG_U64
+        if self.algo == ALGO_HLL:  # HyperLogLogSketch<Kmer, u16>: dnasketch.rs:541-573
+            return SIG_U16
         return SIG_F32
 
 

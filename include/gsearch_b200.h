@@ -73,7 +73,7 @@ typedef enum {
     GSB_ALGO_OPTDENS = 2,    /* --algo optdens  OptDensMinHash, Sig = f32           */
     GSB_ALGO_REVOPTDENS = 3, /* --algo revoptdens  RevOptDensMinHash, Sig = f32      */
     GSB_ALGO_SUPER2 = 4,     /* --algo super2   SuperMinHash2, Sig = item hash u32/u64 */
-    GSB_ALGO_HLL = 5         /* --algo hll      not built: GSB_ERR_UNSUPPORTED       */
+    GSB_ALGO_HLL = 5         /* --algo hll      SetSketch registers, Sig = u16      */
 } gsb_algo;
 
 typedef enum { GSB_DATA_DNA = 0, GSB_DATA_AA = 1 } gsb_data_t;

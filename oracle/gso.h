@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 /* same numeric values as include/gsearch_b200.h */
-enum { GSO_ALGO_PROB3A = 0, GSO_ALGO_SUPER = 1, GSO_ALGO_OPTDENS = 2, GSO_ALGO_REVOPTDENS = 3, GSO_ALGO_SUPER2 = 4 };
+enum { GSO_ALGO_PROB3A = 0, GSO_ALGO_SUPER = 1, GSO_ALGO_OPTDENS = 2, GSO_ALGO_REVOPTDENS = 3, GSO_ALGO_SUPER2 = 4, GSO_ALGO_HLL = 5 };
 enum { GSO_DATA_DNA = 0, GSO_DATA_AA = 1 };
 enum { GSO_SIG_U32 = 0, GSO_SIG_U64 = 1, GSO_SIG_F32 = 2, GSO_SIG_U16 = 3 };
 enum { GSO_SPEC_NOHASH_IDENTITY = 1u << 0, GSO_SPEC_OPTDENS_F64_DRAW = 1u << 1 };
@@ -60,6 +60,7 @@ typedef struct { double lambda, c1, c2, c3; } gso_exp01;
 void gso_exp01_init(gso_exp01 *e, double lambda);
 double gso_exp01_sample(const gso_exp01 *e, gso_xoshiro *r);
 double gso_expm1_spec(double z); /* the frozen expm1 of the sampler's rejection branch, 0 <= z <= ln 2 */
+double gso_ln_spec(double x);    /* the frozen natural logarithm of the SetSketch path, normal x > 0 */
 
 /* ---------------- fasta.c : needletail-like parse + encode ------------------ */
 /* One encoded sequence per kept record (seq mode) or one per file (block mode).
@@ -99,6 +100,7 @@ int gso_revoptdens(const uint64_t *vals, uint64_t n, uint32_t m, uint32_t spec_f
 uint32_t gso_revdens_target(uint32_t i, uint32_t a, uint32_t m);
 /* SuperMinHash2: per slot the fx hash (32- or 64-bit) of the item that gave the minimum */
 int gso_superminhash2(const uint64_t *vals, uint64_t n, uint32_t m, int kt32, uint64_t *sig_out);
+int gso_setsketch(const uint64_t *vals, uint64_t n, uint32_t m, uint16_t *sig_out);
 /* SuperMinHash (f32) over distinct values in first-occurrence order */
 int gso_superminhash(const uint64_t *vals, uint64_t n, uint32_t m, float *sig_out);
 

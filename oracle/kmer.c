@@ -27,6 +27,7 @@ int gso_sig_type(const gso_sketch_params *p) {
         }
         return p->kmer_size <= 6 ? GSO_SIG_U32 : GSO_SIG_U64;
     }
+    if (p->algo == GSO_ALGO_HLL) return GSO_SIG_U16; /* HyperLogLogSketch<Kmer, u16>: dnasketch.rs:541-573 */
     return GSO_SIG_F32; /* SuperHashSketch<_, f32>, OptDensHashSketch<_, f32> */
 }
 

@@ -94,6 +94,40 @@ double gso_expm1_spec(double z) {
     return z * r;
 }
 
+/* ln(x) for normal x > 0, as this repository FREEZES it (SetSketch needs floor(1 - log_b x), and a
+ * last-bit difference between the platform libm and the device flips that floor): argument
+ * reduction x = 2^e * m with sqrt(1/2) < m <= sqrt(2), s = (m-1)/(m+1), the classic degree-14
+ * odd series in s split into even / odd halves (fdlibm's layout and published coefficients), every
+ * step one correctly rounded IEEE operation (no contraction).  Within 1 ulp of libm; the
+ * restatement and the CUDA kernel (common.cuh ln_spec) agree bit for bit.                        */
+double gso_ln_spec(double x) {
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                        Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                        Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                        Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                        Lg7 = 1.479819860511658591e-01;
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    int64_t e = (int64_t)((bits >> 52) & 0x7FF) - 1023;
+    uint64_t mb = (bits & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL;
+    double m;
+    memcpy(&m, &mb, 8);
+    if (m > 1.4142135623730951) {
+        m = m * 0.5;
+        e += 1;
+    }
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)e;
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+}
+
 /* ExpRestricted01::sample */
 double gso_exp01_sample(const gso_exp01 *e, gso_xoshiro *r) {
     double x = e->c1 * gso_uniform_f64(r);

@@ -368,6 +368,83 @@ int gso_superminhash2(const uint64_t *vals, uint64_t n, uint32_t m, int kt32, ui
 /* ------------------------------------------------------------------------- */
 /* per-file driver                                                            */
 /* ------------------------------------------------------------------------- */
+/* SetSketch ("--algo hll": HyperLogLogSketch<Kmer, u16> over probminhash::setsketcher::SetSketcher
+ * [U, low-medium]; dispatch src/dna/dnasketch.rs:541-573 with SetSketchParams::default() and
+ * m = sketch_size: b = 1.001, a = 20, q = 2^16 - 2).  Ertl's SetSketch1: per item, generator seeded
+ * by hval = fx64(item); points x_1 < x_2 < ... with x_{j+1} = x_j + (1/a)/(m-j) * E_j (E_j a unit
+ * exponential), the j-th point goes to the register drawn WITHOUT replacement (lazy Fisher-Yates,
+ * r = j + Uniform<usize>[0, m-j)) with the value k = clamp(floor(1 - log_b x), 0, q+1); a register
+ * keeps the maximum.  An item stops as soon as k <= k_low, a lower bound of all registers refreshed
+ * every m successful updates -- neutral for the result: later points have smaller k.  Items are a
+ * set: repeated k-mers change nothing.
+ * Frozen here: E = -ln_spec(1 - Uniform<f64>) (rand_distr::Exp1 is a ziggurat whose tables are not
+ * restated), ln_spec in place of libm, draw order (E_j, then the register).                       */
+int gso_setsketch(const uint64_t *vals, uint64_t n, uint32_t m, uint16_t *sig_out) {
+    if (m < 1) return 1;
+    const double b = 1.001, a = 20.0;
+    const double lnb = gso_ln_spec(b), inva = 1.0 / a;
+    const double qp1 = 65535.0;
+    int64_t *q = (int64_t *)malloc(m * sizeof(int64_t));
+    uint32_t *p = (uint32_t *)malloc(m * sizeof(uint32_t));
+    if (!q || !p) {
+        free(q);
+        free(p);
+        return 4;
+    }
+    for (uint32_t i = 0; i < m; i++) {
+        sig_out[i] = 0;
+        q[i] = -1;
+        p[i] = 0;
+    }
+    double k_low = 0.0;
+    uint64_t nbmin = 0;
+    for (uint64_t it = 0; it < n; it++) {
+        const uint64_t hval = vals[it] * FX_SEED64;
+        gso_xoshiro rng;
+        gso_xoshiro_seed_from_u64(&rng, hval);
+        const int64_t irank = (int64_t)it;
+        double x = 0.0;
+        for (uint32_t j = 0; j < m; j++) {
+            const double e = -gso_ln_spec(1.0 - gso_uniform_f64(&rng));
+            x = x + (inva / (double)(m - j)) * e;
+            double kf = 0.0;
+            if (x > 0.0) {
+                const double z = 1.0 - gso_ln_spec(x) / lnb;
+                kf = floor(z);
+                if (kf < 0.0) kf = 0.0;
+                if (kf > qp1) kf = qp1;
+            } else {
+                kf = qp1; /* x == 0: the uniform draw was 0 */
+            }
+            if (kf <= k_low) break;
+            const uint32_t r = j + (uint32_t)gso_uniform_usize(&rng, (uint64_t)(m - j));
+            if (q[j] != irank) {
+                q[j] = irank;
+                p[j] = j;
+            }
+            if (q[r] != irank) {
+                q[r] = irank;
+                p[r] = r;
+            }
+            const uint32_t t = p[j];
+            p[j] = p[r];
+            p[r] = t;
+            const uint32_t reg = p[j];
+            if (kf > (double)sig_out[reg]) {
+                sig_out[reg] = (uint16_t)kf;
+                if (++nbmin % m == 0) {
+                    uint16_t mn = 65535;
+                    for (uint32_t i = 0; i < m; i++) mn = sig_out[i] < mn ? sig_out[i] : mn;
+                    k_low = (double)mn;
+                }
+            }
+        }
+    }
+    free(q);
+    free(p);
+    return 0;
+}
+
 static int sketch_one(const gso_sketch_params *p, const uint8_t *bytes, uint64_t len, void *sig,
                       uint64_t *nb_bases) {
     gso_seqs s;
@@ -416,6 +493,8 @@ static int sketch_one(const gso_sketch_params *p, const uint8_t *bytes, uint64_t
         else
             memcpy(sig, tmp, (size_t)m * sizeof(uint64_t));
         free(tmp);
+    } else if (p->algo == GSO_ALGO_HLL) {
+        rc = gso_setsketch(vals, n, m, (uint16_t *)sig);
     } else {
         rc = 6;
     }

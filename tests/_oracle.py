@@ -193,6 +193,19 @@ def superminhash2(vals, m, kt32):
     return sig
 
 
+def setsketch(vals, m):
+    vals = np.ascontiguousarray(vals, dtype=np.uint64)
+    sig = np.zeros(m, dtype=np.uint16)
+    assert L().gso_setsketch(_p(vals), len(vals), m, _p(sig)) == 0
+    return sig
+
+
+def ln_spec(x):
+    L().gso_ln_spec.restype = C.c_double
+    L().gso_ln_spec.argtypes = [C.c_double]
+    return L().gso_ln_spec(float(x))
+
+
 def superminhash(vals, m):
     vals = np.ascontiguousarray(vals, dtype=np.uint64)
     sig = np.zeros(m, dtype=np.float32)

@@ -32,6 +32,59 @@ def expm1_spec(z):
     return z * r
 
 
+def ln_spec(x):
+    """the frozen natural logarithm of the SetSketch path (oracle/rng.c gso_ln_spec); Python floats
+    are IEEE doubles and every line below is one rounded operation, like the C source"""
+    import struct
+    ln2_hi, ln2_lo = 6.93147180369123816490e-01, 1.90821492927058770002e-10
+    Lg1, Lg2, Lg3, Lg4 = 6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01
+    Lg5, Lg6, Lg7 = 1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01
+    bits = struct.unpack("<Q", struct.pack("<d", x))[0]
+    e = ((bits >> 52) & 0x7FF) - 1023
+    m = struct.unpack("<d", struct.pack("<Q", (bits & 0x000FFFFFFFFFFFFF) | 0x3FF0000000000000))[0]
+    if m > 1.4142135623730951:
+        m = m * 0.5
+        e += 1
+    f = m - 1.0
+    s = f / (2.0 + f)
+    z = s * s
+    w = z * z
+    t1 = w * (Lg2 + w * (Lg4 + w * Lg6))
+    t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)))
+    R = t2 + t1
+    hfsq = 0.5 * f * f
+    dk = float(e)
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f)
+
+
+def setsketch_definition(vals, m):
+    """SetSketch1 as a plain definition (no early stop): register i = max over the items and their
+    points of clamp(floor(1 - log_b x_j), 0, 65535) for the point that the item's lazy Fisher-Yates
+    permutation sends to i; b = 1.001, a = 20"""
+    lnb = ln_spec(1.001)
+    inva = 1.0 / 20.0
+    reg = [0] * m
+    for v in set(vals):
+        rng = Xoshiro((v * 0x517CC1B727220A95) & M64)
+        perm = list(range(m))
+        x = 0.0
+        for j in range(m):
+            e = -ln_spec(1.0 - rng.f64())
+            x = x + (inva / float(m - j)) * e
+            if x > 0.0:
+                k = math.floor(1.0 - ln_spec(x) / lnb)
+                k = min(max(k, 0), 65535)
+            else:
+                k = 65535
+            if k <= 0:
+                break
+            r = j + rng.usize(m - j)
+            perm[j], perm[r] = perm[r], perm[j]
+            if k > reg[perm[j]]:
+                reg[perm[j]] = k
+    return reg
+
+
 class Xoshiro:
     def __init__(self, seed=None, state=None):
         if state is not None:

@@ -446,3 +446,25 @@ def test_superminhash2_and_revoptdens_equal_their_definitions(oracle):
     sa, sb = oracle.superminhash2(a, 2048, False), oracle.superminhash2(b, 2048, False)
     j = 2000 / 6000
     assert abs((sa == sb).mean() - j) < 4 * np.sqrt(j * (1 - j) / 2048)
+
+
+def test_ln_spec_and_setsketch_equal_their_definitions(oracle):
+    """--algo hll: the frozen logarithm is the same function in C and Python and within 1 ulp of libm;
+    the oracle's SetSketch (early stop on the running register minimum) equals the plain definition"""
+    import math, random
+    rnd = random.Random(7)
+    for _ in range(3000):
+        x = math.exp(rnd.uniform(-45, 2))
+        a = oracle.ln_spec(x)
+        assert a == R.ln_spec(x)
+        assert abs(a - math.log(x)) <= 1.01 * 2.0 ** -52 * max(abs(math.log(x)), 1e-300) + 1e-320
+    for m, n in ((8, 40), (33, 70), (64, 500)):
+        vals = [rnd.getrandbits(42) for _ in range(n)]
+        vals += vals[:10]                                  # repeated items change nothing
+        assert oracle.setsketch(vals, m).tolist() == R.setsketch_definition(vals, m)
+    # similar sets share most registers, disjoint ones almost none (what DistHamming sees)
+    base = [rnd.getrandbits(42) for _ in range(30000)]
+    near = base[:27000] + [rnd.getrandbits(42) for _ in range(3000)]
+    far = [rnd.getrandbits(42) for _ in range(30000)]
+    s0, s1, s2 = (oracle.setsketch(v, 1024) for v in (base, near, far))
+    assert (s0 != s1).mean() < 0.35 < 0.9 < (s0 != s2).mean()

@@ -269,3 +269,28 @@ def test_super2_large_genome_fast_path(oracle):
     d = g.DistHamming().matrix(got, got)                        # family mates (50, 51 share a root) are close
     assert d[0, 1] < 0.9 < d[0, 2] or True
     sk.close()
+
+
+@pytest.mark.parametrize("k,S", [(21, 600), (16, 256), (14, 100), (5, 64)])
+def test_hll_dna(oracle, k, S):
+    """--algo hll = HyperLogLogSketch<Kmer, u16> (SetSketch registers; src/dna/dnasketch.rs:541-573): the
+    adversarial files are small, so most take the sequential kernel; the ordinary ones the bounded scan"""
+    got, nb, want, wnb = run_both(oracle, adversarial_dna_files(k), k, S, g.ALGO_HLL)
+    assert got.dtype == np.uint16
+    assert_same(got, nb, want, wnb)
+
+
+@pytest.mark.parametrize("k,S,block", [(7, 300, False), (5, 128, True)])
+def test_hll_aa(oracle, k, S, block):
+    assert_same(*run_both(oracle, adversarial_aa_files(k), k, S, g.ALGO_HLL, g.DATA_AA, block))
+
+
+def test_hll_large_genome_bounded_scan(oracle):
+    """large inputs: every k-mer but ~6 % is dismissed by the integer test on its first draw, the bound
+    is verified by the finalize kernel (no retry, no sequential fallback expected)"""
+    files = [g.synth.dna_genome(70 + i, 1_500_000) for i in range(3)]
+    sk = g.Sketcher(g.SeqSketcherParams(21, 4096, g.ALGO_HLL))
+    got, nb = sk.sketch_files(files)
+    assert got.dtype == np.uint16 and sk.retry_count == 0
+    assert_same(got, nb, *oracle.sketch_files(files, 21, 4096, g.ALGO_HLL, nthreads=8))
+    sk.close()
