@@ -80,6 +80,7 @@ SYMBOLS = {
     "gsb_index_load_graph": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64]),
     "gsb_index_graph_sizes": (_int, [_vp, _vp, _vp]),
     "gsb_index_export_graph": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_index_export_signatures": (_int, [_vp, _vp]),
     "gsb_index_set_wave_max": (_int, [_vp, _u32]),
     "gsb_index_dump": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "gsb_index_load": (_int, [_vp, C.c_char_p, C.c_char_p]),

@@ -525,6 +525,21 @@ static int search_batch_impl(gsb_index *idx, const void *queries, uint32_t nq, u
     return GSB_OK;
 }
 
+extern "C" int gsb_index_export_signatures(const gsb_index *cidx, void *sigs_out) {
+    gsb_index *idx = const_cast<gsb_index *>(cidx);
+    if (!idx || (idx->n && !sigs_out)) {
+        set_error("gsb_index_export_signatures: NULL argument");
+        return GSB_ERR_INVALID_ARG;
+    }
+    std::unique_lock<std::recursive_mutex> lock_(idx->mu);
+    if (idx->n == 0) return GSB_OK;
+    GSB_CUDA_TRY(cudaSetDevice(idx->device));
+    const size_t bytes = (size_t)idx->n * idx->p.sketch_size * idx->elem;
+    GSB_CUDA_TRY(cudaMemcpyAsync(sigs_out, idx->d_sigs.p, bytes, cudaMemcpyDeviceToHost, idx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    return GSB_OK;
+}
+
 extern "C" int gsb_index_search_batch(gsb_index *idx, const void *queries, uint32_t nq, uint32_t knbn,
                                       uint32_t ef, gsb_neighbour *out, uint32_t *counts_out,
                                       uint64_t *nb_eval_out) {

@@ -2,6 +2,7 @@
 Hnsw::new (src/dna/dnasketch.rs:139), parallel_insert (:435), parallel_search
 (src/dna/dnarequest.rs:353), get_nb_point, file_dump / load (src/utils/dumpload.rs:31)."""
 import ctypes as C
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -129,8 +130,32 @@ class Hnsw:
                         for r in out[i, :counts[i]]])
         return res
 
+    def export_signatures(self):
+        """the signatures in insertion order (n x S), copied to host memory"""
+        n = self.get_nb_point()
+        out = np.zeros((n, self.sketch_size), dtype=self.dtype)
+        if n:
+            _lib.check(_lib.lib().gsb_index_export_signatures(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
     def file_dump(self, directory, basename="hnswdump"):
+        """hnsw.file_dump (src/utils/dumpload.rs:31).  Native layout by default; GSB_DUMP_HNSWIO=1 writes
+        the hnsw_rs hnswio-style layout of gsearch_b200/hnswio.py (byte compatibility unverified)"""
+        if os.environ.get("GSB_DUMP_HNSWIO", "0") not in ("", "0"):
+            from . import hnswio
+            hnswio.dump(str(directory), basename, self.export_graph(), self.export_signatures(),
+                        self.params.max_nb_conn, self.params.ef)
+            return
         _lib.check(_lib.lib().gsb_index_dump(self._h, str(directory).encode(), basename.encode()))
 
     def load(self, directory, basename="hnswdump"):
+        """HnswIo::load_hnsw; the layout is recognised by its magic number"""
+        from . import hnswio
+        if hnswio.is_hnswio(str(directory), basename):
+            im = hnswio.load(str(directory), basename)
+            if np.dtype(im["dtype"]) != np.dtype(self.dtype) or im["sigs"].shape[1] != self.sketch_size:
+                raise ValueError("dump holds %s signatures of size %d" % (im["dtype"], im["sigs"].shape[1]))
+            self.load_graph(im["sigs"], im["ids"], im["levels"], im["ranks"], im["nbr_offsets"], im["nbr_index"],
+                            im["entry_point"], im["nbr_dist"])
+            return
         _lib.check(_lib.lib().gsb_index_load(self._h, str(directory).encode(), basename.encode()))

@@ -270,6 +270,9 @@ GSB_API int gsb_index_graph_sizes(const gsb_index *idx, uint64_t *total_lists, u
 GSB_API int gsb_index_export_graph(const gsb_index *idx, uint8_t *levels, uint32_t *ranks,
                                    uint64_t *ids, uint64_t *nbr_offsets, uint32_t *nbr_index,
                                    float *nbr_dist, uint64_t *entry_point);
+/* the signatures of the index, n x sketch_size elements in insertion order, to host memory (with the
+ * graph image above this is everything a converter to another dump format needs)                 */
+GSB_API int gsb_index_export_signatures(const gsb_index *idx, void *sigs_out);
 /* Points inserted together by gsb_index_insert_batch (the reference inserts with one rayon
  * task per point, src/dna/dnasketch.rs:435; here a wave of at most wave_max points searches
  * the graph as it was before the wave).  Default = two per SM; 1 = sequential insertion. */
