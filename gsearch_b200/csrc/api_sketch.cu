@@ -375,7 +375,7 @@ void launch_k1(gsb_sketcher *h, const uint8_t *d_bytes, uint64_t total, uint32_t
             d_bytes, total, files, tprefix, nf, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(),
             h->d_tnrec.as<uint16_t>(), tile0, h->d_fqflag.as<uint32_t>() + f0);
     }
-    k1b_resolve<<<(nf * 32 + 127) / 128, 128, 0, st>>>(
+    k1b_resolve<<<nf, kK1bThreads, 0, st>>>(
         files, nf, d_bytes, h->d_tc4.as<uint64_t>(), h->d_ttrans.as<uint8_t>(), h->d_tnrec.as<uint16_t>(),
         h->d_tstate.as<uint8_t>(), h->d_tbase.as<uint32_t>(), h->d_trecbase.as<uint32_t>(), res,
         h->d_misc.as<uint32_t>(), bd_cap, want_bounds ? 1 : 0, (DATA_T == 1 && SEQ_SEP) ? 1 : 0,

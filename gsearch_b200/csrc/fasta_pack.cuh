@@ -17,7 +17,7 @@
 //   k1a_tile_summary : per 4 KiB tile, the tile's effect on the parser state as a function
 //                      of the (unknown) incoming state, and its symbol count for each of the
 //                      four possible incoming states;
-//   k1b_resolve      : one warp per file walks its tiles, resolves states, prefix-sums counts;
+//   k1b_resolve      : one CTA per file resolves states and prefix-sums counts (two block scans);
 //   k1c_pack         : per tile again (bytes now come from L2), compacts and writes.
 // FASTQ (first byte '@'; needletail reads four-line records only [U]) runs through the same three
 // kernels with another 4-state machine: s = line number mod 4, '\n' is s -> s+1, a byte is emitted
@@ -430,8 +430,15 @@ k1a_tile_summary(const uint8_t *__restrict__ bytes, uint64_t total,
 }
 
 // ------------------------------------------------------------------ K1b
-// one warp per file: resolve incoming state and exclusive prefix of symbols / records per tile
-__global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
+// one CTA per file: resolve the incoming parser state and the exclusive prefix of symbols / records
+// of every tile.  A thread owns a run of consecutive tiles: it composes their state functions, the
+// CTA scans the 256 compositions (so every thread knows the state entering its run), the thread
+// walks its run again with the states known, and a second scan turns the per-thread totals into
+// bases.  (Round 1 walked a file with ONE warp, 32 tiles per trip: 42 us for 5 MB files, as long as
+// the tile-summary kernel itself.)
+constexpr int kK1bThreads = 256;
+__global__ void __launch_bounds__(kK1bThreads)
+k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
                             const uint8_t *__restrict__ bytes,
                             const uint64_t *__restrict__ t_counts4,
                             const uint8_t *__restrict__ t_trans,
@@ -440,52 +447,62 @@ __global__ void k1b_resolve(const FileDesc *__restrict__ files, uint32_t nfiles,
                             FileResult *__restrict__ res, uint32_t *__restrict__ bd_cursor,
                             uint32_t bd_capacity, int want_boundaries, int sep_counts_as_symbol,
                             const uint32_t *__restrict__ fq_flags) {
-    const uint32_t fi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ uint32_t s_fn[kK1bThreads];
+    __shared__ uint32_t s_cnt[kK1bThreads], s_rec[kK1bThreads];
+    const uint32_t fi = blockIdx.x;
     if (fi >= nfiles) return;
-    const uint32_t lane = lane_id();
+    const uint32_t t = threadIdx.x;
     const FileDesc fd = files[fi];
     const uint8_t first = fd.end > fd.beg ? bytes[fd.beg] : (uint8_t)'>';
     const bool fq = first == '@';  // FASTQ: t_nrec holds the tile's newline count
-    uint32_t s_carry = 0, base = 0, recbase = 0;
-    for (uint32_t c0 = 0; c0 < fd.ntiles; c0 += 32) {
-        const uint32_t i = c0 + lane;
-        const bool on = i < fd.ntiles;
-        const uint32_t T = fd.tile_first + i;
-        uint32_t f = on ? t_trans[T] : kFnIdent;
-        const unsigned long long c4 = on ? t_counts4[T] : 0ull;
-        const uint32_t nr = on ? t_nrec[T] : 0u;
-        uint32_t incl = f;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl = fn_compose(up, incl);
-        }
-        uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = kFnIdent;
-        const uint32_t s_in = fn_apply(excl, s_carry);
-        const uint32_t cnt = (uint32_t)((c4 >> (16 * s_in)) & 0xFFFFull);
-        // FASTQ: a record starts at the file's first byte and at every newline that leads to line 0
-        const uint32_t nrr = fq ? (on ? ((s_in + nr) >> 2) + (i == 0 ? 1u : 0u) : 0u) : nr;
-        uint32_t ci = cnt, ri = nrr;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u1 = __shfl_up_sync(0xffffffffu, ci, d);
-            const uint32_t u2 = __shfl_up_sync(0xffffffffu, ri, d);
-            if (lane >= (uint32_t)d) {
-                ci += u1;
-                ri += u2;
-            }
-        }
-        if (on) {
-            t_state[T] = (uint8_t)s_in;
-            t_base[T] = base + ci - cnt;
-            t_recbase[T] = recbase + ri - nrr;
-        }
-        s_carry = fn_apply(__shfl_sync(0xffffffffu, incl, 31), s_carry);
-        base += __shfl_sync(0xffffffffu, ci, 31);
-        recbase += __shfl_sync(0xffffffffu, ri, 31);
+    const uint32_t per = (fd.ntiles + kK1bThreads - 1) / kK1bThreads;
+    const uint32_t i0 = t * per, i1 = i0 + per < fd.ntiles ? i0 + per : fd.ntiles;
+    // ---- composition of the run's state functions
+    uint32_t f = kFnIdent;
+    for (uint32_t i = i0; i < i1; i++) f = fn_compose(f, t_trans[fd.tile_first + i]);
+    s_fn[t] = f;
+    __syncthreads();
+    for (int d = 1; d < kK1bThreads; d <<= 1) {  // inclusive scan under composition (earlier first)
+        const uint32_t up = t >= (uint32_t)d ? s_fn[t - d] : kFnIdent;
+        __syncthreads();
+        if (t >= (uint32_t)d) s_fn[t] = fn_compose(up, s_fn[t]);
+        __syncthreads();
     }
-    if (lane == 0) {
+    uint32_t s = t ? fn_apply(s_fn[t - 1], 0u) : 0u;  // state entering the run (a file starts in state 0)
+    // ---- the run with the states known: per-tile state, local prefix of symbols / records
+    uint32_t cnt_tot = 0, rec_tot = 0;
+    for (uint32_t i = i0; i < i1; i++) {
+        const uint32_t T = fd.tile_first + i;
+        const unsigned long long c4 = t_counts4[T];
+        const uint32_t nr = t_nrec[T];
+        const uint32_t cnt = (uint32_t)((c4 >> (16 * s)) & 0xFFFFull);
+        // FASTQ: a record starts at the file's first byte and at every newline that leads to line 0
+        const uint32_t nrr = fq ? ((s + nr) >> 2) + (i == 0 ? 1u : 0u) : nr;
+        t_state[T] = (uint8_t)s;
+        t_base[T] = cnt_tot;      // relative to the run; the base of the run is added below
+        t_recbase[T] = rec_tot;
+        cnt_tot += cnt;
+        rec_tot += nrr;
+        s = fn_apply(t_trans[T], s);
+    }
+    s_cnt[t] = cnt_tot;
+    s_rec[t] = rec_tot;
+    __syncthreads();
+    for (int d = 1; d < kK1bThreads; d <<= 1) {
+        const uint32_t uc = t >= (uint32_t)d ? s_cnt[t - d] : 0u, ur = t >= (uint32_t)d ? s_rec[t - d] : 0u;
+        __syncthreads();
+        s_cnt[t] += uc;
+        s_rec[t] += ur;
+        __syncthreads();
+    }
+    const uint32_t cbase = s_cnt[t] - cnt_tot, rbase = s_rec[t] - rec_tot;
+    for (uint32_t i = i0; i < i1; i++) {
+        const uint32_t T = fd.tile_first + i;
+        t_base[T] += cbase;
+        t_recbase[T] += rbase;
+    }
+    if (t == kK1bThreads - 1) {
+        const uint32_t base = s_cnt[t], recbase = s_rec[t];
         FileResult r;
         r.nsym = base;
         r.nrec = recbase;
@@ -511,10 +528,17 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
          uint32_t *__restrict__ out_dna, uint8_t *__restrict__ out_aa,
          uint32_t *__restrict__ boundaries /* DNA seq mode, else null */, uint32_t tile0) {
     __shared__ __align__(16) uint8_t sm[kTile + 32];
-    __shared__ __align__(16) uint8_t stage[kTile + 256 + 16];
+    // AA: one byte per symbol, staged and copied.  DNA: the thread packs its (at most 16) codes into
+    // one word, first base in the top bits, and ORs it into a word image of the tile's output at its
+    // bit offset -- two shared-memory atomics per thread instead of 16 byte stores and, later, 16
+    // byte loads per output word.
+    __shared__ __align__(16) uint8_t stage[DATA_T == 1 ? kTile + 256 + 16 : 16];
+    __shared__ uint32_t wimg[DATA_T == 0 ? kTile / 16 + 4 : 1];
     __shared__ uint8_t aa_lut[256];
     __shared__ uint32_t wtot[kK1Threads / 32];
     if (DATA_T == 1) init_aa_lut(aa_lut);
+    if (DATA_T == 0)
+        for (uint32_t w = threadIdx.x; w < kTile / 16 + 4; w += kK1Threads) wimg[w] = 0;  // (load_tile synchronises)
     const uint32_t tile = blockIdx.x + tile0;  // files/tile_prefix/res point at the range's first file
     const uint32_t fi = find_file(tile_prefix, nfiles, tile);
     const FileDesc fd = files[fi];
@@ -549,7 +573,14 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
     uint32_t ro = sc >> 16;             // record starts in earlier threads of this tile
     const uint32_t ntile = tile_tot & 0xFFFFu;
     const uint32_t pbase = t_base[tile];
-    // concrete pass: emit symbols into the staging buffer
+    const uint32_t o_first = o;   // DNA: where this thread's codes start; `acc` collects them, top-aligned
+    uint32_t acc = 0;
+    auto emit_sym = [&](uint32_t code) {
+        if (DATA_T == 0) acc |= code << (30u - 2u * (o - o_first));
+        else stage[o] = (uint8_t)code;
+        o++;
+    };
+    // concrete pass: emit symbols
     if (fq) {
         uint32_t bad = 0;
 #pragma unroll 1
@@ -572,10 +603,10 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
                 }
             } else if (s == 1) {
                 const int code = sym_code<DATA_T>(c, aa_lut);
-                if (code >= 0) stage[o++] = (uint8_t)code;
+                if (code >= 0) emit_sym((uint32_t)code);
             }
             if (start) {
-                if (DATA_T == 1 && SEQ_SEP) stage[o++] = 0;
+                if (DATA_T == 1 && SEQ_SEP) emit_sym(0u);
                 if (DATA_T == 0 && boundaries) {
                     boundaries[fr.bd_off + t_recbase[tile] + ro] = pbase + o;
                     ro++;
@@ -595,17 +626,20 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
         }
         if (DATA_T == 0) {
             if (emit == 0xFFFFu) {
+                // four codes per word sit in byte lanes (first byte lowest): one multiply gathers them
+                // into a byte, first base highest ((x * 0x40100401) >> 24 for x = b0 + b1<<8 + b2<<16 + b3<<24)
 #pragma unroll
-                for (int i = 0; i < 16; i++) stage[o + i] = (uint8_t)((ck.codes[i >> 2] >> (8 * (i & 3))) & 3u);
+                for (int q = 0; q < 4; q++) acc |= (((ck.codes[q] & 0x03030303u) * 0x40100401u) >> 24) << (24 - 8 * q);
+                o += 16;
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i++)
-                    if ((emit >> i) & 1u) stage[o++] = (uint8_t)((ck.codes[i >> 2] >> (8 * (i & 3))) & 3u);
+                    if ((emit >> i) & 1u) emit_sym((ck.codes[i >> 2] >> (8 * (i & 3))) & 3u);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if ((emit >> i) & 1u) stage[o++] = (uint8_t)aa_code(p[i]);
+                if ((emit >> i) & 1u) emit_sym(aa_code(p[i]));
         }
     } else {
 #pragma unroll 1
@@ -613,7 +647,7 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
             const uint32_t c = p[i];
             if (c == '>' && p[i - 1] == '\n') {
                 s = 1;
-                if (DATA_T == 1 && SEQ_SEP) stage[o++] = 0;
+                if (DATA_T == 1 && SEQ_SEP) emit_sym(0u);
                 if (DATA_T == 0 && boundaries) {
                     boundaries[fr.bd_off + t_recbase[tile] + ro] = pbase + o;
                     ro++;
@@ -624,31 +658,29 @@ k1c_pack(const uint8_t *__restrict__ bytes, uint64_t total, const FileDesc *__re
                 if (c == 'c' && (s & 1u) && is_capsid(p + i)) s |= 2u;
                 if (s == 0) {
                     const int code = sym_code<DATA_T>(c, aa_lut);
-                    if (code >= 0) stage[o++] = (uint8_t)code;
+                    if (code >= 0) emit_sym((uint32_t)code);
                 }
             }
         }
+    }
+    if (DATA_T == 0 && o != o_first) {
+        const uint32_t pos = (pbase & 15u) + o_first, w = pos >> 4, sh = pos & 15u;
+        atomicOr(&wimg[w], acc >> (2u * sh));
+        if (sh && (o - o_first) + sh > 16u) atomicOr(&wimg[w + 1], acc << (32u - 2u * sh));
     }
     __syncthreads();
     if (DATA_T == 1) {
         uint8_t *dst = out_aa + fd.out_off + pbase;
         for (uint32_t i = threadIdx.x; i < ntile; i += kK1Threads) dst[i] = stage[i];
     } else {
-        // pack 16 bases per word, first base in the top bits; edge words are shared with
-        // the neighbouring tiles and go through atomicOr (the output is pre-zeroed)
+        // 16 bases per word, first base in the top bits; edge words are shared with the
+        // neighbouring tiles and go through atomicOr (the output is pre-zeroed)
         if (ntile == 0) return;
         uint32_t *dst = out_dna + fd.out_off;
         const uint32_t w_first = pbase >> 4, w_last = (pbase + ntile - 1) >> 4;
         for (uint32_t w = w_first + threadIdx.x; w <= w_last; w += kK1Threads) {
-            uint32_t val = 0;
-            const int64_t rel = (int64_t)w * 16 - (int64_t)pbase;  // stage index of base 16w
-            bool full = rel >= 0 && rel + 16 <= (int64_t)ntile;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int64_t j = rel + i;
-                const uint32_t code = (j >= 0 && j < (int64_t)ntile) ? stage[j] : 0u;
-                val |= code << (30 - 2 * i);
-            }
+            const uint32_t val = wimg[w - w_first];
+            const bool full = w * 16 >= pbase && w * 16 + 16 <= pbase + ntile;
             if (full) dst[w] = val; else if (val) atomicOr(&dst[w], val);
         }
     }
