@@ -241,6 +241,10 @@ struct Visit {
         if (bits) atomicOr(&bits[x >> 5], 1u << (x & 31u));
         else stamps[x] = stamp;
     }
+    __device__ __forceinline__ void unmark(uint32_t x) {  // (stamps start at 1: 0 is "never visited")
+        if (bits) atomicAnd(&bits[x >> 5], ~(1u << (x & 31u)));
+        else stamps[x] = 0;
+    }
 };
 
 template <int ELEM, bool F32>
@@ -309,16 +313,25 @@ __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView
 // compare the two pieces out of shared memory.  No register loads, no LSU slots, and the L2 policies
 // keep the queries resident under the stream of rows.  full[s]: both copies landed; empty[s]: the
 // eight warps are done with the slot.
+//
+// Roles inside the CTA (ring kernel): warp 0 is the CONTROL warp -- its lane 0 owns the two heaps --
+// and warps 1..7 are the 224 WORKERS that gather neighbours and compare rows.  While the control
+// lane files the results of expansion i into the heaps (a serial chain of dependent sift steps,
+// ~6 000 cycles), the workers already gather and stream the expansion the search will most likely
+// do next (search_layer_ring below): the heap work left the critical path.
 constexpr uint32_t kRingSlots = 3;
-constexpr uint32_t kRingChunk = 8192;   // 2 x 16 bytes of the row per thread and job
+constexpr uint32_t kRingWorkers = kSearchThreads - 32;   // 224
+constexpr uint32_t kRingChunk = kRingWorkers * 32;       // 7168 bytes: 2 x 16 bytes of the row per worker and job
 constexpr uint32_t kRingBytes = kRingSlots * 2 * kRingChunk;
 struct RowRing {
     uint8_t *buf;             // kRingSlots x [row piece | query piece], 128-byte aligned
     uint64_t *full, *empty;   // [kRingSlots] each
-    uint32_t slot, par;       // next job's slot and the parity of its use (uniform in the CTA)
+    uint32_t slot, par;       // next job's slot and the parity of its use (uniform among the workers)
     uint64_t pol_rows, pol_query;
 };
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(kRingWorkers) : "memory"); }
 
+// workers only (threadIdx.x >= 32); ends with a workers' barrier: D[0..nE) is complete for them
 template <int ELEM, bool F32>
 __device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g, const uint32_t *E, uint32_t nE,
                                             float *D, uint32_t *acc, RowRing &ring) {
@@ -327,10 +340,10 @@ __device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g
     const uint32_t row = g.S * ELEM;
     const uint32_t nch = (row + kRingChunk - 1) / kRingChunk;
     const uint32_t J = nE * nch;
-    const uint32_t t = threadIdx.x;
-    for (uint32_t i = t; i < nE; i += blockDim.x) acc[i] = 0;
-    __syncthreads();
-    uint32_t pr = 0, pc = 0, pj = 0, pslot = rr.slot;  // producer (thread 0): next job to issue
+    const uint32_t t = threadIdx.x - 32;  // worker index
+    for (uint32_t i = t; i < nE; i += kRingWorkers) acc[i] = 0;
+    bar_workers();
+    uint32_t pr = 0, pc = 0, pj = 0, pslot = rr.slot;  // producer (worker 0): next job to issue
     auto issue = [&]() {
         const uint32_t off = pc * kRingChunk;
         const uint32_t bytes = row - off < kRingChunk ? row - off : kRingChunk;
@@ -351,11 +364,11 @@ __device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g
     for (uint32_t j = 0; j < J; j++) {
         const uint32_t off = c * kRingChunk;
         const uint32_t nv = (row - off < kRingChunk ? row - off : kRingChunk) / 16;
-        mbar_wait(&rr.full[rr.slot], rr.par);
+        mbar_wait(&rr.full[rr.slot], rr.par);  // (one polling lane per warp + __syncwarp: measured 14 % slower)
         const uint4 *s4 = reinterpret_cast<const uint4 *>(rr.buf + rr.slot * (2 * kRingChunk));
         const uint4 *sq = s4 + kRingChunk / 16;
         if (t < nv) cnt += diff16<ELEM, F32>(sq[t], s4[t]);
-        if (t + 256 < nv) cnt += diff16<ELEM, F32>(sq[t + 256], s4[t + 256]);
+        if (t + kRingWorkers < nv) cnt += diff16<ELEM, F32>(sq[t + kRingWorkers], s4[t + kRingWorkers]);
         if (++c == nch) {  // the row is complete (uniform)
             c = 0;
 #pragma unroll
@@ -366,7 +379,7 @@ __device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g
         }
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&rr.empty[rr.slot]);
-        if (t == 0 && pj < J) {  // refill this slot as soon as the eight warps have released it
+        if (t == 0 && pj < J) {  // refill this slot as soon as the seven warps have released it
             mbar_wait(&rr.empty[rr.slot], rr.par);
             issue();
         }
@@ -377,9 +390,10 @@ __device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g
     }
     ring.slot = rr.slot;
     ring.par = rr.par;
-    __syncthreads();
+    bar_workers();
     const float fS = (float)g.S;
-    for (uint32_t i = t; i < nE; i += blockDim.x) D[i] = __fdiv_rn((float)acc[i], fS);
+    for (uint32_t i = t; i < nE; i += kRingWorkers) D[i] = __fdiv_rn((float)acc[i], fS);
+    bar_workers();
 }
 
 // stage one signature row in shared memory (TMA bulk copy when alignment allows) and return where
@@ -473,8 +487,7 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
 #ifdef GSB_K7_PROF
         pt_g += clock64() - pt0; pt0 = clock64();
 #endif
-        if (RING) eval_list_ring<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc, *rr);
-        else eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
+        eval_list<ELEM, F32>(smem_q, g, sh.E, tot, sh.D, sh.acc);
         __syncthreads();
 #ifdef GSB_K7_PROF
         pt_e += clock64() - pt0; pt0 = clock64(); pt_n++; pt_rows += tot;
@@ -505,6 +518,192 @@ __device__ void search_layer_dev(const GraphView &g, const uint8_t *smem_q, uint
     __syncthreads();
 }
 
+#ifdef GSB_K7_PROF
+__device__ __forceinline__ long long gsb_clk() {
+    long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory");
+    return c;
+}
+#endif
+// workers: the unvisited neighbours of `node` (layer 0) in list order -> E[0..tot), marked visited
+__device__ __forceinline__ uint32_t gather_workers(const GraphView &g, uint32_t node, uint32_t *E, uint32_t *wcnt,
+                                                   Visit &vis) {
+    const uint32_t t = threadIdx.x - 32, warp = t >> 5, lane = lane_id();
+    const uint32_t cap = 2 * g.M;
+    uint32_t len;
+    const uint32_t *lst = list_of(g, node, 0, len);
+    uint32_t tot = 0;
+    for (uint32_t base = 0; base < cap; base += kRingWorkers) {
+        const uint32_t i = base + t;
+        const uint32_t nb = i < cap ? __ldg(&lst[i]) : 0u;
+        const bool unv = i < len && !vis.seen(nb);
+        const uint32_t bal = __ballot_sync(0xffffffffu, unv);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        bar_workers();
+        uint32_t pre = tot;
+        for (uint32_t w = 0; w < kRingWorkers / 32; w++) {
+            const uint32_t c = wcnt[w];
+            if (w < warp) pre += c;
+            tot += c;
+        }
+        if (unv) {
+            E[pre + __popc(bal & ((1u << lane) - 1))] = nb;
+            vis.mark(nb);
+        }
+        bar_workers();
+        if (base + kRingWorkers >= len) break;  // nothing valid beyond the count
+    }
+    return tot;
+}
+
+// search_layer on layer 0 for the ring kernel, same results as search_layer_dev.  Per expansion the
+// reference files the evaluated neighbours into the heaps and THEN pops the next candidate; here the
+// control lane first PREDICTS that pop -- the current root of the candidate heap unless an evaluated
+// neighbour is strictly closer (the first such in list order; an equal one stays below the root in
+// Rust's sift-up) -- the workers gather and stream the predicted node while the control lane does
+// the heap work, and the prediction is then compared with the real pop.  A wrong prediction (only
+// when the heaps' tie handling or the result-heap threshold intervenes) is rolled back: the
+// visited marks of the speculative gather are cleared and the real node is expanded.
+template <int ELEM, bool F32>
+__device__ void search_layer_ring(const GraphView &g, const uint8_t *q, uint32_t ep, float d_ep, uint32_t ef,
+                                  HnswShared &sh, uint32_t *E2, float *D2, Visit &vis, unsigned long long &neval,
+                                  RowRing &rr) {
+    vis.begin();
+    __syncthreads();
+    const bool worker = threadIdx.x >= 32;
+    const bool ctl = threadIdx.x == 0;
+    auto pop_next = [&]() {
+        sh.done = 0;
+        if (sh.cand.n == 0) {
+            sh.done = 1;
+        } else {
+            const HItem c = sh.cand.pop();
+            if (-c.d > sh.ret.at(0).d) sh.done = 1;
+            sh.node = c.p;
+        }
+    };
+    if (ctl) {
+        sh.cand.n = 0;
+        sh.ret.n = 0;
+        vis.mark(ep);
+        sh.cand.push(-d_ep, ep);
+        sh.ret.push(d_ep, ep);
+        neval += 1;  // the reference evaluates the distance to the layer's entry point again
+        pop_next();
+    }
+    __syncthreads();
+    if (sh.done) return;
+    uint32_t *Ec = sh.E, *En = E2;
+    float *Dc = sh.D, *Dn = D2;
+    if (worker) {
+        const uint32_t tot = gather_workers(g, sh.node, Ec, sh.wcnt, vis);
+        if (threadIdx.x == 32) sh.work = tot;
+        eval_list_ring<ELEM, F32>(q, g, Ec, tot, Dc, sh.acc, rr);
+    }
+#ifdef GSB_K7_PROF
+    long long pt_g = 0, pt_e = 0, pt_h = 0, pt_n = 0, pt_w1 = 0, pt_w2 = 0, pt_miss = 0, pt_p = 0, pt0;
+#endif
+    for (;;) {
+#ifdef GSB_K7_PROF
+        pt0 = gsb_clk();
+#endif
+        __syncthreads();  // D of the current expansion is complete, the heaps are at rest
+#ifdef GSB_K7_PROF
+        pt_w1 += gsb_clk() - pt0;
+#endif
+        const uint32_t tot = sh.work;
+#ifdef GSB_K7_PROF
+        const long long ptp = gsb_clk();
+#endif
+        if (ctl) {  // predict the next pop
+            uint32_t pred = sh.cand.n ? sh.cand.at(0).p : 0xFFFFFFFFu;
+            float best = sh.cand.n ? -sh.cand.at(0).d : 3.0e38f;
+            const bool room = sh.ret.n + tot <= ef;   // every evaluated neighbour will be pushed
+            const float top = sh.ret.at(0).d;
+            for (uint32_t i = 0; i < tot; i++) {
+                const float ed = Dc[i];
+                if (ed < best && (room || ed < top)) {
+                    best = ed;
+                    pred = Ec[i];
+                }
+            }
+            sh.next = pred;
+        }
+        __syncthreads();
+#ifdef GSB_K7_PROF
+        pt_p += gsb_clk() - ptp;
+#endif
+        const uint32_t pred = sh.next;
+        uint32_t tot_n = 0;
+        if (worker) {
+            if (pred != 0xFFFFFFFFu) {
+#ifdef GSB_K7_PROF
+                pt0 = gsb_clk();
+#endif
+                tot_n = gather_workers(g, pred, En, sh.wcnt, vis);
+#ifdef GSB_K7_PROF
+                pt_g += gsb_clk() - pt0; pt0 = gsb_clk();
+#endif
+                eval_list_ring<ELEM, F32>(q, g, En, tot_n, Dn, sh.acc, rr);
+#ifdef GSB_K7_PROF
+                pt_e += gsb_clk() - pt0; pt_n++;
+#endif
+            }
+        } else if (ctl) {
+#ifdef GSB_K7_PROF
+            pt0 = gsb_clk();
+#endif
+            neval += tot;
+            for (uint32_t i = 0; i < tot; i++) {
+                const float ed = Dc[i];
+                if (ed < sh.ret.at(0).d || sh.ret.n < ef) {
+                    sh.cand.push(-ed, Ec[i]);
+                    sh.ret.push(ed, Ec[i]);
+                    if (sh.ret.n > ef) (void)sh.ret.pop();
+                }
+            }
+            pop_next();
+#ifdef GSB_K7_PROF
+            pt_h += gsb_clk() - pt0; pt_n++;
+#endif
+        }
+#ifdef GSB_K7_PROF
+        pt0 = gsb_clk();
+#endif
+        __syncthreads();
+#ifdef GSB_K7_PROF
+        pt_w2 += gsb_clk() - pt0;
+        if (pred != sh.node) pt_miss++;
+#endif
+        if (sh.done) {
+            // (a speculative gather left marks behind: the layer search is over, nobody reads them)
+            break;
+        }
+        if (pred != sh.node) {  // rare: undo the speculation, expand the real node
+            if (worker) {
+                if (pred != 0xFFFFFFFFu)
+                    for (uint32_t i = threadIdx.x - 32; i < tot_n; i += kRingWorkers) vis.unmark(En[i]);
+                bar_workers();
+                tot_n = gather_workers(g, sh.node, En, sh.wcnt, vis);
+                eval_list_ring<ELEM, F32>(q, g, En, tot_n, Dn, sh.acc, rr);
+            }
+        }
+        if (threadIdx.x == 32) sh.work = tot_n;
+        uint32_t *te = Ec;
+        Ec = En;
+        En = te;
+        float *td = Dc;
+        Dc = Dn;
+        Dn = td;
+    }
+#ifdef GSB_K7_PROF
+    if ((threadIdx.x == 0 || threadIdx.x == 32) && blockIdx.x % 97 == 0 && pt_n)
+        printf("k7prof cta %u thr %u: n %lld miss %lld  cycles/expansion: gather %lld eval %lld heap %lld wait_top %lld wait_end %lld predict+bar %lld\n",
+               blockIdx.x, threadIdx.x, pt_n, pt_miss, pt_g / pt_n, pt_e / pt_n, pt_h / pt_n, pt_w1 / pt_n, pt_w2 / pt_n, pt_p / pt_n);
+#endif
+    __syncthreads();
+}
+
 // per-CTA workspace layout in global memory
 struct WsLayout {
     size_t stride;     // bytes per CTA
@@ -528,6 +727,8 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
     __shared__ HnswShared sh;
     __shared__ __align__(8) HItem cand_sm[kCandSmemK7];
     __shared__ uint32_t s_q;
+    __shared__ uint32_t E2[RING ? kMaxList : 1];   // second expansion buffer (search_layer_ring)
+    __shared__ float D2[RING ? kMaxList : 1];
     const size_t row = (size_t)g.S * ELEM;
     const size_t row128 = staged ? ((row + 127) & ~(size_t)127) : (RING ? (size_t)kRingBytes : 0);
     uint8_t *my = ws + (size_t)blockIdx.x * wl.stride;
@@ -536,7 +737,7 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
         mbar_init(&bar, 1);
         for (uint32_t s = 0; s < kRingSlots; s++) {
             mbar_init(&ring_bar[s], 1);
-            mbar_init(&ring_bar[kRingSlots + s], kSearchThreads / 32);
+            mbar_init(&ring_bar[kRingSlots + s], kRingWorkers / 32);
         }
         fence_barrier_init();
         sh.cand.a = cand_sm;
@@ -575,8 +776,11 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
         uint32_t pivot = g.entry;
         if (threadIdx.x == 0) sh.E[0] = pivot;
         __syncthreads();
-        if (RING) eval_list_ring<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc, *rr);
-        else eval_list<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc);
+        if (RING) {
+            if (threadIdx.x >= 32) eval_list_ring<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc, *rr);
+        } else {
+            eval_list<ELEM, F32>(cur, g, sh.E, 1, sh.D, sh.acc);
+        }
         __syncthreads();
         float dist_to_entry = sh.D[0];
         neval += 1;
@@ -588,8 +792,11 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sh.E[i] = __ldg(&lst[i]);
             __syncthreads();
-            if (RING) eval_list_ring<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc, *rr);
-            else eval_list<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc);
+            if (RING) {
+                if (threadIdx.x >= 32) eval_list_ring<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc, *rr);
+            } else {
+                eval_list<ELEM, F32>(cur, g, sh.E, len, sh.D, sh.acc);
+            }
             __syncthreads();
             neval += len;
             // every thread scans the same shared arrays: uniform result, no broadcast needed
@@ -603,7 +810,8 @@ k7_hnsw_search(GraphView g, const uint8_t *__restrict__ queries, uint32_t nq, ui
             pivot = newp;
         }
         // ---- search_layer(q, pivot, ef, 0)
-        search_layer_dev<ELEM, F32, RING>(g, cur, pivot, dist_to_entry, ef, 0, sh, vis, neval, rr);
+        if (RING) search_layer_ring<ELEM, F32>(g, cur, pivot, dist_to_entry, ef, sh, E2, D2, vis, neval, *rr);
+        else search_layer_dev<ELEM, F32, false>(g, cur, pivot, dist_to_entry, ef, 0, sh, vis, neval, nullptr);
 #ifdef GSB_K7_PROF
         const long long qt1 = clock64();
 #endif

@@ -73,6 +73,28 @@ def test_search_identical_to_oracle_on_same_graph(oracle, dt, S, M, ef_c, scale,
             assert got["rank"][i, :n].tolist() == want["rank"][i, :n].tolist()
 
 
+@pytest.mark.parametrize("dt,S", [(np.uint64, 2000), (np.float32, 1200), (np.uint16, 4096), (np.uint32, 1028)])
+def test_search_ring_path_identical_to_oracle(oracle, monkeypatch, dt, S):
+    """K7's TMA-ring variant (candidate rows + query pieces by bulk copy, control warp / worker warps,
+    speculative expansion of the predicted next candidate with roll-back): forced for every ef here
+    (by default it serves ef_search > 2046), tie-heavy data, and an ef larger than the index"""
+    monkeypatch.setenv("GSB_K7_RING", "1")
+    rng = np.random.default_rng(S)
+    sigs = tree_sigs(rng, 700, S, dt) if dt != np.uint16 else (tree_sigs(rng, 700, S, np.uint32) % 7).astype(np.uint16)
+    h, ids = build(oracle, sigs, 24, 100, 0.5)
+    idx = load(h, sigs, 24, 100)
+    queries = np.concatenate([sigs[::41], sigs[:3][:, ::-1].copy()])
+    for knbn, ef in [(10, 50), (50, 400), (5, 1), (20, 3000)]:
+        got, gc, ge = idx.search_raw(queries, knbn, ef)
+        want, wc, we = h.search(queries, knbn, ef, nthreads=4)
+        assert gc.tolist() == wc.tolist() and ge.tolist() == we.tolist()
+        for i in range(len(queries)):
+            n = gc[i]
+            assert got["d_id"][i, :n].tolist() == want["d_id"][i, :n].tolist()
+            assert got["distance"][i, :n].tobytes() == want["distance"][i, :n].tobytes()
+            assert got["rank"][i, :n].tolist() == want["rank"][i, :n].tolist()
+
+
 def test_search_recall_against_brute_force(oracle):
     rng = np.random.default_rng(4)
     S = 4096
