@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -168,6 +169,11 @@ struct gsb_sketcher {
     std::vector<cudaEvent_t> ev_h2d;       // one per H2D chunk of the current host call
     std::vector<uint32_t> h2d_end;         // chunk c holds the files [h2d_end[c-1], h2d_end[c])
     bool h2d_active = false;               // batch_dev must wait for the chunk events
+    // host call with a pinned output buffer: the signatures of a genome group start their way back
+    // as soon as the group is final (first pass), under the kernels of the later groups
+    uint8_t *early_out = nullptr;          // host signatures, or null
+    const uint8_t *early_src = nullptr;    // device signatures of the call
+    std::vector<cudaEvent_t> ev_grp;
     uint32_t file_base = 0;  // offset added to file indices in messages
     cudaStream_t gstream[2] = {nullptr, nullptr};  // group streams of the prob path
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -744,6 +750,18 @@ int run_prob(gsb_sketcher *h, const std::vector<uint32_t> &todo, const std::vect
                 else GSB_PROB_LAUNCH(SrcAA, uint64_t, false, false);
             }
 #undef GSB_PROB_LAUNCH
+            if (kp.pending && h->early_out) {
+                if (h->ev_grp.size() <= g) {
+                    cudaEvent_t e = nullptr;
+                    GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->ev_grp.push_back(e);
+                }
+                const size_t rowb = (size_t)h->sc.m * h->elem;
+                GSB_CUDA_TRY(cudaEventRecord(h->ev_grp[g], gs));
+                GSB_CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_grp[g], 0));
+                GSB_CUDA_TRY(cudaMemcpyAsync(h->early_out + (size_t)joff * rowb, h->early_src + (size_t)joff * rowb,
+                                             (size_t)nj * rowb, cudaMemcpyDeviceToHost, h->d2h_stream));
+            }
         }
         kp.pending = false;
         for (int i = 0; i < 2; i++) {
@@ -1153,17 +1171,44 @@ static int sketch_host_in(gsb_sketcher *h, const uint8_t *bytes, const uint64_t 
     }
     std::vector<uint64_t> rel(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
+    static const bool trace = getenv("GSB_E2E_TRACE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    h->early_out = nullptr;
+    if (!out_dev && h->p.algo == GSB_ALGO_PROB3A && !getenv("GSB_NO_EARLY_D2H")) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, sig_out) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+            h->early_out = (uint8_t *)sig_out;  // pinned: an asynchronous copy really is one
+            h->early_src = (const uint8_t *)h->d_sig.p;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    const uint64_t retries_before = h->retries;
     h->h2d_active = true;
     rc = sketch_batch_dev_locked(h, h->d_bytes.as<uint8_t>(), rel.data(), n, out_dev ? sig_out : h->d_sig.p,
                                  (out_dev && nb_bases_out) ? nb_bases_out : h->d_nb.as<uint64_t>(), (void *)st);
     h->h2d_active = false;
+    const auto tr1 = std::chrono::steady_clock::now();
     if (rc) {
         cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->d2h_stream);  // early copies into the caller's buffer must not outlive the call
+        h->early_out = nullptr;
         return rc;
     }
+    if (trace) {
+        cudaStreamSynchronize(h->copy_stream);
+        const auto tr2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "e2e trace: n=%u compute-done %.3f ms, copy stream idle at %.3f ms\n", n,
+                std::chrono::duration<double, std::milli>(tr1 - tr0).count(),
+                std::chrono::duration<double, std::milli>(tr2 - tr0).count());
+    }
     if (out_dev) return GSB_OK;  // batch_dev returned after synchronising `st`
-    // batch_dev returned after synchronising `st`: the results are complete
-    GSB_CUDA_TRY(cudaMemcpyAsync(sig_out, h->d_sig.p, (size_t)n * sig_row, cudaMemcpyDeviceToHost, h->d2h_stream));
+    // batch_dev returned after synchronising `st`: the results are complete.  Rows that went back
+    // early are final unless a file was re-run (bound retry / general path): then everything is copied again
+    const bool early_done = h->early_out != nullptr && h->retries == retries_before;
+    h->early_out = nullptr;
+    if (!early_done)
+        GSB_CUDA_TRY(cudaMemcpyAsync(sig_out, h->d_sig.p, (size_t)n * sig_row, cudaMemcpyDeviceToHost, h->d2h_stream));
     if (nb_bases_out)
         GSB_CUDA_TRY(cudaMemcpyAsync(nb_bases_out, h->d_nb.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
     GSB_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
