@@ -1158,6 +1158,13 @@ static int sketch_host_in(gsb_sketcher *h, const uint8_t *bytes, const uint64_t 
         GSB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->ev_h2d.push_back(e);
     }
+    static const bool trace = getenv("GSB_E2E_TRACE") != nullptr;
+    static cudaEvent_t tr_c0 = nullptr, tr_c1 = nullptr;
+    if (trace && !tr_c0) {
+        cudaEventCreate(&tr_c0);
+        cudaEventCreate(&tr_c1);
+    }
+    if (trace) cudaEventRecord(tr_c0, h->copy_stream);
     {
         uint32_t f0 = 0;
         for (size_t c = 0; c < h->h2d_end.size(); c++) {
@@ -1171,7 +1178,7 @@ static int sketch_host_in(gsb_sketcher *h, const uint8_t *bytes, const uint64_t 
     }
     std::vector<uint64_t> rel(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - lo;
-    static const bool trace = getenv("GSB_E2E_TRACE") != nullptr;
+    if (trace) cudaEventRecord(tr_c1, h->copy_stream);
     const auto tr0 = std::chrono::steady_clock::now();
     h->early_out = nullptr;
     if (!out_dev && h->p.algo == GSB_ALGO_PROB3A && !getenv("GSB_NO_EARLY_D2H")) {
@@ -1198,9 +1205,11 @@ static int sketch_host_in(gsb_sketcher *h, const uint8_t *bytes, const uint64_t 
     if (trace) {
         cudaStreamSynchronize(h->copy_stream);
         const auto tr2 = std::chrono::steady_clock::now();
-        fprintf(stderr, "e2e trace: n=%u compute-done %.3f ms, copy stream idle at %.3f ms\n", n,
+        float h2d_ms = 0;
+        cudaEventElapsedTime(&h2d_ms, tr_c0, tr_c1);
+        fprintf(stderr, "e2e trace: n=%u compute-done %.3f ms, copy stream idle at %.3f ms, H2D alone took %.3f ms\n", n,
                 std::chrono::duration<double, std::milli>(tr1 - tr0).count(),
-                std::chrono::duration<double, std::milli>(tr2 - tr0).count());
+                std::chrono::duration<double, std::milli>(tr2 - tr0).count(), h2d_ms);
     }
     if (out_dev) return GSB_OK;  // batch_dev returned after synchronising `st`
     // batch_dev returned after synchronising `st`: the results are complete.  Rows that went back
