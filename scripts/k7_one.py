@@ -1,4 +1,7 @@
-"""one K7 launch at BASELINE configs[2] (for ncu): EF env = ef_search"""
+"""one K7 launch at BASELINE configs[2]: EF env = ef_search.
+  ncu:           ncu --set full --clock-control none -k regex:k7_hnsw -c 1 -o out python scripts/k7_one.py
+  phase timing:  make -C gsearch_b200/csrc clean all EXTRA=-DGSB_K7_PROF ; python scripts/k7_one.py
+                 (clock64 per phase of the search loop, printed by a few CTAs; rebuild without EXTRA afterwards)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
