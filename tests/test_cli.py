@@ -120,6 +120,31 @@ def test_tohnsw_request_aa_optdens(tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("algo,json_name", [("hll", "HLL"), ("super2", "SUPER2"), ("revoptdens", "REVOPTDENS")])
+def test_tohnsw_request_other_algos_through_hnswio_files(tmp_path, monkeypatch, algo, json_name):
+    """the remaining --algo values end to end, with the database written in the hnswio-style layout
+    (GSB_DUMP_HNSWIO=1) and reloaded from it by `request`; one query is a FASTQ copy of a database genome"""
+    from gsearch_b200 import hnswio
+    db, qd, work = tmp_path / "db", tmp_path / "q", tmp_path / "work"
+    for d in (db, qd, work):
+        d.mkdir()
+    for i in range(16):
+        (db / f"g{i:03d}.fna").write_bytes(g.synth.dna_genome(100 + i, 50_000))
+    recs = g.synth.dna_genome(107, 50_000).split(b">")[1:]
+    fq = b"".join(b"@" + r.partition(b"\n")[0] + b"\n" + r.partition(b"\n")[2].replace(b"\n", b"") + b"\n+\n" +
+                  b"I" * len(r.partition(b"\n")[2].replace(b"\n", b"")) + b"\n" for r in recs)
+    (qd / "q.fna").write_bytes(fq)   # FASTQ content under a suffix the directory walk accepts (src/utils/files.rs:116-137)
+    monkeypatch.chdir(work)
+    monkeypatch.setenv("GSB_DUMP_HNSWIO", "1")
+    cli.main("tohnsw -d {} -k 21 -s 384 -n 12 --ef 48 --algo {}".format(db, algo).split())
+    assert hnswio.is_hnswio(str(work))
+    assert json.load(open(work / "parameters.json"))["sketch"]["algo"] == json_name
+    cli.main("request -b {} -r {} -n 4".format(work, qd).split())
+    txt = open(work / "gsearch.neighbors.txt").read()
+    assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(db / "g007.fna") in txt
+
+
+@pytest.mark.gpu
 def test_bindash_all_pairs(tmp_path, oracle):
     """`gsearch bindash` (src/bin/bindash.rs): all query x reference distances from OptDens / RevOptDens
     sketches; rows `Query<TAB>Reference<TAB>Distance` with 1 - (2J/(1+J))^(1/k), 0 for equal basenames"""
