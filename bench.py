@@ -622,7 +622,7 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
             uid_t.copy_(torch.frombuffer(bytearray(g.comm.unique_id()), dtype=torch.uint8))
         dist.broadcast(uid_t, 0)
         comm = g.comm.Comm(bytes(uid_t.cpu().numpy().tobytes()), world, rank, local)
-        idx.set_wave_max(min(512, 296 * world))
+        idx.set_wave_max(min(1024, 296 * world))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -770,7 +770,7 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
     head["build"] = {"genomes_per_s_inserted": n / t_build, "seconds": t_build, "kernel": "k8_hnsw_insert_select",
                      "ef_construction": a.ef, "datagen_seconds": t_gen,
                      "sharding": ("gsb_index_insert_batch_sharded: phase A of every wave split over the GPUs, "
-                                  "selections all-gathered, wave_max %d" % min(512, 296 * world)) if world > 1
+                                  "selections all-gathered, wave_max %d" % min(1024, 296 * world)) if world > 1
                      else "single GPU, wave_max 296"}
     if build_parity:
         head["build"]["multi_gpu_parity"] = build_parity

@@ -204,7 +204,7 @@ def dumpall(idx, dirpath, seqdict, p, nb_file, elapsed):
 
 
 WAVE_PER_GPU = 296   # one insertion wave = two points per SM of every GPU (capped by the library)
-WAVE_CAP = 512
+WAVE_CAP = 1024       # (every point of a wave meets the earlier ones by exact distance: O(W^2) per wave)
 
 
 def build_worker(rank, world, uid, files, p, pio, nbthreads, load_dir, out_dir, first_id, result_q):

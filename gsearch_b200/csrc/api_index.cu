@@ -197,8 +197,8 @@ extern "C" void gsb_index_destroy(gsb_index *idx) {
 extern "C" uint64_t gsb_index_nb_point(const gsb_index *idx) { return idx ? idx->n : 0; }
 
 extern "C" int gsb_index_set_wave_max(gsb_index *idx, uint32_t wave_max) {
-    if (!idx || wave_max < 1 || wave_max > (uint32_t)kMaxList) {
-        set_error("wave_max must be in 1..%d", kMaxList);
+    if (!idx || wave_max < 1 || wave_max > (uint32_t)kMaxWave) {
+        set_error("wave_max must be in 1..%d", kMaxWave);
         return GSB_ERR_INVALID_ARG;
     }
     idx->wave_max = wave_max;

@@ -34,7 +34,8 @@ namespace gsb {
 
 constexpr int kSearchThreads = 256;   // K7: 8 warps per CTA, three CTAs per SM (three independent search chains)
 constexpr int kInsertThreads = 256;   // K8: 8 warps per CTA, two CTAs per SM (128 registers per thread)
-constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255) and >= wave size
+constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255): list scratch of a CTA
+constexpr int kMaxWave = 4096;   // points of one insertion wave (wave mates are met kMaxList at a time)
 constexpr int kMaxLayers = 17;   // levels 0..16
 
 struct HItem {
@@ -957,10 +958,11 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
         const int top = (int)(level < lmax ? level : lmax);
         for (int l = top; l >= 0; l--) {
             search_layer_dev<ELEM, F32>(g, cur, ep, d_ep, wv.ef_c, (uint32_t)l, sh, vis, neval, nullptr);
-            // ---- earlier points of this wave, in order, as if search_layer had met them last
-            {
+            // ---- earlier points of this wave, in order, as if search_layer had met them last (a wave
+            // may be longer than the list scratch: kMaxList mates at a time, the heap sees them in order)
+            for (uint32_t base = 0; wv.first + base < np;) {
                 uint32_t tot = 0;
-                for (uint32_t base = 0; wv.first + base < np; base += blockDim.x) {
+                for (; wv.first + base < np && tot + blockDim.x <= (uint32_t)kMaxList; base += blockDim.x) {
                     const uint32_t m = wv.first + base + threadIdx.x;
                     const bool on = m < np && g.levels[m] >= (uint32_t)l;
                     const uint32_t bal = __ballot_sync(0xffffffffu, on);
@@ -985,12 +987,15 @@ k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_wor
                             if (sh.ret.n > wv.ef_c) (void)sh.ret.pop();
                         }
                     }
-                    // from_positive_binaryheap_to_negative_binary_heap: push in underlying-vec order
-                    sh.cand.n = 0;
-                    for (uint32_t i = 0; i < sh.ret.n; i++) sh.cand.push(-sh.ret.at(i).d, sh.ret.at(i).p);
                 }
                 __syncthreads();
             }
+            if (threadIdx.x == 0) {
+                // from_positive_binaryheap_to_negative_binary_heap: push in underlying-vec order
+                sh.cand.n = 0;
+                for (uint32_t i = 0; i < sh.ret.n; i++) sh.cand.push(-sh.ret.at(i).d, sh.ret.at(i).p);
+            }
+            __syncthreads();
             // ---- select_neighbours
             const uint32_t nb_asked = l == 0 ? 2 * g.M : g.M;
             const bool extend_asked = l == 0 && wv.extend != 0;

@@ -55,6 +55,17 @@ def test_insert_builds_the_oracle_graph(oracle, dt, S, gen, M, ef_c, wave, scale
     assert got["distance"].tobytes() == want["distance"].tobytes()
 
 
+def test_waves_longer_than_the_list_scratch(oracle):
+    """a wave may hold more points than a CTA's list scratch (512): the wave mates are met 512 at a time, in
+    order; wave = n / 4 while that is below wave_max, so 3 000 points reach waves of 700"""
+    rng = np.random.default_rng(21)
+    sigs = tree_sigs(rng, 3000, 128, np.uint32)
+    h, idx = both(oracle, sigs, 12, 48, 700, 0.5)
+    assert_same_graph(idx.export_graph(), h.export())
+    with pytest.raises(g.GsbError):
+        idx.set_wave_max(5000)
+
+
 def test_insert_in_several_calls_and_without_extension(oracle):
     rng = np.random.default_rng(11)
     sigs = tree_sigs(rng, 500, 400, np.uint64)
