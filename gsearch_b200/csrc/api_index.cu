@@ -425,9 +425,9 @@ static int launch_search(gsb_index *idx, const SearchBufs &sb, uint32_t nq, uint
     size_t smem;
     if (ring) {
         // dynamic bytes of one of three CTAs per SM: (228 KB / 3 - 1 KB reserved) - 19.6 KB static
-        constexpr size_t kBudget = 233472 / 3 - 1024 - 20096 - 128;
+        constexpr size_t kBudget = 233472 / 3 - 1024 - (20096 - (1024 - kCandSmemK7) * sizeof(HItem)) - 128;
         smem = row128;
-        bm_words = (smem + bm_bytes + 512 * sizeof(HItem) <= kBudget && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
+        bm_words = (smem + bm_bytes + 256 * sizeof(HItem) <= kBudget && !getenv("GSB_NO_BITMAP")) ? (uint32_t)(bm_bytes / 4) : 0u;
         smem += (size_t)bm_words * 4;
         ret_cs = (uint32_t)std::min<size_t>((size_t)ef + 2, (kBudget - smem) / sizeof(HItem));
         smem += (size_t)ret_cs * sizeof(HItem);

@@ -140,7 +140,10 @@ struct HeapT {
     }
 };
 constexpr uint32_t kCandSmem = 2048;  // entries of the candidate heap kept in shared memory (K8)
-constexpr uint32_t kCandSmemK7 = 1024;  // K7: three CTAs per SM, the row ring takes the room
+#ifndef GSB_CAND_K7
+#define GSB_CAND_K7 512
+#endif
+constexpr uint32_t kCandSmemK7 = GSB_CAND_K7;  // K7: three CTAs per SM, the row ring takes the room
 
 struct GraphView {
     const uint8_t *sigs;        // n x S x elem
@@ -310,7 +313,7 @@ __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView
 //   rows + query both by TMA, default L2 policy, 444 CTAs          3.8 TB/s   (64 MB of queries thrash L2)
 //   rows (evict-first) + query (evict-last) both by TMA, 444 CTAs  7.0 TB/s of rows
 // So ONE thread streams, per job, kRingChunk bytes of a row and the same piece of the query as two
-// bulk copies (cp.async.bulk + mbarrier: SASS UBLKCP) onto one transaction barrier; the 256 threads
+// bulk copies (cp.async.bulk + mbarrier: SASS UBLKCP) onto one transaction barrier; the worker threads
 // compare the two pieces out of shared memory.  No register loads, no LSU slots, and the L2 policies
 // keep the queries resident under the stream of rows.  full[s]: both copies landed; empty[s]: the
 // eight warps are done with the slot.
@@ -320,9 +323,20 @@ __device__ __forceinline__ void eval_list(const uint8_t *smem_q, const GraphView
 // lane files the results of expansion i into the heaps (a serial chain of dependent sift steps,
 // ~6 000 cycles), the workers already gather and stream the expansion the search will most likely
 // do next (search_layer_ring below): the heap work left the critical path.
-constexpr uint32_t kRingSlots = 3;
+// Ring geometry.  A bulk copy has a fixed cost of a few hundred cycles in the copy engine besides its
+// bytes (per job: 824 cycles for 2 x 7 KB, measured with clock64 -- the same for 3 or 10 slots, for one
+// or three CTAs per SM, for one or seven issuing threads), so the copies are made as large as the
+// shared memory of three CTAs per SM allows and the ring as shallow as a double buffer:
+//   3 slots x 7 KB   3 840 queries/s     2 slots x 10.5 KB   4 020     2 slots x 14 KB   4 370
+// (same box, ef_search 5000; the last one gives up the shared-memory visited bitmap for room).
+#ifndef GSB_RING_SLOTS
+#define GSB_RING_SLOTS 2
+#define GSB_RING_VEC 4
+#endif
+constexpr uint32_t kRingSlots = GSB_RING_SLOTS;
 constexpr uint32_t kRingWorkers = kSearchThreads - 32;   // 224
-constexpr uint32_t kRingChunk = kRingWorkers * 32;       // 7168 bytes: 2 x 16 bytes of the row per worker and job
+constexpr uint32_t kRingVec = GSB_RING_VEC;              // 16-byte vectors of the row per worker and job
+constexpr uint32_t kRingChunk = kRingWorkers * 16 * kRingVec;   // 14 336 bytes of a row per job
 constexpr uint32_t kRingBytes = kRingSlots * 2 * kRingChunk;
 struct RowRing {
     uint8_t *buf;             // kRingSlots x [row piece | query piece], 128-byte aligned
@@ -368,8 +382,9 @@ __device__ __noinline__ void eval_list_ring(const uint8_t *q, const GraphView &g
         mbar_wait(&rr.full[rr.slot], rr.par);  // (one polling lane per warp + __syncwarp: measured 14 % slower)
         const uint4 *s4 = reinterpret_cast<const uint4 *>(rr.buf + rr.slot * (2 * kRingChunk));
         const uint4 *sq = s4 + kRingChunk / 16;
-        if (t < nv) cnt += diff16<ELEM, F32>(sq[t], s4[t]);
-        if (t + kRingWorkers < nv) cnt += diff16<ELEM, F32>(sq[t + kRingWorkers], s4[t + kRingWorkers]);
+#pragma unroll
+        for (uint32_t u = 0; u < kRingVec; u++)
+            if (t + u * kRingWorkers < nv) cnt += diff16<ELEM, F32>(sq[t + u * kRingWorkers], s4[t + u * kRingWorkers]);
         if (++c == nch) {  // the row is complete (uniform)
             c = 0;
 #pragma unroll
