@@ -16,6 +16,9 @@
 // inner loop).  Heap order, visit order and tie behaviour reproduce Rust's std BinaryHeap exactly
 // (see oracle/hnsw.c), so that on the same graph the returned ids are identical to the CPU
 // restatement.
+// For large ef_search (the reference's 5000) K7 has a second layout, the TMA RING further down:
+// candidate rows and the matching query pieces arrive as bulk copies in shared memory, a control
+// warp runs the heaps while worker warps already stream the predicted next expansion.
 //
 // The graph is mutable and device resident: fixed-capacity adjacency (2M entries per point on
 // layer 0, M per upper layer, with the distances kept beside the indices because
