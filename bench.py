@@ -41,10 +41,6 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-# stdout carries ONE JSON line: NCCL's own messages (the "NCCL version ..." banner of NCCL_DEBUG=VERSION
-# on some boxes) go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
