@@ -169,7 +169,7 @@ extern "C" int gsb_index_create(const gsb_index_params *params, int device, gsb_
                        log((double)params->max_nb_connection);
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&idx->nsm, cudaDevAttrMultiProcessorCount, device);
-    idx->wave_max = (uint32_t)idx->nsm * 2;  // one wave = one point per resident insertion CTA
+    idx->wave_max = (uint32_t)idx->nsm * GSB_K8_PER_SM;  // one wave = one point per resident insertion CTA
     if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete idx;
@@ -604,7 +604,7 @@ int launch_wave(gsb_index *idx, uint32_t first, uint32_t W, cudaStream_t st, gsb
     const uint32_t world = comm ? (uint32_t)comm_size(comm) : 1u, rank = comm ? (uint32_t)comm_rank(comm) : 0u;
     const uint32_t per = (W + world - 1) / world;  // points of the wave per rank (the last slices may be short or empty)
     const uint32_t t_begin = std::min(W, rank * per), t_end = std::min(W, t_begin + per);
-    const uint32_t nctas = std::max<uint32_t>(1u, std::min<uint32_t>(t_end - t_begin, (uint32_t)idx->nsm * (staged ? 1u : 2u)));
+    const uint32_t nctas = std::max<uint32_t>(1u, std::min<uint32_t>(t_end - t_begin, (uint32_t)idx->nsm * (staged ? 1u : (uint32_t)GSB_K8_PER_SM)));
     int rc;
     if ((rc = ensure_workspace(idx, nctas, (uint64_t)first + W, ef_c))) return rc;
     WaveView wv;

@@ -36,7 +36,10 @@
 namespace gsb {
 
 constexpr int kSearchThreads = 256;   // K7: 8 warps per CTA, three CTAs per SM (three independent search chains)
-constexpr int kInsertThreads = 256;   // K8: 8 warps per CTA, two CTAs per SM (128 registers per thread)
+#ifndef GSB_K8_PER_SM
+#define GSB_K8_PER_SM 2
+#endif
+constexpr int kInsertThreads = 256;   // K8: 8 warps per CTA, GSB_K8_PER_SM CTAs per SM
 constexpr int kMaxList = 512;    // >= 2 * max_nb_connection (<= 255): list scratch of a CTA
 constexpr int kMaxWave = 4096;   // points of one insertion wave (wave mates are met kMaxList at a time)
 constexpr int kMaxLayers = 17;   // levels 0..16
@@ -898,7 +901,7 @@ __device__ __forceinline__ size_t sel_off(uint32_t M, uint32_t t, uint32_t l) {
 // Phase A.  One CTA per new point: greedy descent, search_layer(ef_c) per layer, earlier points
 // of the wave merged in, select_neighbours (Malkov heuristic, extension on layer 0), sort.
 template <int ELEM, bool F32>
-__global__ void __launch_bounds__(kInsertThreads, 2)
+__global__ void __launch_bounds__(kInsertThreads, GSB_K8_PER_SM)
 k8_hnsw_insert_select(GraphView g, WaveView wv, int ret_in_smem, uint32_t bm_words, int staged,
                       uint8_t *__restrict__ ws, WsLayout wl) {
     extern __shared__ __align__(128) uint8_t smem[];
