@@ -693,9 +693,19 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
             dist.all_gather_into_tensor(g_out, d_out)
 
     host_res = {}
+    # host side of the e2e call: queries and answers in pinned memory (the copies run at link speed)
+    from gsearch_b200.comm import PinnedBuffer
+    hq_c = np.ascontiguousarray(hq_loc)
+    pin_q = PinnedBuffer(max(hq_c.nbytes, 16))
+    pin_q.array[:hq_c.nbytes] = hq_c.view(np.uint8).reshape(-1)
+    pin_out = PinnedBuffer(max(nq_loc * a.knbn * item, 16))
+    pin_cnt = PinnedBuffer(max(nq_loc * 4, 16))
+    pin_nev = PinnedBuffer(max(nq_loc * 8, 16))
 
     def search_host(ef):
-        host_res["r"] = idx.search_raw(hq_loc, a.knbn, ef)
+        idx.search_pointers(pin_q.ptr, nq_loc, a.knbn, ef, pin_out.ptr, pin_cnt.ptr, pin_nev.ptr)
+        host_res["r"] = (pin_out.array[:nq_loc * a.knbn * item].view(g.index.NEIGHBOUR_DTYPE).reshape(nq_loc, a.knbn),
+                         pin_cnt.array[:nq_loc * 4].view(np.uint32), pin_nev.array[:nq_loc * 8].view(np.uint64))
         if world > 1:  # the answers go back to the device for the gather
             d_out[:nq_loc].copy_(torch.from_numpy(host_res["r"][0].view(np.uint8).reshape(nq_loc, -1)), non_blocking=True)
             dist.all_gather_into_tensor(g_out, d_out)
@@ -732,7 +742,7 @@ def own_request(a, torch, dist, g, rank, world, local, dev):
                          "mean_evaluations_per_query": float(tot_ev.item()) / nq,
                          "avg_launch_ms": 1e3 * dt / calls},
         }
-        recs[ef]["_host"] = (out, cnt)
+        recs[ef]["_host"] = (out.copy(), cnt.copy())  # (views of the pinned buffers: the next call overwrites them)
     clk = clocks.stop() if clocks else None
     # multi-GPU parity: the gathered answers of every query equal a single-GPU search of that query
     parity = None

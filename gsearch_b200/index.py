@@ -114,6 +114,13 @@ class Hnsw:
                                                      p(neval)))
         return out, counts, neval
 
+    def search_pointers(self, queries_ptr, nq, knbn, ef, out_ptr, counts_ptr, nb_eval_ptr=0):
+        """gsb_index_search_batch with raw HOST pointers (e.g. pinned buffers: the copies then run at link
+        speed): queries nq x S, out nq x knbn gsb_neighbour (24 B each), counts nq x u32, nb_eval nq x u64"""
+        _lib.check(_lib.lib().gsb_index_search_batch(self._h, C.c_void_p(queries_ptr), nq, knbn, ef,
+                                                     C.c_void_p(out_ptr), C.c_void_p(counts_ptr),
+                                                     C.c_void_p(nb_eval_ptr) if nb_eval_ptr else C.c_void_p(0)))
+
     def search_device(self, d_queries_ptr, nq, knbn, ef, d_out_ptr, d_counts_ptr, d_nb_eval_ptr=0):
         """gsb_index_search_batch_dev: queries and results in device memory (raw pointers); out is
         nq x knbn gsb_neighbour (24 B each), counts nq x u32, nb_eval nq x u64 (optional)"""
