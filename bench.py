@@ -537,8 +537,8 @@ def own_sketch(a, torch, dist, g, rank, world, local, dev):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {
-            "kernel": ("prob sketch pipeline (k2p_partition dominant, k2p_count, K1 pack, K3 replay; concurrent "
-                       "streams)" if algo == 0 else "k2_optdens"),
+            "kernel": ("prob sketch pipeline (k2p_count 45 % and k2p_partition 36 % of the kernel time, K1 parse + "
+                       "pack 17 %; concurrent streams)" if algo == 0 else "k2_optdens"),
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None,
             "traffic": (traffic["dram_bytes_per_genome"] * B if traffic else None),
