@@ -95,6 +95,30 @@ def test_search_ring_path_identical_to_oracle(oracle, monkeypatch, dt, S):
             assert got["rank"][i, :n].tolist() == want["rank"][i, :n].tolist()
 
 
+def test_search_pointers_and_device_forms_agree(oracle):
+    """the raw host-pointer form (pinned buffers in bench.py) and the device-pointer form return what
+    search_raw returns"""
+    from gsearch_b200.comm import DeviceBuffer, PinnedBuffer
+    rng = np.random.default_rng(3)
+    sigs = tree_sigs(rng, 400, 512, np.uint64)
+    h, ids = build(oracle, sigs, 12, 48)
+    idx = load(h, sigs, 12, 48)
+    q = np.ascontiguousarray(sigs[::29])
+    nq, knbn = len(q), 7
+    want, wc, we = idx.search_raw(q, knbn, 100)
+    pq, po, pc, pe = PinnedBuffer(q.nbytes), PinnedBuffer(nq * knbn * 24), PinnedBuffer(nq * 4), PinnedBuffer(nq * 8)
+    pq.array[:q.nbytes] = q.view(np.uint8).reshape(-1)
+    idx.search_pointers(pq.ptr, nq, knbn, 100, po.ptr, pc.ptr, pe.ptr)
+    assert po.array[:nq * knbn * 24].tobytes() == want.tobytes()
+    assert pc.array[:nq * 4].view(np.uint32).tolist() == wc.tolist()
+    assert pe.array[:nq * 8].view(np.uint64).tolist() == we.tolist()
+    dq, do, dc, de = DeviceBuffer(q.nbytes), DeviceBuffer(nq * knbn * 24), DeviceBuffer(nq * 4), DeviceBuffer(nq * 8)
+    dq.upload(q)
+    idx.search_device(dq.ptr, nq, knbn, 100, do.ptr, dc.ptr, de.ptr)
+    assert do.download(np.uint8, nq * knbn * 24).tobytes() == want.tobytes()
+    assert dc.download(np.uint32, nq).tolist() == wc.tolist()
+
+
 def test_search_recall_against_brute_force(oracle):
     rng = np.random.default_rng(4)
     S = 4096
