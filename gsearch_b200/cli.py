@@ -10,16 +10,18 @@ JSON / text; sketching, HNSW construction and search all run in libgsearch_b200.
   gsearch add -b DBDIR -n NEWDIR
   gsearch request -b DBDIR -r QUERYDIR -n NBANSWERS
   gsearch bindash -q QUERY_LIST -r REFERENCE_LIST [-k 16] [-s 2048] [-d 0|1] [-o OUT]   (src/bin/bindash.rs)
+  gsearch reformat KMER MODEL gsearch.neighbors.txt OUT.tsv                              (src/bin/reformat.rs)
 
 Outputs, as in the reference: tohnsw writes hnswdump.hnsw.graph, hnswdump.hnsw.data, seqdict.json,
 parameters.json and processing_state.json into the CURRENT directory (src/dna/dnasketch.rs:152-156),
-add writes them back into DBDIR, request writes gsearch.neighbors.txt into the current directory
-(src/dna/dnarequest.rs:85-87)."""
+add writes them back into DBDIR, request writes gsearch.neighbors.txt (src/dna/dnarequest.rs:85-87) and, in
+sequence mode, gsearch.matches (src/matcher.rs:233-277) into the current directory."""
 import argparse
 import bz2
 import gzip
 import json
 import lzma
+import math
 import os
 import sys
 import time
@@ -326,6 +328,75 @@ def request_worker(rank, world, files, p, pio, nbthreads, dbdir, knbn, result_q)
                   out["d_id"].copy(), out["distance"].copy(), cnt))
 
 
+def rust_exp(x, digits):
+    """Rust's {:.<digits>E}: mantissa with `digits` decimals, 'E', exponent without sign padding"""
+    mant, exp = f"{x:.{digits}E}".split("E")
+    return f"{mant}E{int(exp)}"
+
+
+def format_matches(queries, threshold=ANSWER_THRESHOLD):
+    """Matcher::analyze (src/matcher.rs:233-277), the `gsearch.matches` file of sequence mode: per request
+    genome the (at most five) database genomes of smallest merit, merit = product of the distances below
+    the threshold of the sequences matched in that genome (MatchList::compute_merit_wl, :86-94), as f32.
+    `queries` = [(request path, [(target path, distance), ...]), ...]; the reference walks a HashMap
+    (arbitrary order), here the request genomes come in the order of their first appearance."""
+    per_request = {}
+    for qpath, nbrs in queries:
+        targets = per_request.setdefault(qpath, {})
+        for tpath, d in nbrs:
+            merit = targets.get(tpath, 1.0)
+            if np.float32(d) < np.float32(threshold):
+                merit *= float(np.float32(d))
+            targets[tpath] = merit
+    out = []
+    for qpath, targets in per_request.items():
+        ranked = sorted(((t, float(np.float32(m))) for t, m in targets.items()), key=lambda tm: tm[1])
+        out.append(f"\n\n request genome : {qpath}")
+        for t, m in ranked[:5]:
+            out.append(f"\n\t matched genome {t}  merit : {rust_exp(m, 3)}")
+    return "".join(out)
+
+
+def rust_f64(x):
+    """Rust's `{}` for an f64: shortest digits that round-trip, never an exponent"""
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    return np.format_float_positional(x, trim="-")
+
+
+def cmd_reformat(a):
+    """src/bin/reformat.rs: gsearch.neighbors.txt -> a table with an ANI column.  Rows are the lines that
+    start with `query_id:`; columns 1, 3, 5, 7 of the tab-split line (file names reduced to their last
+    component; column 7 is whatever the answer line holds there, kept byte for byte like the reference
+    does); ANI model 1 (Poisson): (1 + ln(2J / (1 + J)) / k) * 100, model 2 (binomial):
+    (2J / (1 + J))^(1/k) * 100 with J = 1 - distance; sorted by query name, then distance."""
+    rows = []
+    with open(a.input_file) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if not line.startswith("query_id:"):
+                continue
+            parts = line.split("\t")
+            d = float(parts[3])
+            j = 1.0 - d
+            frac = j * 2.0 / (j + 1.0)
+            if a.model == 1:
+                ani = rust_f64((1.0 + (math.log(frac) if frac > 0 else float("-inf")) / a.kmer) * 100.0)
+            elif a.model == 2:
+                ani = rust_f64(math.pow(frac, 1.0 / a.kmer) * 100.0)
+            else:
+                ani = "Invalid Model"
+            rows.append((os.path.basename(parts[1]), d, f"{os.path.basename(parts[1])}\t{rust_f64(d)}\t"
+                         f"{os.path.basename(parts[5])}\t{parts[7]}\t{ani}"))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    with open(a.output_file, "w") as f:
+        f.write("Query_Name\tDistance\tNeighbor_Fasta_name\tNeighbor_Seq_Len\tANI\n")
+        for r in rows:
+            f.write(r[2] + "\n")
+
+
 def cmd_request(a):
     p = reload_parameters(a.hnsw)
     seqdict = reload_seqdict(a.hnsw)
@@ -352,12 +423,17 @@ def cmd_request(a):
             if pr.exitcode != 0:
                 raise SystemExit(f"a GPU worker failed (exit code {pr.exitcode})")
     by_rank = {r: (items, ids, dd, cnt) for r, items, ids, dd, cnt in parts}
+    matches = []
     with open("gsearch.neighbors.txt", "w") as f:
         for j in range(len(files)):   # query order = file order, whatever the number of GPUs
             items, ids, dd, cnt = by_rank[j % world]
             t = j // world
             nbrs = [(int(ids[t, i]), float(dd[t, i])) for i in range(cnt[t])]
             f.write(format_answers(j, items[t], nbrs, seqdict))
+            matches.append((items[t][0], [(seqdict[d_id][0], d) for d_id, d in nbrs]))
+    if not p["block"]:   # sequence mode: seq_matcher.analyze() (src/bin/gsearch.rs:926-929)
+        with open("gsearch.matches", "w") as f:
+            f.write(format_matches(matches))
     print(f"request: {len(files)} queries answered in gsearch.neighbors.txt")
 
 
@@ -423,6 +499,12 @@ def build_parser():
     r.add_argument("-n", "--nbanswers", type=int, required=True)
     r.add_argument("-r", "--query", required=True)
     r.set_defaults(fn=cmd_request)
+    rf = sub.add_parser("reformat", help="gsearch.neighbors.txt -> table with ANI (src/bin/reformat.rs)")
+    rf.add_argument("kmer", type=int)
+    rf.add_argument("model", type=int)
+    rf.add_argument("input_file")
+    rf.add_argument("output_file")
+    rf.set_defaults(fn=cmd_reformat)
     b = sub.add_parser("bindash", help="all-pairs OptDens / RevOptDens distances (src/bin/bindash.rs)")
     b.add_argument("-q", "--query_list", required=True)
     b.add_argument("-r", "--reference_list", required=True)

@@ -66,6 +66,36 @@ def test_parser_mirrors_reference_flags():
     assert (a.hnsw, a.new) == ("dbdir", "newdir")
 
 
+def test_matches_file_and_reformat(tmp_path):
+    """gsearch.matches (Matcher::analyze, src/matcher.rs:233-277) and `reformat` (src/bin/reformat.rs):
+    text formats, merit = product of the distances below the threshold, ANI models, the column-7 quirk"""
+    import math
+    seqdict = [("/db/x.fna", "x", 1000), ("/db/y.fna", "y", 2000), ("/db/z.fna", "z", 3000)]
+    q = ("/q/a.fna", "a", 49950)
+    nbrs = [(0, 0.0), (1, 0.9453125), (2, 0.995)]
+    txt = cli.format_matches([(q[0], [(seqdict[i][0], d) for i, d in nbrs]), ("/q/b.fna", [("/db/y.fna", 0.5)])])
+    assert txt == ("\n\n request genome : /q/a.fna\n\t matched genome /db/x.fna  merit : 0.000E0"
+                   "\n\t matched genome /db/y.fna  merit : 9.453E-1\n\t matched genome /db/z.fna  merit : 1.000E0"
+                   "\n\n request genome : /q/b.fna\n\t matched genome /db/y.fna  merit : 5.000E-1")
+    many = [(f"/db/g{i}.fna", 0.1 + 0.1 * i) for i in range(8)]
+    assert cli.format_matches([("/q/c.fna", many)]).count("matched genome") == 5       # at most five per request
+    # reformat reads what format_answers wrote
+    (tmp_path / "n.txt").write_text(cli.format_answers(0, q, nbrs, seqdict) + cli.format_answers(1, ("/q/0.fna", "0", 5), [(1, 0.25)], seqdict))
+    for model in (1, 2, 3):
+        cli.main(f"reformat 16 {model} {tmp_path / 'n.txt'} {tmp_path / 'o.tsv'}".split())
+        rows = (tmp_path / "o.tsv").read_text().splitlines()
+        assert rows[0] == "Query_Name\tDistance\tNeighbor_Fasta_name\tNeighbor_Seq_Len\tANI"
+        assert [r.split("\t")[0] for r in rows[1:]] == ["0.fna", "a.fna", "a.fna"]       # sorted by query, then distance
+        name, d, nb, col7, ani = rows[3].split("\t")
+        assert (name, d, nb, col7) == ("a.fna", "0.945312", "y.fna", " answer_seq_len:")  # (0.995 is above the threshold)
+        j = 1.0 - 0.945312
+        frac = j * 2.0 / (j + 1.0)
+        want = {1: (1.0 + math.log(frac) / 16) * 100.0, 2: math.pow(frac, 1.0 / 16) * 100.0}.get(model)
+        assert ani == ("Invalid Model" if want is None else cli.rust_f64(want))
+        assert rows[2].split("\t")[1] == "0" and rows[2].split("\t")[4] == ("100" if model in (1, 2) else "Invalid Model")
+    assert cli.rust_f64(0.00005) == "0.00005" and cli.rust_f64(float("nan")) == "NaN" and cli.rust_f64(1e21) == "1000000000000000000000"
+
+
 @pytest.mark.gpu
 def test_tohnsw_request_add_end_to_end(tmp_path, monkeypatch):
     db, new, qd, work = tmp_path / "db", tmp_path / "new", tmp_path / "q", tmp_path / "work"
@@ -91,6 +121,8 @@ def test_tohnsw_request_add_end_to_end(tmp_path, monkeypatch):
     txt = open(work / "gsearch.neighbors.txt").read()
     assert "distance:\t0.00000E0\tanswer_fasta_path\t{}".format(db / "g005.fna") in txt
     assert str(new / "g025.fa") not in txt
+    mtxt = open(work / "gsearch.matches").read()
+    assert "\n\n request genome : {}\n\t matched genome {}  merit : 0.000E0".format(qd / "q0.fna", db / "g005.fna") in mtxt
     cli.main("add -b {} -n {}".format(work, new).split())
     assert len(cli.reload_seqdict(work)) == 28
     assert json.load(open(work / "processing_state.json"))["nb_seq"] == 28
