@@ -83,8 +83,9 @@ def dump(directory, basename, image, sigs, max_nb_connection, ef):
 def load(directory, basename="hnswdump"):
     """-> dict(max_nb_connection, ef, dtype, sigs, ids, levels, ranks, nbr_offsets, nbr_index, nbr_dist,
     entry_point); points are numbered in file order (layer by layer, by rank)"""
-    g = open(os.path.join(directory, basename + ".hnsw.graph"), "rb").read()
-    d = open(os.path.join(directory, basename + ".hnsw.data"), "rb").read()
+    # (memory-mapped: the data file is the whole signature matrix)
+    g = np.memmap(os.path.join(directory, basename + ".hnsw.graph"), dtype=np.uint8, mode="r")
+    d = np.memmap(os.path.join(directory, basename + ".hnsw.data"), dtype=np.uint8, mode="r")
     magic, mode, M, nb_layer, ef, n, S = struct.unpack_from("<IBBBQQQ", g, 0)
     if magic != MAGIC_DESCR or nb_layer != NB_LAYER:
         raise ValueError("not an hnswio graph file")
@@ -92,7 +93,7 @@ def load(directory, basename="hnswdump"):
     names = []
     for _ in range(2):
         (ln,) = struct.unpack_from("<Q", g, pos)
-        names.append(g[pos + 8:pos + 8 + ln].decode())
+        names.append(bytes(g[pos + 8:pos + 8 + ln]).decode())
         pos += 8 + ln
     dtype = {v: k for k, v in T_NAMES.items()}[names[1]]
     dmagic, dS = struct.unpack_from("<IQ", d, 0)
